@@ -1,0 +1,105 @@
+"""In-tree build of the native pieces (no cmake, no JIT cache):
+
+* ``lib/libqsv_b200.so``            -- CUDA kernels + C ABI (include/qsv_b200.h), nvcc, sm_100a only
+* ``lightning_gpu_qubit_ops*.so``   -- pybind11 module mirroring bindings/Bindings.cpp of the
+                                        reference, g++ only, links libqsv_b200.so
+
+Objects are rebuilt only when a source or header is newer; translation units compile in parallel.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import sysconfig
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+SRC = os.path.join(PKG, "src")
+LIBDIR = os.path.join(PKG, "lib")
+OBJDIR = os.path.join(PKG, "build")
+LIB = os.path.join(LIBDIR, "libqsv_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd: list[str]) -> None:
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    out = (r.stdout + r.stderr).strip()
+    if out:
+        print(out, file=sys.stderr)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(ROOT, "include", "qsv_b200.h"))
+    sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    jobs = []
+    objs = []
+    for s in sources:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJDIR, s[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + headers):
+            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append(cmd)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(_run, jobs))
+    if jobs or not os.path.exists(LIB):
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lnccl"])
+    return LIB
+
+
+def pybind_module_path() -> str:
+    return os.path.join(PKG, "lightning_gpu_qubit_ops" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind(force: bool = False) -> str | None:
+    """pybind11 module with the reference's class names, calling only the C ABI."""
+    src = os.path.join(SRC, "bindings", "Bindings.cpp")
+    if not os.path.exists(src):
+        return None
+    import pybind11
+
+    out = pybind_module_path()
+    deps = [src, os.path.join(ROOT, "include", "qsv_b200.h")]
+    for d, _, files in os.walk(SRC):
+        deps += [os.path.join(d, f) for f in files if f.endswith((".hpp", ".h"))]
+    if force or _newer(out, deps) or _newer(out, [LIB]):
+        cmd = [
+            "g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-fvisibility=hidden",
+            "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(SRC, "simulator"),
+            "-I", os.path.join(SRC, "algorithms"), "-I", os.path.join(SRC, "util"),
+            src, "-o", out, "-L", LIBDIR, "-lqsv_b200", "-Wl,-rpath,$ORIGIN/lib",
+        ]
+        _run(cmd)
+    return out
+
+
+def build_all(force: bool = False) -> None:
+    build_lib(force)
+    build_pybind(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print(LIB)

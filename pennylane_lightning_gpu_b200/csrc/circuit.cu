@@ -1,0 +1,360 @@
+// Host-side orchestration above the kernels: op dispatch, observables, adjoint Jacobian.
+//
+// Mirrors (behaviour, not code)
+//   applyOperation                     simulator/StateVectorCudaManaged.hpp:198-247
+//   ObservableGPU<T>::applyInPlace     algorithms/ObservablesGPU.hpp:56-587
+//   AdjointJacobianGPU::adjointJacobian algorithms/AdjointDiffGPU.hpp:499-596, updateJacobian :132-162
+// with these structural differences (all on the hot path, none visible in results):
+//   * no mu vector: <H_lambda| G |lambda> is one fused read of both vectors (launch_bra_op_ket);
+//   * U^dagger is applied to lambda and to all bras by ONE launch (gridDim.y = 1 + n_obs);
+//   * Jacobian entries accumulate in a device buffer and are read back once, not once per
+//     parameter (AdjointDiffGPU.hpp:153-155 syncs every parameter);
+//   * a Hamiltonian of Pauli words is applied by one gather kernel, not by per-term
+//     copy + apply + axpy (ObservablesGPU.hpp:346-362).
+#include <algorithm>
+
+#include "qsv_internal.h"
+
+namespace qsv {
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t bytes) { QSV_CUDA(cudaMalloc(&p, bytes)); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+LoweredGate lower_op(const State &sv, const Op &op, bool extra_adjoint) {
+    const bool adj = op.inverse != extra_adjoint;
+    if (find_gate(op.name) != nullptr) return lower_named(sv.n, op.name, op.wires, op.params, adj);
+    if (op.matrix.empty()) fail("Currently unsupported gate: " + op.name);
+    const size_t dim = 1ull << op.wires.size();
+    QSV_CHECK(op.matrix.size() == dim * dim, "matrix of gate " + op.name + " does not match its wires");
+    return lower_matrix(sv.n, op.matrix.data(), {}, op.wires, adj);
+}
+
+// Pauli word view of an observable: Named X/Y/Z/Identity or a tensor product of those on
+// distinct wires
+bool as_pauli_word(const Obs &o, int n, uint64_t &x, uint64_t &z, int &ny) {
+    if (o.kind == Obs::NAMED) {
+        if (o.wires.size() != 1) return false;
+        const int w = o.wires[0];
+        QSV_CHECK(w >= 0 && w < n, "observable wire out of range");
+        const uint64_t b = 1ull << (n - 1 - w);
+        if ((x | z) & b) return false;  // same wire twice: not a plain word
+        if (o.name == "PauliX") {
+            x |= b;
+        } else if (o.name == "PauliY") {
+            x |= b;
+            z |= b;
+            ny += 1;
+        } else if (o.name == "PauliZ") {
+            z |= b;
+        } else if (o.name != "Identity") {
+            return false;
+        }
+        return true;
+    }
+    if (o.kind == Obs::TENSOR) {
+        for (const auto &c : o.children)
+            if (!as_pauli_word(*c, n, x, z, ny)) return false;
+        return true;
+    }
+    return false;
+}
+
+bool hamiltonian_of_pauli_words(const Obs &o, int n, std::vector<uint64_t> &xs, std::vector<uint64_t> &zs,
+                                std::vector<cplx> &cf) {
+    if (o.kind != Obs::HAMILTONIAN) return false;
+    for (size_t t = 0; t < o.children.size(); ++t) {
+        uint64_t x = 0, z = 0;
+        int ny = 0;
+        if (!as_pauli_word(*o.children[t], n, x, z, ny)) return false;
+        cplx ph(1.0, 0.0);
+        for (int i = 0; i < (ny & 3); ++i) ph *= cplx(0.0, 1.0);
+        xs.push_back(x);
+        zs.push_back(z);
+        cf.push_back(ph * o.coeffs[t]);
+    }
+    return true;
+}
+
+struct CsrDev {
+    DevBuf indptr, indices, values;
+    CsrDev(State &sv, const Obs &o)
+        : indptr(o.indptr.size() * 8), indices(std::max<size_t>(o.indices.size(), 1) * 8),
+          values(std::max<size_t>(o.values.size(), 1) * 16) {
+        QSV_CUDA(cudaMemcpyAsync(indptr.p, o.indptr.data(), o.indptr.size() * 8, cudaMemcpyHostToDevice, sv.stream));
+        QSV_CUDA(cudaMemcpyAsync(indices.p, o.indices.data(), o.indices.size() * 8, cudaMemcpyHostToDevice, sv.stream));
+        QSV_CUDA(cudaMemcpyAsync(values.p, o.values.data(), o.values.size() * 16, cudaMemcpyHostToDevice, sv.stream));
+    }
+};
+
+void check_sparse_shape(const State &sv, const Obs &o) {
+    QSV_CHECK(o.indptr.size() == sv.length() + 1, "sparse Hamiltonian dimension does not match the state vector");
+}
+
+// replace the contents of sv by those of tmp (same size)
+void adopt(State &sv, DevBuf &tmp) {
+    if (sv.owns) {
+        std::swap(sv.data, tmp.p);  // the old buffer is released by tmp's destructor
+    } else {
+        QSV_CUDA(cudaMemcpyAsync(sv.data, tmp.p, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    }
+}
+
+double obs_expval_generic(State &sv, const Obs &o) {
+    // tmp = O sv ; <sv|tmp>
+    DevBuf tmp(sv.bytes());
+    State t;
+    t.n = sv.n;
+    t.dtype = sv.dtype;
+    t.device = sv.device;
+    t.stream = sv.stream;
+    t.data = tmp.p;
+    t.owns = false;
+    QSV_CUDA(cudaMemcpyAsync(t.data, sv.data, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+    apply_observable(t, o);
+    double *red = sv.reduction_buffer(2);
+    reduction_zero(sv, red, 2);
+    LoweredGate id;
+    launch_bra_op_ket(sv, sv.data, t.data, id, red, 0);
+    double out[2];
+    reduction_read(sv, red, out, 2);
+    return out[0];
+}
+
+}  // namespace
+
+void apply_op(State &sv, const Op &op, bool extra_adjoint) {
+    if (op.name == "Identity") return;
+    launch_gate(sv, lower_op(sv, op, extra_adjoint));
+}
+
+void apply_observable(State &sv, const Obs &o) {
+    sv.use();
+    switch (o.kind) {
+    case Obs::NAMED: {
+        Op op;
+        op.name = o.name;
+        op.wires = o.wires;
+        op.params = o.params;
+        op.matrix = o.matrix;
+        apply_op(sv, op, false);
+        return;
+    }
+    case Obs::HERMITIAN: {
+        const size_t dim = 1ull << o.wires.size();
+        QSV_CHECK(o.matrix.size() == dim * dim, "Hermitian matrix does not match its wires");
+        launch_gate(sv, lower_matrix(sv.n, o.matrix.data(), {}, o.wires, false));
+        return;
+    }
+    case Obs::TENSOR:
+        for (const auto &c : o.children) apply_observable(sv, *c);
+        return;
+    case Obs::HAMILTONIAN: {
+        std::vector<uint64_t> xs, zs;
+        std::vector<cplx> cf;
+        if (hamiltonian_of_pauli_words(o, sv.n, xs, zs, cf)) {
+            DevBuf tmp(sv.bytes());
+            launch_pauli_sum_apply(sv, sv.data, tmp.p, (int)xs.size(), xs.data(), zs.data(), cf.data());
+            adopt(sv, tmp);
+            return;
+        }
+        // generic terms: acc = sum_t c_t O_t psi
+        DevBuf acc(sv.bytes()), tmp(sv.bytes());
+        QSV_CUDA(cudaMemsetAsync(acc.p, 0, sv.bytes(), sv.stream));
+        State t;
+        t.n = sv.n;
+        t.dtype = sv.dtype;
+        t.device = sv.device;
+        t.stream = sv.stream;
+        t.owns = false;
+        for (size_t i = 0; i < o.children.size(); ++i) {
+            t.data = tmp.p;
+            QSV_CUDA(cudaMemcpyAsync(t.data, sv.data, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+            apply_observable(t, *o.children[i]);
+            launch_axpy(sv, cplx(o.coeffs[i], 0.0), t.data, acc.p);
+        }
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));
+        adopt(sv, acc);
+        return;
+    }
+    case Obs::SPARSE: {
+        check_sparse_shape(sv, o);
+        CsrDev csr(sv, o);
+        DevBuf y(sv.bytes());
+        launch_csr(sv, sv.data, y.p, csr.indptr.p, csr.indices.p, csr.values.p, (int64_t)sv.length(),
+                   (int64_t)o.values.size(), 8, nullptr, 0);
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));
+        adopt(sv, y);
+        return;
+    }
+    }
+}
+
+double observable_expval(State &sv, const Obs &o) {
+    sv.use();
+    uint64_t x = 0, z = 0;
+    int ny = 0;
+    if (as_pauli_word(o, sv.n, x, z, ny)) {
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        launch_bra_pauli_ket(sv, sv.data, sv.data, x, z, ny, red, 0);
+        double out[2];
+        reduction_read(sv, red, out, 2);
+        return out[0];
+    }
+    switch (o.kind) {
+    case Obs::NAMED: {
+        // any named gate used as an observable: its full matrix on its wires
+        std::vector<cplx> m = o.matrix;
+        if (find_gate(o.name) != nullptr) m = named_gate_matrix(o.name, o.params, (int)o.wires.size());
+        QSV_CHECK(!m.empty(), "Currently unsupported observable: " + o.name);
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        launch_bra_op_ket(sv, sv.data, sv.data, lower_matrix(sv.n, m.data(), {}, o.wires, false), red, 0);
+        double out[2];
+        reduction_read(sv, red, out, 2);
+        return out[0];
+    }
+    case Obs::HERMITIAN: {
+        const size_t dim = 1ull << o.wires.size();
+        QSV_CHECK(o.matrix.size() == dim * dim, "Hermitian matrix does not match its wires");
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        launch_bra_op_ket(sv, sv.data, sv.data, lower_matrix(sv.n, o.matrix.data(), {}, o.wires, false), red, 0);
+        double out[2];
+        reduction_read(sv, red, out, 2);
+        return out[0];
+    }
+    case Obs::HAMILTONIAN: {
+        std::vector<uint64_t> xs, zs;
+        std::vector<cplx> cf;
+        if (hamiltonian_of_pauli_words(o, sv.n, xs, zs, cf)) {
+            const size_t T = xs.size();
+            double *red = sv.reduction_buffer(2 * T);
+            reduction_zero(sv, red, 2 * T);
+            for (size_t t = 0; t < T; ++t)
+                launch_bra_pauli_ket(sv, sv.data, sv.data, xs[t], zs[t], 0, red, (int)t);
+            std::vector<double> out(2 * T);
+            reduction_read(sv, red, out.data(), 2 * T);
+            double tot = 0;
+            for (size_t t = 0; t < T; ++t) tot += (cf[t] * cplx(out[2 * t], out[2 * t + 1])).real();
+            return tot;
+        }
+        double tot = 0;
+        for (size_t i = 0; i < o.children.size(); ++i) tot += o.coeffs[i] * observable_expval(sv, *o.children[i]);
+        return tot;
+    }
+    case Obs::SPARSE: {
+        check_sparse_shape(sv, o);
+        CsrDev csr(sv, o);
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        launch_csr(sv, sv.data, nullptr, csr.indptr.p, csr.indices.p, csr.values.p, (int64_t)sv.length(),
+                   (int64_t)o.values.size(), 8, red, 0);
+        double out[2];
+        reduction_read(sv, red, out, 2);
+        return out[0];
+    }
+    case Obs::TENSOR:
+        return obs_expval_generic(sv, o);
+    }
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjoint Jacobian
+// ------------------------------------------------------------------------------------------------
+void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
+                      const std::vector<int64_t> &trainable, bool apply_operations, double *jac) {
+    sv.use();
+    QSV_CHECK(!trainable.empty(), "No trainable parameters provided.");
+    const size_t n_obs = obs.size();
+    const size_t n_tp = trainable.size();
+    for (size_t i = 0; i < n_obs * n_tp; ++i) jac[i] = 0.0;
+    if (n_obs == 0) return;
+    for (const auto &op : ops.ops)
+        QSV_CHECK(op.params.size() <= 1, "The operation is not supported using the adjoint differentiation method");
+
+    // lambda and the bras H_lambda[i] = O_i lambda
+    const size_t bytes = sv.bytes();
+    std::vector<std::unique_ptr<State>> vecs;  // [0] = lambda, [1..] = bras
+    for (size_t i = 0; i < 1 + n_obs; ++i) {
+        auto s = std::make_unique<State>();
+        s->n = sv.n;
+        s->dtype = sv.dtype;
+        s->device = sv.device;
+        s->stream = sv.stream;
+        QSV_CUDA(cudaMalloc(&s->data, bytes));
+        s->owns = true;
+        vecs.push_back(std::move(s));
+    }
+    State &lambda = *vecs[0];
+    QSV_CUDA(cudaMemcpyAsync(lambda.data, sv.data, bytes, cudaMemcpyDeviceToDevice, sv.stream));
+    if (apply_operations)
+        for (const auto &op : ops.ops) apply_op(lambda, op, false);
+    for (size_t i = 0; i < n_obs; ++i) {
+        QSV_CUDA(cudaMemcpyAsync(vecs[1 + i]->data, lambda.data, bytes, cudaMemcpyDeviceToDevice, sv.stream));
+        apply_observable(*vecs[1 + i], *obs[i]);
+    }
+    // device table of vector pointers for the batched U^dagger launch
+    std::vector<void *> h_table(1 + n_obs);
+    for (size_t i = 0; i < 1 + n_obs; ++i) h_table[i] = vecs[i]->data;
+    DevBuf d_table(h_table.size() * sizeof(void *));
+    QSV_CUDA(cudaMemcpyAsync(d_table.p, h_table.data(), h_table.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                             sv.stream));
+
+    // one complex slot per (trainable parameter, observable) for op part, one more for the identity part
+    const size_t n_slots = 2 * n_obs * n_tp;
+    double *red = sv.reduction_buffer(2 * n_slots);
+    reduction_zero(sv, red, 2 * n_slots);
+    std::vector<double> factor(n_tp, 0.0), extra(n_tp, 0.0);
+
+    size_t n_par_ops = 0;
+    for (const auto &op : ops.ops) n_par_ops += op.params.empty() ? 0 : 1;
+    int64_t tp_pos = (int64_t)n_tp - 1;
+    int64_t cur = (int64_t)n_par_ops - 1;
+    for (int64_t idx = (int64_t)ops.ops.size() - 1; idx >= 0; --idx) {
+        const Op &op = ops.ops[idx];
+        if (op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState") continue;
+        if (tp_pos < 0) break;
+        if (!op.params.empty()) {
+            if (cur == trainable[tp_pos]) {
+                LoweredGenerator g = lower_generator(sv.n, op.name, op.wires);
+                factor[tp_pos] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
+                extra[tp_pos] = g.extra_identity;
+                for (size_t i = 0; i < n_obs; ++i) {
+                    launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, g.op, red, (int)((tp_pos * n_obs + i) * 2));
+                    if (g.extra_identity != 0.0) {
+                        LoweredGate id;
+                        launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red,
+                                          (int)((tp_pos * n_obs + i) * 2 + 1));
+                    }
+                }
+                --tp_pos;
+            }
+            --cur;
+        }
+        // lambda <- U^dagger lambda and H_lambda[i] <- U^dagger H_lambda[i], one launch
+        if (op.name != "Identity")
+            launch_gate_multi(sv, lower_op(sv, op, true), (void *const *)d_table.p, (int)(1 + n_obs));
+    }
+    std::vector<double> h(2 * n_slots);
+    reduction_read(sv, red, h.data(), 2 * n_slots);
+    for (size_t p = 0; p < n_tp; ++p)
+        for (size_t i = 0; i < n_obs; ++i) {
+            const size_t s = (p * n_obs + i) * 2;
+            const double im = h[2 * s + 1] + extra[p] * h[2 * (s + 1) + 1];
+            jac[i * n_tp + p] = factor[p] * im;
+        }
+}
+
+}  // namespace qsv

@@ -1,0 +1,185 @@
+// Internal declarations shared by the translation units of libqsv_b200.so.
+// Nothing in here is part of the C ABI (see include/qsv_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qsv_b200.h"
+
+namespace qsv {
+
+using cplx = std::complex<double>;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const std::string &msg);
+void set_last_error(const std::string &msg);
+
+#define QSV_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            ::qsv::fail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " in " #expr " (" + \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ")");                          \
+    } while (0)
+
+#define QSV_CHECK(cond, msg)                                                                       \
+    do {                                                                                           \
+        if (!(cond)) ::qsv::fail(msg);                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Lowered gate: what the kernels consume.  Bits are amplitude-index bit positions.
+// ------------------------------------------------------------------------------------------------
+struct LoweredGate {
+    enum Kind { NOP, DENSE, DIAG, PARITY } kind = NOP;
+    // DENSE : 2^k x 2^k row-major matrix acting on the 2^k amplitudes base + offs[j];
+    //         `holes` are all index bits fixed by the group (targets and controls), ascending.
+    // DIAG  : amp *= tab[t], t = bits of the index at tgt_bits (tgt_bits[0] = MSB of t)
+    // PARITY: amp *= tab[popc(index & zmask) & 1]
+    // All kinds: only indices with every bit of ctrl_mask set are touched.
+    int k = 0;                     // log2(#amplitudes per group) for DENSE, #table bits for DIAG
+    std::vector<int> holes;        // DENSE
+    std::vector<uint64_t> offs;    // DENSE, 2^k entries
+    std::vector<int> tgt_bits;     // DIAG (MSB first), DENSE (for the tile executor; MSB first or empty)
+    uint64_t ctrl_mask = 0;
+    uint64_t zmask = 0;            // PARITY
+    std::vector<cplx> mat;         // DENSE: 4^k, DIAG: 2^k, PARITY: 2
+    int n_ctrl() const { return __builtin_popcountll(ctrl_mask); }
+};
+
+// Named-gate table (gate definitions follow simulator/cuGates_host.hpp and the control/target split
+// of StateVectorCudaManaged.hpp:321-560; see gates.cu).
+struct GateInfo {
+    const char *name;
+    int n_wires;   // 0 = variadic (MultiRZ)
+    int n_params;
+};
+const GateInfo *find_gate(const std::string &name);
+// full matrix (controls included) of a named gate in wire order; used by observables and tests
+std::vector<cplx> named_gate_matrix(const std::string &name, const std::vector<double> &params,
+                                    int n_wires);
+LoweredGate lower_named(int n_qubits, const std::string &name, const std::vector<int> &wires,
+                        const std::vector<double> &params, bool adjoint);
+LoweredGate lower_matrix(int n_qubits, const cplx *matrix, const std::vector<int> &ctrl_wires,
+                         const std::vector<int> &tgt_wires, bool adjoint);
+
+// Generator of a parametric gate as an operator (GateGenerators.hpp); `scale` per
+// AdjointDiffGPU.hpp:96-114.  `extra_identity` is the coefficient d of an additional d * Identity
+// term (SingleExcitationMinus/Plus, DoubleExcitationMinus/Plus) so that the remaining part stays
+// sparse:  G = extra_identity * I + op.
+struct LoweredGenerator {
+    LoweredGate op;             // non-unitary operator in LoweredGate form (projectors = ctrl_mask)
+    double extra_identity = 0;  // G = op + extra_identity * 1
+    double scale = -0.5;
+};
+LoweredGenerator lower_generator(int n_qubits, const std::string &name, const std::vector<int> &wires);
+
+// ------------------------------------------------------------------------------------------------
+// State
+// ------------------------------------------------------------------------------------------------
+struct DistCtx;  // dist.cu
+
+struct State {
+    int n = 0;
+    int dtype = QSV_C128;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    void *data = nullptr;
+    bool owns = false;
+    // reduction scratch (device) + pinned host mirror, lazily allocated
+    double *red_dev = nullptr;
+    double *red_host = nullptr;
+    size_t red_cap = 0;  // doubles
+    // generic device scratch (matrices of big gates, pointer tables, ...)
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+    int64_t stat_launches = 0, stat_sweeps = 0;
+    DistCtx *dist = nullptr;
+
+    size_t amp_bytes() const { return dtype == QSV_C128 ? 16 : 8; }
+    uint64_t length() const { return 1ull << n; }
+    size_t bytes() const { return length() * amp_bytes(); }
+    void use() const { QSV_CUDA(cudaSetDevice(device)); }
+    double *reduction_buffer(size_t n_doubles);
+    void *scratch_buffer(size_t bytes);
+    ~State();
+};
+
+struct Op {
+    std::string name;
+    std::vector<int> wires;
+    std::vector<double> params;
+    bool inverse = false;
+    std::vector<cplx> matrix;
+};
+struct Ops {
+    std::vector<Op> ops;
+};
+
+struct Obs {
+    enum Kind { NAMED, HERMITIAN, TENSOR, HAMILTONIAN, SPARSE } kind = NAMED;
+    std::string name;
+    std::vector<int> wires;
+    std::vector<double> params;
+    std::vector<cplx> matrix;
+    std::vector<double> coeffs;
+    std::vector<std::shared_ptr<Obs>> children;
+    // SPARSE
+    std::vector<int64_t> indptr, indices;
+    std::vector<cplx> values;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Kernel launchers (apply_kernels.cu / measure_kernels.cu / tile_kernels.cu).
+// `vecs` = device pointers of the vectors the op is applied to (all same n/dtype, same stream).
+// ------------------------------------------------------------------------------------------------
+void launch_gate(State &sv, const LoweredGate &g);
+void launch_gate_multi(State &sv, const LoweredGate &g, void *const *vecs, int n_vecs);
+
+void launch_fill_basis(State &sv, uint64_t index);
+void launch_scatter(State &sv, const int64_t *dev_idx, const void *dev_vals, size_t count);
+void launch_axpy(State &sv, cplx alpha, const void *x, void *y);
+
+// <bra| op |ket> for a LoweredGate used as an operator (DENSE / DIAG / PARITY / NOP = identity);
+// results (re, im) are accumulated as doubles into out_dev[2*slot..] asynchronously.
+void launch_bra_op_ket(State &sv, const void *bra, const void *ket, const LoweredGate &op,
+                       double *out_dev, int slot);
+// <bra| P |ket> for a Pauli word given by masks; result *(i^ny) applied on device
+void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t xmask, uint64_t zmask,
+                          int ny, double *out_dev, int slot);
+// out[i] = sum_t coeff_t (P_t in)[i]   (out-of-place, in != out)
+void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
+                            const uint64_t *zmasks, const cplx *coeffs_with_phase);
+void launch_probs(State &sv, const std::vector<int> &bits_lsb_first, double *out_host);
+void launch_sample(State &sv, const double *uniforms, int64_t shots, uint64_t *out_host);
+// CSR: y = H x (y may be null) and/or accumulate <x|Hx> into out_dev[2*slot..]
+void launch_csr(State &sv, const void *x, void *y, const void *dev_indptr, const void *dev_indices,
+                const void *dev_values, int64_t n_rows, int64_t nnz, int index_bytes, double *out_dev,
+                int slot);
+// zero `count` doubles of the reduction buffer / read them back (one sync)
+void reduction_zero(State &sv, double *dev, size_t count);
+void reduction_read(State &sv, const double *dev, double *host, size_t count);
+
+// circuits
+void apply_op(State &sv, const Op &op, bool extra_adjoint);
+void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
+void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
+double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>
+void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
+                      const std::vector<int64_t> &trainable, bool apply_operations, double *jac);
+
+// dist.cu
+void dist_free(State &sv);
+
+}  // namespace qsv

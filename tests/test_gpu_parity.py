@@ -1,0 +1,536 @@
+"""Parity of the CUDA path (through the C ABI) against the NumPy oracle and the reference's golden
+vectors.  Tolerances are north_star's: 1e-10 for complex128, 1e-5 for complex64.
+
+Runs on the B200 box only (``-m gpu``); nothing here reads /root/reference.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import c_arr, obs_from_json, random_state
+from oracle import np_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.complex128): 1e-10, np.dtype(np.complex64): 1e-5}
+DTYPES = [np.complex128, np.complex64]
+
+
+@pytest.fixture(scope="module")
+def q():
+    import pennylane_lightning_gpu_b200 as q
+
+    assert q.device_count() >= 1
+    assert q.device_arch(0)[0] == 10, "these kernels are built for sm_100a"
+    return q
+
+
+def gpu_state(q, psi, dtype):
+    n = int(math.log2(psi.size))
+    sv = q.StateVector(n, dtype)
+    sv.h2d(psi.astype(dtype))
+    return sv
+
+
+def assert_close(a, b, dtype, scale=1.0, what=""):
+    tol = TOL[np.dtype(dtype)] * scale
+    err = np.max(np.abs(np.asarray(a) - np.asarray(b)))
+    assert err <= tol, f"{what}: max abs err {err:.3e} > {tol:.1e}"
+
+
+PARAM_GATES = {name: ar for name, ar in orc.GATE_ARITY.items()}
+
+
+def _rand_wires(rng, n, k):
+    return [int(w) for w in rng.choice(n, size=k, replace=False)]
+
+
+# ---------------------------------------------------------------------------------------------
+# gates
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [4, 7, 12])
+def test_every_named_gate_vs_oracle(q, n, dtype):
+    rng = np.random.default_rng(100 + n)
+    psi = random_state(n, 7 + n)
+    for name, (nw, npar) in orc.GATE_ARITY.items():
+        widths = [nw] if nw is not None else [1, 2, 3, min(5, n)]
+        for k in widths:
+            if k > n:
+                continue
+            for rep in range(3):
+                wires = _rand_wires(rng, n, k)
+                if rep == 0:  # make sure the lowest and highest index bits are exercised
+                    wires[0] = n - 1
+                    if k > 1:
+                        wires[-1] = 0 if 0 not in wires[:-1] else wires[-1]
+                    if len(set(wires)) != k:
+                        wires = _rand_wires(rng, n, k)
+                params = [float(x) for x in rng.uniform(-math.pi, math.pi, npar)]
+                for adj in (False, True):
+                    sv = gpu_state(q, psi, dtype)
+                    sv.apply(name, wires, params, adj)
+                    want = orc.apply_op(psi, name, wires, params, adj)
+                    assert_close(sv.d2h(), want, dtype, what=f"{name}{wires} adj={adj}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gate_golden_vectors(q, kats, dtype):
+    """The reference's own in/out state pairs (tests/test_apply.py, src/tests/*_Param/_NonParam.cpp)."""
+    for case in kats["gates_py"] + kats["gates_cpp"]:
+        psi = c_arr(case["input"])
+        if psi.size < 2:
+            continue
+        sv = gpu_state(q, psi, dtype)
+        sv.apply(case["gate"], case["wires"], case["params"], case.get("adjoint", False))
+        tol = max(case.get("atol", 0.0), TOL[np.dtype(dtype)])
+        assert np.allclose(sv.d2h(), c_arr(case["expected"]), atol=tol, rtol=case.get("rtol", 0.0)), case.get("cite")
+
+
+def _haar(rng, dim):
+    z = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+    qm, r = np.linalg.qr(z)
+    return qm * (np.diag(r) / np.abs(np.diag(r)))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_matrix_gates_with_controls(q, k, dtype):
+    n = 9
+    rng = np.random.default_rng(200 + k)
+    psi = random_state(n, 3)
+    for n_ctrl in (0, 1, 2):
+        for rep in range(3):
+            wires = _rand_wires(rng, n, k + n_ctrl)
+            if rep == 0:
+                wires = list(range(n - k - n_ctrl, n))[::-1]  # low index bits, reversed order
+            ctrls, tgts = wires[:n_ctrl], wires[n_ctrl:]
+            u = _haar(rng, 1 << k)
+            for adj in (False, True):
+                sv = gpu_state(q, psi, dtype)
+                sv.apply_matrix(u, tgts, ctrls, adj)
+                full = orc._controlled(u.conj().T if adj else u, n_ctrl)
+                want = orc.apply_matrix(psi, full, ctrls + tgts)
+                assert_close(sv.d2h(), want, dtype, what=f"k={k} ctrls={ctrls} tgts={tgts} adj={adj}")
+    # diagonal matrices take the phase-table path
+    d = np.diag(np.exp(1j * rng.uniform(0, 2 * math.pi, 1 << min(k, 4))))
+    tg = _rand_wires(rng, n, min(k, 4))
+    sv = gpu_state(q, psi, dtype)
+    sv.apply_matrix(d, tg)
+    assert_close(sv.d2h(), orc.apply_matrix(psi, d, tg), dtype, what="diag matrix")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_unknown_gate_and_matrix_fallback(q, dtype):
+    sv = q.StateVector(3, dtype)
+    with pytest.raises(q.QsvError, match="Currently unsupported gate: Foo"):
+        sv.apply("Foo", [0])
+    u = _haar(np.random.default_rng(0), 4)
+    psi = random_state(3, 1)
+    sv.h2d(psi.astype(dtype))
+    sv.apply("QubitUnitary", [2, 0], matrix=u)
+    assert_close(sv.d2h(), orc.apply_matrix(psi, u, [2, 0]), dtype)
+    with pytest.raises(q.QsvError):
+        sv.apply("RX", [7], [0.1])
+    with pytest.raises(q.QsvError):
+        sv.apply("CNOT", [1, 1])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_init_and_copies(q, dtype):
+    n = 5
+    sv = q.StateVector(n, dtype)
+    assert np.array_equal(sv.d2h(), orc.basis_state(n, 0, dtype))
+    for idx in (1, 17, 31):
+        sv.set_basis_state(idx)
+        assert np.array_equal(sv.d2h(), orc.basis_state(n, idx, dtype))
+    rng = np.random.default_rng(5)
+    idx = rng.choice(1 << n, size=7, replace=False)
+    vals = (rng.normal(size=7) + 1j * rng.normal(size=7)).astype(dtype)
+    sv.set_state_vector(idx, vals)
+    assert np.array_equal(sv.d2h(), orc.set_state_vector(n, idx, vals, dtype))
+    other = q.StateVector(n, dtype)
+    other.copy_from(sv)
+    assert np.array_equal(other.d2h(), sv.d2h())
+    with pytest.raises(q.QsvError):
+        sv.set_basis_state(1 << n)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_random_circuit_unfused_and_fused(q, dtype):
+    n = 13
+    rng = np.random.default_rng(2024)
+    names = ["RX", "RY", "RZ", "CNOT", "CZ", "Hadamard", "PhaseShift", "IsingXX", "IsingZZ", "CRY", "SWAP",
+             "Toffoli", "SingleExcitation", "T", "PauliY", "MultiRZ", "CRot", "ControlledPhaseShift", "CSWAP",
+             "DoubleExcitationPlus", "Rot", "QubitUnitary1", "QubitUnitary2", "QubitUnitary3"]
+    ops = []
+    for _ in range(160):
+        name = names[rng.integers(len(names))]
+        if name.startswith("QubitUnitary"):
+            k = int(name[-1])
+            ops.append({"name": "QubitUnitary", "wires": _rand_wires(rng, n, k), "params": [],
+                        "matrix": _haar(rng, 1 << k), "adjoint": bool(rng.integers(2))})
+            continue
+        nw, npar = orc.GATE_ARITY[name]
+        nw = nw if nw is not None else int(rng.integers(1, 5))
+        ops.append({"name": name, "wires": _rand_wires(rng, n, nw),
+                    "params": [float(x) for x in rng.uniform(-3, 3, npar)], "adjoint": bool(rng.integers(2))})
+    psi = random_state(n, 9)
+    want = orc.apply_ops(psi, ops)
+    rec = q.Ops(ops)
+    assert len(rec) == len(ops)
+    for fuse in (False, True):
+        sv = gpu_state(q, psi, dtype)
+        sv.apply_ops(rec, fuse=fuse)
+        assert_close(sv.d2h(), want, dtype, scale=10, what=f"fuse={fuse}")
+        launches, sweeps = sv.last_apply_stats()
+        assert launches >= 1 and sweeps >= 1
+        if not fuse:
+            assert sweeps == len(ops)
+
+
+# ---------------------------------------------------------------------------------------------
+# measurements
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_measurement_golden_vectors(q, kats, dtype):
+    tol = max(1e-6, TOL[np.dtype(dtype)])
+    k = kats["expval_matrix"]
+    sv = gpu_state(q, c_arr(k["state"]), dtype)
+    r = sv.expval_matrix(c_arr(k["matrix"]).reshape(8, 8), k["wires"])
+    assert abs(r.real - k["expected"][0]) < tol * 10 and abs(r.imag - k["expected"][1]) < tol * 10
+    k = kats["expval_csr"]
+    sv = gpu_state(q, c_arr(k["state"]), dtype)
+    assert abs(sv.expval_csr(k["indptr"], k["indices"], c_arr(k["values"])) - k["expected"]) < tol * 10
+    k = kats["pauli_words"]
+    sv = gpu_state(q, c_arr(k["state"]), dtype)
+    for case in k["cases"]:
+        got = sv.expval_pauli_words(case["words"], case["tgts"], case["coeffs"])
+        assert abs(got - case["expected"]) < max(tol, case.get("atol", 0.0)), case
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [3, 10, 14])
+def test_expvals_vs_oracle(q, n, dtype):
+    rng = np.random.default_rng(300 + n)
+    psi = random_state(n, 21)
+    sv = gpu_state(q, psi, dtype)
+    for name in ("PauliX", "PauliY", "PauliZ", "Hadamard", "Identity"):
+        for w in (0, n // 2, n - 1):
+            got = sv.expval_named(name, [w])
+            want = np.vdot(psi, orc.apply_op(psi, name, [w]))
+            assert_close(got, want, dtype, what=f"<{name}({w})>")
+    for k in (1, 2, 3, 4, 5):
+        if k > n:
+            continue
+        wires = _rand_wires(rng, n, k)
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        got = sv.expval_matrix(a, wires)  # deliberately non-Hermitian: the reference returns a complex
+        assert_close(got, orc.expval_matrix(psi, a, wires), dtype, scale=1 << k, what=f"dense k={k}")
+    words, wires, coeffs = [], [], []
+    for _ in range(12):
+        k = int(rng.integers(1, min(n, 5) + 1))
+        words.append("".join(rng.choice(list("XYZI"), size=k)))
+        wires.append(_rand_wires(rng, n, k))
+        coeffs.append(float(rng.normal()))
+    words.append("Z")
+    wires.append([n - 1])
+    coeffs.append(0.5)
+    words.append("XY"[: min(2, n)])
+    wires.append([n - 1, 0][: min(2, n)])
+    coeffs.append(-1.5)
+    tot, terms = sv.expval_pauli_words(words, wires, coeffs, return_terms=True)
+    state_cast = psi.astype(dtype)
+    assert_close(tot, orc.expval_pauli_words(state_cast, words, wires, coeffs), dtype, scale=20)
+    for t, (w, ws) in enumerate(zip(words, wires)):
+        want = np.vdot(psi, orc.pauli_word_matrix_free(psi, w, ws)).real
+        assert_close(terms[t], want, dtype, what=f"word {w}{ws}")
+    # inner product and norm
+    phi = random_state(n, 22)
+    sv2 = gpu_state(q, phi, dtype)
+    assert_close(sv.inner_product(sv2), np.vdot(psi, phi), dtype)
+    assert_close(sv.inner_product(sv), 1.0, dtype)
+
+
+def _random_csr(rng, n, per_row):
+    import scipy.sparse as sp
+
+    dim = 1 << n
+    rows = np.repeat(np.arange(dim), per_row)
+    cols = rng.integers(0, dim, size=rows.size)
+    vals = rng.normal(size=rows.size) + 1j * rng.normal(size=rows.size)
+    m = sp.csr_matrix((vals, (rows, cols)), shape=(dim, dim))
+    m = (m + m.getH()).tocsr()
+    m.sort_indices()
+    return m
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("per_row", [1, 3, 20])
+def test_csr_expval_and_apply(q, per_row, dtype):
+    n = 9
+    rng = np.random.default_rng(per_row)
+    m = _random_csr(rng, n, per_row)
+    psi = random_state(n, 4)
+    sv = gpu_state(q, psi, dtype)
+    want = orc.expval_csr(psi, m.indptr, m.indices, m.data)
+    assert_close(sv.expval_csr(m.indptr, m.indices, m.data), want, dtype, scale=100)
+    obs = q.Observable.sparse(m.indptr, m.indices, m.data)
+    assert_close(sv.expval(obs), want, dtype, scale=100)
+    sv.apply_observable(obs)
+    assert_close(sv.d2h(), m @ psi, dtype, scale=100)
+    # empty rows
+    import scipy.sparse as sp
+
+    e = sp.csr_matrix(([2.0 + 0j], ([5], [5])), shape=(1 << n, 1 << n))
+    sv = gpu_state(q, psi, dtype)
+    assert_close(sv.expval_csr(e.indptr, e.indices, e.data), 2 * abs(psi[5]) ** 2, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_probs(q, kats, dtype):
+    n = 13
+    psi = random_state(n, 31)
+    sv = gpu_state(q, psi, dtype)
+    tol_scale = 1
+    for wires in ([0], [n - 1], [3, 7], [0, 1, 2], [2, 5, 11, 12], list(range(n)), list(range(1, n)),
+                  [12, 0, 6], list(range(12))):
+        got = sv.probs(wires)
+        assert_close(got, orc.probs_custatevec_order(psi.astype(dtype), wires), dtype, scale=tol_scale,
+                     what=f"probs{wires}")
+        assert abs(got.sum() - 1.0) < 1e-5
+    k = kats["probs"]
+    st = orc.apply_ops(orc.basis_state(k["n"]), k["ops"])
+    sv = gpu_state(q, st, dtype)
+    for wires, expected in k["cases"]:
+        got = sv.probs(wires[::-1])  # PennyLane order = reversed custatevec order
+        assert np.allclose(got, expected, atol=max(k["atol"], 1e-5))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sampling_matches_inverse_cdf_definition(q, dtype):
+    n = 12
+    psi = random_state(n, 41).astype(dtype)
+    sv = gpu_state(q, psi, dtype)
+    shots = 5000
+    u = np.random.default_rng(1234).random(shots)
+    got = sv.sample(u)
+    assert got.shape == (shots, n) and got.dtype == np.uint64
+    want = orc.sample(psi, shots, seed=1234)
+    # identical except where u falls within FP64 rounding of a CDF edge (different summation order)
+    cdf = np.cumsum(np.abs(psi.astype(np.complex128)) ** 2)
+    near_edge = np.min(np.abs(cdf[None, :] - (u * cdf[-1])[:, None]), axis=1) < 1e-12
+    same = np.all(got == want, axis=1)
+    assert np.all(same | near_edge)
+    assert same.mean() > 0.999
+    # basis state: every shot returns that basis state
+    sv.set_basis_state(0b101101110001)
+    got = sv.sample(u[:50])
+    assert np.all(got == np.array([int(b) for b in "101101110001"], dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# observables and generators
+# ---------------------------------------------------------------------------------------------
+def _obs_zoo(rng, n):
+    h2 = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    h2 = h2 + h2.conj().T
+    h1 = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    h1 = h1 + h1.conj().T
+    zoo = [
+        ("Named", "PauliZ", [0]),
+        ("Named", "PauliX", [n - 1]),
+        ("Named", "PauliY", [1]),
+        ("Named", "Hadamard", [2]),
+        ("Hermitian", h1, [n - 2]),
+        ("Hermitian", h2, [n - 1, 0]),
+        ("TensorProd", [("Named", "PauliX", [0]), ("Named", "PauliY", [2]), ("Named", "PauliZ", [n - 1])]),
+        ("TensorProd", [("Named", "PauliZ", [1]), ("Hermitian", h1, [3])]),
+        ("Hamiltonian", [0.3, -1.1, 0.7],
+         [("Named", "PauliZ", [0]), ("TensorProd", [("Named", "PauliX", [1]), ("Named", "PauliX", [2])]),
+          ("TensorProd", [("Named", "PauliY", [0]), ("Named", "PauliZ", [n - 1])])]),
+        ("Hamiltonian", [0.9, 0.4], [("Hermitian", h2, [1, 2]), ("Named", "Hadamard", [0])]),
+    ]
+    return zoo
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_observables_apply_and_expval(q, dtype):
+    n = 6
+    rng = np.random.default_rng(77)
+    psi = random_state(n, 78)
+    for o in _obs_zoo(rng, n):
+        obs = q.Observable.from_tuple(o)
+        sv = gpu_state(q, psi, dtype)
+        assert_close(sv.expval(obs), orc.expval_obs(psi, o), dtype, scale=20, what=f"expval {o[0]}")
+        assert_close(sv.d2h(), psi, dtype, what="expval must not modify the state")
+        sv.apply_observable(obs)
+        assert_close(sv.d2h(), orc.apply_observable(psi, o), dtype, scale=20, what=f"apply {o[0]}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_generators_vs_oracle(q, dtype):
+    n = 6
+    rng = np.random.default_rng(88)
+    psi = random_state(n, 89)
+    for name, (nw, npar) in orc.GATE_ARITY.items():
+        if npar != 1:
+            continue
+        nw = nw if nw is not None else 3
+        wires = _rand_wires(rng, n, nw)
+        g, scale = orc.generator(name, nw)
+        sv = gpu_state(q, psi, dtype)
+        got_scale = sv.apply_generator(name, wires)
+        assert got_scale == scale
+        assert_close(sv.d2h(), orc.apply_matrix(psi, g, wires), dtype, what=f"generator {name}{wires}")
+
+
+# ---------------------------------------------------------------------------------------------
+# adjoint Jacobian
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_adjoint_golden_vectors(q, kats, dtype):
+    tol = 1e-5 if dtype == np.complex128 else 2e-4
+    for case in kats["adjoint"]:
+        ops = case["ops"]
+        obs = [obs_from_json(o) for o in case["obs"]]
+        n = case["n"]
+        init = orc.basis_state(n) if case["init"] == "zero" else c_arr(case["init"])
+        sv = gpu_state(q, init, dtype)
+        jac = sv.adjoint_jacobian(q.Ops(ops), [q.Observable.from_tuple(o) for o in obs], case["trainable"],
+                                  apply_operations=True)
+        want = np.asarray(case["expected"], dtype=float).reshape(jac.shape)
+        assert np.allclose(jac, want, atol=max(tol, case.get("atol", 0.0))), case.get("cite")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_adjoint_all_parametric_gates_vs_oracle(q, dtype):
+    n = 6
+    rng = np.random.default_rng(555)
+    ops = []
+    for name, (nw, npar) in orc.GATE_ARITY.items():
+        nw = nw if nw is not None else 3
+        if npar == 1:
+            ops.append({"name": name, "wires": _rand_wires(rng, n, nw), "params": [float(rng.uniform(-2, 2))],
+                        "adjoint": bool(rng.integers(2))})
+        elif npar == 0 and name != "Identity":
+            ops.append({"name": name, "wires": _rand_wires(rng, n, nw), "params": [], "adjoint": False})
+    rng.shuffle(ops)
+    ops = [{"name": "Hadamard", "wires": [w], "params": []} for w in range(n)] + list(ops)
+    n_par = sum(1 for o in ops if o["params"])
+    obs = _obs_zoo(rng, n)
+    psi0 = orc.basis_state(n)
+    final = orc.apply_ops(psi0, ops)
+    gobs = [q.Observable.from_tuple(o) for o in obs]
+    rec = q.Ops(ops)
+    for trainable in (list(range(n_par)), [0, 3, n_par - 1], [n_par // 2]):
+        want = orc.adjoint_jacobian(final, ops, obs, trainable)
+        sv = gpu_state(q, final, dtype)
+        jac = sv.adjoint_jacobian(rec, gobs, trainable)
+        assert_close(jac, want, dtype, scale=50, what=f"trainable={trainable}")
+        # apply_operations = True starts from the initial state
+        sv0 = gpu_state(q, psi0, dtype)
+        jac0 = sv0.adjoint_jacobian(rec, gobs, trainable, apply_operations=True)
+        assert_close(jac0, want, dtype, scale=50)
+        assert_close(sv0.d2h(), psi0, dtype, what="adjoint must not modify the input state")
+    sv = gpu_state(q, final, dtype)
+    with pytest.raises(q.QsvError, match="No trainable parameters provided"):
+        sv.adjoint_jacobian(rec, gobs, [])
+    bad = q.Ops([{"name": "Rot", "wires": [0], "params": [0.1, 0.2, 0.3]}])
+    with pytest.raises(q.QsvError, match="not supported using the adjoint"):
+        sv.adjoint_jacobian(bad, gobs, [0])
+
+
+def test_config1_sel20_expval_and_jacobian(q):
+    """BASELINE config 1 (20-qubit StronglyEntanglingLayers, 2 layers, <Z0>, 120 parameters) against
+    the fixture generated by the oracle (tests/golden/make_config_fixtures.py)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "config1_sel20.json")
+    with open(path) as f:
+        fx = json.load(f)
+    w = np.random.default_rng(fx["seed"]).uniform(0, 2 * math.pi, (fx["layers"], fx["n"], 3))
+    ops = orc.strongly_entangling_layers(w)
+    sv = q.StateVector(fx["n"], np.complex128)
+    rec = q.Ops(ops)
+    sv.apply_ops(rec, fuse=True)
+    z0 = q.Observable.named("PauliZ", [0])
+    assert abs(sv.expval(z0) - fx["expval"]) < 1e-10
+    jac = sv.adjoint_jacobian(rec, [z0], list(range(fx["n_params"])))
+    assert np.max(np.abs(jac[0] - np.asarray(fx["jacobian"]))) < 1e-10
+    idx = np.asarray(fx["state_sample_idx"])
+    assert np.max(np.abs(sv.d2h()[idx] - c_arr(fx["state_sample"]))) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at sizes the oracle cannot reach
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,n", [(np.complex128, 26), (np.complex64, 27)])
+def test_large_state_properties(q, dtype, n):
+    rng = np.random.default_rng(9)
+    sv = q.StateVector(n, dtype)
+    for w in range(n):
+        sv.apply("Hadamard", [w])
+    ops = []
+    for _ in range(40):
+        name = ["RX", "RY", "RZ", "CNOT", "CZ", "IsingXX", "CRZ", "Toffoli", "SWAP", "PhaseShift"][rng.integers(10)]
+        nw, npar = orc.GATE_ARITY[name]
+        ops.append({"name": name, "wires": _rand_wires(rng, n, nw),
+                    "params": [float(x) for x in rng.uniform(-3, 3, npar)]})
+    for o in ops:
+        sv.apply(o["name"], o["wires"], o["params"])
+    tol = 1e-10 if dtype == np.complex128 else 1e-4
+    assert abs(sv.inner_product(sv) - 1.0) < tol  # unitarity
+    p = sv.probs([0, n - 1])
+    assert abs(p.sum() - 1.0) < tol
+    z0 = sv.expval_named("PauliZ", [0]).real
+    assert abs((p[0] + p[2]) - (p[1] + p[3]) - z0) < tol  # probs and expval agree (wire 0 = LSB of probs)
+    ref = q.StateVector(n, dtype)
+    ref.copy_from(sv)
+    for o in reversed(ops):
+        sv.apply(o["name"], o["wires"], o["params"], adjoint=True)  # U^dagger U = 1
+    for w in range(n):
+        sv.apply("Hadamard", [w])
+    amp0 = sv.d2h()[:4]
+    assert abs(amp0[0] - 1.0) < (1e-9 if dtype == np.complex128 else 1e-3)
+    assert np.max(np.abs(amp0[1:])) < (1e-9 if dtype == np.complex128 else 1e-3)
+    # fused execution equals gate-by-gate execution
+    a = q.StateVector(n, dtype)
+    b = q.StateVector(n, dtype)
+    rec = q.Ops([{"name": "Hadamard", "wires": [w], "params": []} for w in range(n)] + ops)
+    a.apply_ops(rec, fuse=False)
+    b.apply_ops(rec, fuse=True)
+    assert abs(a.inner_product(b) - 1.0) < tol
+    assert abs(a.inner_product(ref) - 1.0) < tol
+
+
+def test_config3_vqe_reduced(q):
+    """BASELINE config 3 generator (hardware-efficient ansatz, 100-term Pauli Hamiltonian) at 14 qubits."""
+    import json
+    import os
+
+    from pennylane_lightning_gpu_b200 import workloads
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "config3_vqe14.json")) as f:
+        fx = json.load(f)
+    n = fx["n"]
+    ops, n_params = workloads.hardware_efficient_ansatz(n, layers=fx["layers"], seed=11)
+    words, wires, coeffs = workloads.random_pauli_hamiltonian(n, fx["n_terms"], seed=5)
+    ham = q.Observable.from_tuple(workloads.hamiltonian_tuple(words, wires, coeffs))
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 2e-4)):
+        sv = q.StateVector(n, dtype)
+        rec = q.Ops(ops)
+        sv.apply_ops(rec, fuse=True)
+        assert abs(sv.expval(ham) - fx["expval"]) < tol
+        assert abs(sv.expval_pauli_words(words, wires, coeffs) - fx["expval"]) < tol
+        jac = sv.adjoint_jacobian(rec, [ham], list(range(n_params)))
+        assert np.max(np.abs(jac[0] - np.asarray(fx["jacobian"]))) < tol
+    # sparse form of the same kind of Hamiltonian agrees with its Pauli-word form (config 4, reduced)
+    m, (w2, ws2, c2) = workloads.molecular_style_sparse_hamiltonian(n, n_terms=60, n_flip_masks=8, seed=3)
+    sv = q.StateVector(n, np.complex128)
+    sv.apply_ops(q.Ops(ops), fuse=True)
+    a = sv.expval_csr(m.indptr, m.indices, m.data)
+    b = sv.expval_pauli_words(w2, ws2, c2)
+    assert abs(a - b) < 1e-10
