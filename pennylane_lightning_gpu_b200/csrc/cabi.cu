@@ -163,10 +163,12 @@ int qsv_set_state_vector(qsv_state *sv, const int64_t *indices, const void *valu
     QSV_CUDA(cudaMemsetAsync(sv->data, 0, sv->bytes(), sv->stream));
     if (count) {
         const size_t vb = count * sv->amp_bytes();
-        char *scr = (char *)sv->scratch_buffer(count * 8 + vb);
-        QSV_CUDA(cudaMemcpyAsync(scr, indices, count * 8, cudaMemcpyHostToDevice, sv->stream));
-        QSV_CUDA(cudaMemcpyAsync(scr + count * 8, values, vb, cudaMemcpyHostToDevice, sv->stream));
-        launch_scatter(*sv, (const int64_t *)scr, scr + count * 8, count);
+        // values first: they need the 16-byte alignment of the 128-bit loads, the indices only 8
+        const size_t vb_al = (vb + 15) / 16 * 16;
+        char *scr = (char *)sv->scratch_buffer(vb_al + count * 8);
+        QSV_CUDA(cudaMemcpyAsync(scr, values, vb, cudaMemcpyHostToDevice, sv->stream));
+        QSV_CUDA(cudaMemcpyAsync(scr + vb_al, indices, count * 8, cudaMemcpyHostToDevice, sv->stream));
+        launch_scatter(*sv, (const int64_t *)(scr + vb_al), scr, count);
     }
     QSV_CUDA(cudaStreamSynchronize(sv->stream));
     QSV_API_END
