@@ -160,12 +160,30 @@ int qsv_adjoint_jacobian(qsv_state *sv, const qsv_ops *ops, qsv_obs *const *obse
 int qsv_dist_unique_id(void *id128);            /* 128 bytes out (rank 0)                    */
 int qsv_dist_init(qsv_state *local, const void *id128, int rank, int world_size);
 int qsv_dist_finalize(qsv_state *local);
-/* global<->local index-bit swap (MPI.hpp:2488-2587): exchanges, with rank ^ (1 << global_bit),
- * the half of the local shard whose local_bit differs from this rank's global bit */
+/* global<->local index-bit swap (MPI.hpp:2488-2587): exchanges, with rank ^ (1 << (global_bit - n_local)),
+ * the half of the local shard whose local_bit differs from this rank's value of global_bit (both are
+ * PHYSICAL index bits), through chunk_bytes-sized staging buffers (0 = 256 MiB; the reference's
+ * mpi_buf_size, MPIWorker.hpp:276-294), and records the exchange in the logical->physical qubit map */
 int qsv_dist_swap_bits(qsv_state *local, int global_bit, int local_bit, size_t chunk_bytes);
+/* whole circuit on the sharded register (wires refer to all n_total qubits): dense targets on global
+ * qubits are swapped in lazily (farthest-next-use eviction), controls / diagonal gates on global qubits
+ * run without communication (the reference swaps for every global wire, MPI.hpp:2023-2088) */
+int qsv_dist_apply_ops(qsv_state *local, const qsv_ops *ops, int fuse, size_t chunk_bytes);
+/* restore the identity qubit map so that rank r's shard is amplitudes [r * 2^n_local, (r+1) * 2^n_local) */
+int qsv_dist_canonicalize(qsv_state *local, size_t chunk_bytes);
+int qsv_dist_qubit_map(const qsv_state *local, int *phys_of_logical_bit, int n_total);
+/* getExpectationValuePauliWords on a sharded register (MPI.hpp:1296-1445): local reduction + all-reduce */
+int qsv_dist_expval_pauli_words(qsv_state *local, int n_terms, const char *letters, const int *wires,
+                                const int *offsets, const double *coeffs_re_im, double *per_term, double *out);
+/* MPI_Allreduce(sum) of small host vectors (MPI.hpp:1176, :1426, :2361): ncclAllReduce on a device buffer */
 int qsv_dist_allreduce_f64(qsv_state *local, double *host_values, int count);
-/* NVLink bytes sent by this rank and device milliseconds of the last qsv_dist_swap_bits */
+/* NVLink bytes sent by this rank and device milliseconds of the last exchange / of all exchanges */
 int qsv_dist_last_swap_stats(const qsv_state *local, uint64_t *bytes_sent, float *ms);
+int qsv_dist_total_swap_stats(qsv_state *local, int *n_swaps, uint64_t *bytes_sent, float *ms, int reset);
+/* host-only (no GPU, no NCCL): the exchanges qsv_dist_apply_ops would perform.  steps receives triples
+ * (kind, a, b): kind 0 = swap physical global bit a with local bit b, kind 1 = apply op number a */
+int qsv_dist_plan(const qsv_ops *ops, int n_total, int n_local, int *steps, int max_steps, int *n_steps,
+                  int *final_phys_of_logical_bit);
 
 #ifdef __cplusplus
 }

@@ -275,6 +275,13 @@ Mat controlled(const Mat &u, int du, int n_ctrl) {
 
 }  // namespace
 
+LoweredGate make_dense_gate(const std::vector<int> &tgt_bits, uint64_t ctrl_mask, std::vector<cplx> m) {
+    return make_dense(tgt_bits, ctrl_mask, std::move(m));
+}
+LoweredGate make_diag_gate(const std::vector<int> &tgt_bits, uint64_t ctrl_mask, std::vector<cplx> d) {
+    return make_diag(tgt_bits, ctrl_mask, std::move(d));
+}
+
 const GateInfo *find_gate(const std::string &name) {
     const Entry *e = find_entry(name);
     return e ? &e->info : nullptr;

@@ -73,6 +73,9 @@ LoweredGate lower_named(int n_qubits, const std::string &name, const std::vector
                         const std::vector<double> &params, bool adjoint);
 LoweredGate lower_matrix(int n_qubits, const cplx *matrix, const std::vector<int> &ctrl_wires,
                          const std::vector<int> &tgt_wires, bool adjoint);
+// building blocks on index bits (tgt_bits[0] = most significant matrix / table bit)
+LoweredGate make_dense_gate(const std::vector<int> &tgt_bits, uint64_t ctrl_mask, std::vector<cplx> matrix);
+LoweredGate make_diag_gate(const std::vector<int> &tgt_bits, uint64_t ctrl_mask, std::vector<cplx> diag);
 
 // Generator of a parametric gate as an operator (GateGenerators.hpp); `scale` per
 // AdjointDiffGPU.hpp:96-114.  `extra_identity` is the coefficient d of an additional d * Identity
@@ -105,6 +108,9 @@ struct State {
     void *scratch = nullptr;
     size_t scratch_cap = 0;
     int64_t stat_launches = 0, stat_sweeps = 0;
+    // sharded states: value of the index bits above n (rank << n); controls / diagonal gates on those
+    // "global" bits are evaluated against it and need no communication
+    uint64_t index_hi = 0;
     DistCtx *dist = nullptr;
 
     size_t amp_bytes() const { return dtype == QSV_C128 ? 16 : 8; }
@@ -174,6 +180,8 @@ void reduction_read(State &sv, const double *dev, double *host, size_t count);
 // circuits
 void apply_op(State &sv, const Op &op, bool extra_adjoint);
 void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
+// same, on several vectors at once (dev_table = device array of n_vecs pointers, or null for sv.data)
+void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs);
 void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
 double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>
 void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
