@@ -1,0 +1,114 @@
+"""Sharded state vectors over NCCL: one process per GPU, launched by torchrun.
+
+StateVectorCudaMPI analogue (simulator/StateVectorCudaMPI.hpp of the reference).  torch.distributed is
+only the rendezvous that carries the 128-byte NCCL unique id from rank 0 to the other ranks (the role
+MPI_Bcast / MPI_Allgather of IPC handles plays at MPIWorker.hpp:306-320); all data-path communication
+is NCCL send/recv + all-reduce inside libqsv_b200.so (csrc/dist.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import Ops, StateVector, _check, lib
+
+
+def plan(ops: Ops, n_total: int, n_local: int):
+    """Host-only view of the exchange schedule: -> (steps, final map).  steps = list of
+    ("swap", global_phys_bit, local_phys_bit) | ("gate", op_index)."""
+    cap = 4 * len(ops) + 16
+    steps = (C.c_int * (3 * cap))()
+    n_steps = C.c_int(0)
+    final = (C.c_int * n_total)()
+    _check(lib().qsv_dist_plan(ops._h, n_total, n_local, steps, cap, C.byref(n_steps), final))
+    out = []
+    for i in range(n_steps.value):
+        kind, a, b = steps[3 * i], steps[3 * i + 1], steps[3 * i + 2]
+        out.append(("swap", a, b) if kind == 0 else ("gate", a))
+    return out, list(final)
+
+
+class DistributedStateVector:
+    """n_total-qubit register sharded over WORLD_SIZE GPUs on the top log2(WORLD_SIZE) index bits
+    (PennyLane wires 0..g-1 are global, as in lightning_gpu.py:317-319 / MPI.hpp:240-246)."""
+
+    def __init__(self, n_total: int, dtype=np.complex128, device: int = 0, *, external_ptr: int | None = None,
+                 chunk_bytes: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (torchrun) before creating a sharded register")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        g = int(math.log2(self.world))
+        if 1 << g != self.world:
+            raise ValueError("number of ranks must be a power of two")
+        self.n_total, self.n_global, self.n_local = n_total, g, n_total - g
+        self.chunk_bytes = chunk_bytes
+        self.local = StateVector(self.n_local, dtype, device, external_ptr=external_ptr)
+        if external_ptr is None:
+            # |0...0>: only rank 0 holds the amplitude 1
+            if self.rank != 0:
+                self.local.set_state_vector([], np.zeros(0, dtype=dtype))
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _check(lib().qsv_dist_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(torch.device("cuda", device)) if dist.get_backend() == "nccl" else ident
+        dist.broadcast(ident, src=0)
+        raw = bytes(ident.cpu().tolist())
+        self._id = (C.c_ubyte * 128).from_buffer_copy(raw)
+        _check(lib().qsv_dist_init(self.local._h, self._id, self.rank, self.world))
+
+    # -- gates ----------------------------------------------------------------------------------
+    def apply_ops(self, ops: Ops, fuse: bool = True):
+        _check(lib().qsv_dist_apply_ops(self.local._h, ops._h, int(bool(fuse)), self.chunk_bytes))
+
+    def last_apply_stats(self):
+        return self.local.last_apply_stats()
+
+    def swap_stats(self, reset: bool = False):
+        n, b, ms = C.c_int(0), C.c_uint64(0), C.c_float(0)
+        _check(lib().qsv_dist_total_swap_stats(self.local._h, C.byref(n), C.byref(b), C.byref(ms), int(reset)))
+        return n.value, b.value, ms.value
+
+    def qubit_map(self):
+        m = (C.c_int * self.n_total)()
+        _check(lib().qsv_dist_qubit_map(self.local._h, m, self.n_total))
+        return list(m)
+
+    def canonicalize(self):
+        _check(lib().qsv_dist_canonicalize(self.local._h, self.chunk_bytes))
+
+    # -- measurements ---------------------------------------------------------------------------
+    def expval_pauli_words(self, words, wires, coeffs, return_terms: bool = False):
+        letters = "".join(words).encode()
+        offs = np.zeros(len(words) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(w) for w in words])
+        wa, wp = _cabi._ints([int(x) for ws in wires for x in ws])
+        ca, cp = _cabi._cmat(coeffs)
+        terms = np.zeros(max(len(words), 1), dtype=np.float64)
+        out = C.c_double(0)
+        _check(lib().qsv_dist_expval_pauli_words(self.local._h, len(words), letters, wp,
+                                                 offs.ctypes.data_as(_cabi._IP), cp,
+                                                 terms.ctypes.data_as(_cabi._DP), C.byref(out)))
+        return (out.value, terms[: len(words)]) if return_terms else out.value
+
+    def norm2(self) -> float:
+        v = np.array([self.local.inner_product(self.local).real], dtype=np.float64)
+        _check(lib().qsv_dist_allreduce_f64(self.local._h, v.ctypes.data_as(_cabi._DP), 1))
+        return float(v[0])
+
+    def local_state(self) -> np.ndarray:
+        """This rank's shard in the CURRENT qubit map (call canonicalize() first for the standard layout)."""
+        return self.local.d2h()
+
+    def synchronize(self):
+        self.local.synchronize()
+
+    def close(self):
+        _check(lib().qsv_dist_finalize(self.local._h))
