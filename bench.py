@@ -270,6 +270,23 @@ def run_ours(args):
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms}
 
     detail = {}
+    if distributed:
+        n_swaps, swap_bytes, swap_ms = sv.swap_stats()
+        # per-direction NVLink bandwidth of the global<->local index-bit swaps (device time of the
+        # NCCL send/recv stream, this rank) over warm-up + timed steps
+        detail["nvlink_swaps"] = {
+            "n_swaps_per_step": n_swaps / (max(args.warmup, 3) + args.steps),
+            "gb_sent_per_swap": (swap_bytes / max(n_swaps, 1)) / 1e9,
+            "gbs_per_direction": (swap_bytes / 1e9) / (swap_ms * 1e-3) if swap_ms > 0 else None,
+            "frac_of_770_measured_peer_copy": ((swap_bytes / 1e9) / (swap_ms * 1e-3) / 770.0) if swap_ms > 0 else None,
+            "swap_ms_per_step": swap_ms / (max(args.warmup, 3) + args.steps),
+        }
+        kernel_ms = ms_total - detail["nvlink_swaps"]["swap_ms_per_step"] * args.steps
+        if launches > 0 and kernel_ms > 0:
+            roofline["ms_per_launch"] = kernel_ms / launches
+            roofline["achieved"] = bytes_per_launch / (roofline["ms_per_launch"] * 1e-3) / 1e9
+            roofline["frac"] = roofline["achieved"] / hbm_peak
+            roofline["note"] = "exchange time (NCCL stream) subtracted from the region before dividing by launches"
     # ---- single-gate sweeps: C2(i), every target wire individually ----------------------------
     if args.sweeps and not distributed:
         detail["single_gate_sweeps"] = single_gate_sweeps(torch, q, sv, n_local, amp_bytes, hbm_peak)

@@ -44,6 +44,9 @@ int qsv_version(void);
 int qsv_device_count(int *count);
 int qsv_device_arch(int device, int *major, int *minor);
 int qsv_device_mem_info(int device, size_t *free_bytes, size_t *total_bytes);
+/* deviceReset (cuda_helpers.hpp) and the allToAllAccess loop of bindings/Bindings.cpp:1737-1741 */
+int qsv_device_reset(void);
+int qsv_enable_peer_access(void);
 
 /* ---- state-vector lifetime: StateVectorCudaManaged ctor/dtor (Managed.hpp:83-134),
  *      DataBuffer (util/DataBuffer.hpp:31-121) ------------------------------- */

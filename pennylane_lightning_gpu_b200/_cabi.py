@@ -39,6 +39,8 @@ SIGNATURES = {
     "qsv_device_count": (_I, [_IP]),
     "qsv_device_arch": (_I, [_I, _IP, _IP]),
     "qsv_device_mem_info": (_I, [_I, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "qsv_device_reset": (_I, []),
+    "qsv_enable_peer_access": (_I, []),
     "qsv_create": (_I, [_I, _I, _I, C.POINTER(_P)]),
     "qsv_create_external": (_I, [_I, _I, _I, _P, _P, C.POINTER(_P)]),
     "qsv_destroy": (_I, [_P]),

@@ -86,6 +86,38 @@ int qsv_device_mem_info(int device, size_t *free_bytes, size_t *total_bytes) {
     QSV_API_END
 }
 
+int qsv_device_reset(void) {
+    QSV_API_BEGIN
+    int count = 0;
+    QSV_CUDA(cudaGetDeviceCount(&count));
+    for (int d = 0; d < count; ++d) {
+        QSV_CUDA(cudaSetDevice(d));
+        QSV_CUDA(cudaDeviceReset());
+    }
+    QSV_API_END
+}
+
+int qsv_enable_peer_access(void) {
+    QSV_API_BEGIN
+    int count = 0;
+    QSV_CUDA(cudaGetDeviceCount(&count));
+    for (int a = 0; a < count; ++a) {
+        QSV_CUDA(cudaSetDevice(a));
+        for (int b = 0; b < count; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            QSV_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
+            if (!can) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError();
+            else
+                QSV_CUDA(e);
+        }
+    }
+    QSV_API_END
+}
+
 int qsv_create_external(int n_qubits, int dtype, int device, void *device_ptr, void *cuda_stream,
                         qsv_state **out) {
     QSV_API_BEGIN
