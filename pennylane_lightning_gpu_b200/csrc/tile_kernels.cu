@@ -31,7 +31,7 @@ constexpr int TILE_NT = 256;
 constexpr int TILE_MAX_GATES = 40;
 constexpr int TILE_POOL = 1280;  // doubles
 
-enum : unsigned char { TG_DENSE1 = 1, TG_DENSE2 = 2, TG_DIAG = 3, TG_PARITY = 4 };
+enum : unsigned char { TG_DENSE1 = 1, TG_DENSE2 = 2, TG_DIAG = 3, TG_PARITY = 4, TG_SWAP1 = 5, TG_REAL1 = 6 };
 
 struct TileGate {
     unsigned char kind;
@@ -46,6 +46,9 @@ struct TileGate {
     uint32_t zmask_loc;     // parity
     uint32_t mat_off;       // first double of this gate in the pool
     uint64_t zmask_out;
+    // dense: expand_local(it * TILE_NT) for it = 0..15, so that group (tid + it * TILE_NT) sits at
+    // expand_local(tid) | hi_tab[it]  (bit deposit is linear over disjoint bit sets)
+    uint16_t hi_tab[16];
 };
 
 struct TileProgram {
@@ -152,22 +155,53 @@ __global__ void __launch_bounds__(TILE_NT)
         const TileGate &g = P.gates[gi];
         if ((outside & g.out_ctrl) == g.out_ctrl) {  // CTA-uniform
             const double *mp = P.pool + g.mat_off;
-            if (g.kind == TG_DENSE1) {
-                const T m00r = (T)mp[0], m00i = (T)mp[1], m01r = (T)mp[2], m01i = (T)mp[3];
-                const T m10r = (T)mp[4], m10i = (T)mp[5], m11r = (T)mp[6], m11i = (T)mp[7];
+            if (g.kind == TG_DENSE1 || g.kind == TG_SWAP1 || g.kind == TG_REAL1) {
                 const uint32_t n_groups = tile_amps >> g.n_holes;
                 const uint32_t o0 = g.offs[0], o1 = g.offs[1];
+                const bool active = threadIdx.x < n_groups;
+                const uint32_t e_tid = expand_local(threadIdx.x, g.holes, g.n_holes) | g.loc_ctrl;
+                const int iters = n_groups >= TILE_NT ? (int)(n_groups / TILE_NT) : 1;
+                if (active) {
+                    if (g.kind == TG_SWAP1) {
+                        // X-type gate (PauliX / CNOT / Toffoli / SWAP / CSWAP): a pure exchange, no FP
 #pragma unroll 4
-                for (uint32_t grp = threadIdx.x; grp < n_groups; grp += TILE_NT) {
-                    const uint32_t i0 = expand_local(grp, g.holes, g.n_holes) | g.loc_ctrl;
-                    const A a = s[i0 + o0], b = s[i0 + o1];
-                    A x, y;
-                    x.x = m00r * a.x - m00i * a.y + m01r * b.x - m01i * b.y;
-                    x.y = m00r * a.y + m00i * a.x + m01r * b.y + m01i * b.x;
-                    y.x = m10r * a.x - m10i * a.y + m11r * b.x - m11i * b.y;
-                    y.y = m10r * a.y + m10i * a.x + m11r * b.y + m11i * b.x;
-                    s[i0 + o0] = x;
-                    s[i0 + o1] = y;
+                        for (int it = 0; it < iters; ++it) {
+                            const uint32_t i0 = e_tid | g.hi_tab[it];
+                            const A a = s[i0 + o0], b = s[i0 + o1];
+                            s[i0 + o0] = b;
+                            s[i0 + o1] = a;
+                        }
+                    } else if (g.kind == TG_REAL1) {
+                        // real 2x2 (RY, Hadamard, ...): half the FP64 work
+                        const T m00 = (T)mp[0], m01 = (T)mp[2], m10 = (T)mp[4], m11 = (T)mp[6];
+#pragma unroll 4
+                        for (int it = 0; it < iters; ++it) {
+                            const uint32_t i0 = e_tid | g.hi_tab[it];
+                            const A a = s[i0 + o0], b = s[i0 + o1];
+                            A x, y;
+                            x.x = m00 * a.x + m01 * b.x;
+                            x.y = m00 * a.y + m01 * b.y;
+                            y.x = m10 * a.x + m11 * b.x;
+                            y.y = m10 * a.y + m11 * b.y;
+                            s[i0 + o0] = x;
+                            s[i0 + o1] = y;
+                        }
+                    } else {
+                        const T m00r = (T)mp[0], m00i = (T)mp[1], m01r = (T)mp[2], m01i = (T)mp[3];
+                        const T m10r = (T)mp[4], m10i = (T)mp[5], m11r = (T)mp[6], m11i = (T)mp[7];
+#pragma unroll 4
+                        for (int it = 0; it < iters; ++it) {
+                            const uint32_t i0 = e_tid | g.hi_tab[it];
+                            const A a = s[i0 + o0], b = s[i0 + o1];
+                            A x, y;
+                            x.x = m00r * a.x - m00i * a.y + m01r * b.x - m01i * b.y;
+                            x.y = m00r * a.y + m00i * a.x + m01r * b.y + m01i * b.x;
+                            y.x = m10r * a.x - m10i * a.y + m11r * b.x - m11i * b.y;
+                            y.y = m10r * a.y + m10i * a.x + m11r * b.y + m11i * b.x;
+                            s[i0 + o0] = x;
+                            s[i0 + o1] = y;
+                        }
+                    }
                 }
             } else if (g.kind == TG_DENSE2) {
                 T mr[16], mi[16];
@@ -178,30 +212,35 @@ __global__ void __launch_bounds__(TILE_NT)
                 }
                 const uint32_t n_groups = tile_amps >> g.n_holes;
                 const uint32_t o0 = g.offs[0], o1 = g.offs[1], o2 = g.offs[2], o3 = g.offs[3];
+                const bool active = threadIdx.x < n_groups;
+                const uint32_t e_tid = expand_local(threadIdx.x, g.holes, g.n_holes) | g.loc_ctrl;
+                const int iters = n_groups >= TILE_NT ? (int)(n_groups / TILE_NT) : 1;
+                if (active) {
 #pragma unroll 2
-                for (uint32_t grp = threadIdx.x; grp < n_groups; grp += TILE_NT) {
-                    const uint32_t i0 = expand_local(grp, g.holes, g.n_holes) | g.loc_ctrl;
-                    A x[4];
-                    x[0] = s[i0 + o0];
-                    x[1] = s[i0 + o1];
-                    x[2] = s[i0 + o2];
-                    x[3] = s[i0 + o3];
-                    A y[4];
+                    for (int it = 0; it < iters; ++it) {
+                        const uint32_t i0 = e_tid | g.hi_tab[it];
+                        A x[4];
+                        x[0] = s[i0 + o0];
+                        x[1] = s[i0 + o1];
+                        x[2] = s[i0 + o2];
+                        x[3] = s[i0 + o3];
+                        A y[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        T yr = T(0), yi = T(0);
+                        for (int r = 0; r < 4; ++r) {
+                            T yr = T(0), yi = T(0);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            yr += mr[r * 4 + c] * x[c].x - mi[r * 4 + c] * x[c].y;
-                            yi += mr[r * 4 + c] * x[c].y + mi[r * 4 + c] * x[c].x;
+                            for (int c = 0; c < 4; ++c) {
+                                yr += mr[r * 4 + c] * x[c].x - mi[r * 4 + c] * x[c].y;
+                                yi += mr[r * 4 + c] * x[c].y + mi[r * 4 + c] * x[c].x;
+                            }
+                            y[r].x = yr;
+                            y[r].y = yi;
                         }
-                        y[r].x = yr;
-                        y[r].y = yi;
+                        s[i0 + o0] = y[0];
+                        s[i0 + o1] = y[1];
+                        s[i0 + o2] = y[2];
+                        s[i0 + o3] = y[3];
                     }
-                    s[i0 + o0] = y[0];
-                    s[i0 + o1] = y[1];
-                    s[i0 + o2] = y[2];
-                    s[i0 + o3] = y[3];
                 }
             } else {
                 // DIAG / PARITY: per-amplitude phase; table bits outside the tile are fixed per CTA
@@ -379,10 +418,27 @@ void run_sweep(State &sv, const Sweep &sw, int tb, int L, void *const *table, in
         t.loc_ctrl = map_mask(g.ctrl_mask, t.out_ctrl);
         if (g.kind == LoweredGate::DENSE) {
             t.kind = g.k == 1 ? TG_DENSE1 : TG_DENSE2;
+            if (g.k == 1) {
+                const cplx zero(0.0, 0.0), one(1.0, 0.0);
+                bool real = true;
+                for (const cplx &c : g.mat) real = real && c.imag() == 0.0;
+                if (g.mat[0] == zero && g.mat[3] == zero && g.mat[1] == one && g.mat[2] == one)
+                    t.kind = TG_SWAP1;
+                else if (real)
+                    t.kind = TG_REAL1;
+            }
             int nh = 0;
             for (int h : g.holes)
                 if (pos[h] >= 0) t.holes[nh++] = (unsigned char)pos[h];  // ascending: pos is monotonic
             t.n_holes = (unsigned char)nh;
+            for (int it = 0; it < 16; ++it) {
+                uint32_t o = (uint32_t)it * TILE_NT;
+                for (int j = 0; j < nh; ++j) {
+                    const int hp = t.holes[j];
+                    o = ((o >> hp) << (hp + 1)) | (o & ((1u << hp) - 1u));
+                }
+                t.hi_tab[it] = (uint16_t)(o & 0xffffu);  // entries beyond the tile are never used
+            }
             for (size_t j = 0; j < g.offs.size(); ++j) {
                 uint64_t dummy;
                 t.offs[j] = (uint16_t)map_mask(g.offs[j], dummy);
@@ -489,7 +545,7 @@ void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void
     sv.use();
     const bool f32 = sv.dtype == QSV_C64;
     int tb = env_int("QSV_TILE_BITS", f32 ? 13 : 12);
-    int L = env_int("QSV_TILE_LOW", f32 ? 7 : 6);
+    int L = env_int("QSV_TILE_LOW", f32 ? 8 : 7);
     const bool tma = env_int("QSV_TILE_TMA", 1) != 0;
     const bool merge = env_int("QSV_MERGE_1Q", 1) != 0;
     tb = std::min(tb, sv.n);
