@@ -106,7 +106,7 @@ template <> struct Cx<double> { using type = double2; };
 template <> struct Cx<float> { using type = float2; };
 
 template <typename T, bool USE_TMA>
-__global__ void __launch_bounds__(TILE_NT)
+__global__ void __launch_bounds__(TILE_NT, 3)
     k_tile_sweep(void *single, void *const *table, const __grid_constant__ TileProgram P) {
     using A = typename Cx<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
