@@ -257,17 +257,26 @@ def run_ours(args):
     # roofline of the dominant kernel: the gate / tile sweep kernels are the only kernels in the
     # timed region, so average launch duration = region time / launches (CUDA events, this stream).
     per_launch_ms = ms_total / max(launches, 1)
-    if args.fuse and sweeps < len(ops) * args.steps:
-        # fused tile kernel: every launch reads and writes the whole local shard once
-        bytes_per_launch = 2 * amp_bytes * (1 << n_local)
-        kernel = "k_tile_sweep (fused shared-memory tile kernel), 2*B*N_local bytes per launch"
-    else:
-        bytes_per_launch = alg_bytes_total / world / max(len(ops), 1)
-        kernel = "k_apply_dense / k_apply_diag (one sweep per gate), mean algorithmic bytes per gate"
+    fused = bool(args.fuse) and sweeps < len(ops) * args.steps
+    # algorithmic bytes per launch per SURVEY.md 8d: the gates a launch applies, 2*B*N/2^c each, no credit for
+    # fusion -- so a fused sweep can exceed 1.0x of the copy bandwidth; the actual DRAM rate is reported beside it
+    bytes_per_launch = alg_bytes_total / world * args.steps / max(launches, 1)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    sweep_bytes = 2 * amp_bytes * (1 << n_local)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": kernel, "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms}
+                "traffic": sweep_bytes if fused else None,
+                "traffic_source": ("ncu dram__bytes_read+write per k_tile_sweep launch = 34.3 GB = 2*B*N at 30q c128 "
+                                   "(profiles/r1_ncu_summary.txt)") if fused else
+                                  "ncu: 34.4 GB per full-state gate launch (profiles/r1_ncu_summary.txt); controlled gates move less",
+                "kernel": "k_tile_sweep (fused shared-memory tile kernel, TMA-staged)" if fused else
+                          "k_apply_dense / k_apply_diag (one sweep per gate)",
+                "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "gates_per_launch": len(ops) * args.steps / max(launches, 1)}
+    if fused:
+        roofline["hbm_actual_gbs"] = sweep_bytes / (per_launch_ms * 1e-3) / 1e9
+        roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
+        roofline["note"] = ("fused sweeps are shared-memory-bandwidth-bound (1024 clk per gate per 64 KiB tile), not "
+                            "HBM-bound: see DESIGN.md 4.2; --fuse 0 gives the HBM-bound one-sweep-per-gate kernels")
 
     detail = {}
     if distributed:
@@ -286,10 +295,21 @@ def run_ours(args):
             roofline["ms_per_launch"] = kernel_ms / launches
             roofline["achieved"] = bytes_per_launch / (roofline["ms_per_launch"] * 1e-3) / 1e9
             roofline["frac"] = roofline["achieved"] / hbm_peak
-            roofline["note"] = "exchange time (NCCL stream) subtracted from the region before dividing by launches"
+            if fused:
+                roofline["hbm_actual_gbs"] = sweep_bytes / (roofline["ms_per_launch"] * 1e-3) / 1e9
+                roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
+            roofline["exchange_note"] = "exchange time (NCCL stream) subtracted from the region before dividing by launches"
     # ---- single-gate sweeps: C2(i), every target wire individually ----------------------------
     if args.sweeps and not distributed:
         detail["single_gate_sweeps"] = single_gate_sweeps(torch, q, sv, n_local, amp_bytes, hbm_peak)
+
+    if args.adjoint and not distributed:
+        del sv
+        detail["adjoint_config3"] = adjoint_config3(torch, q, args)
+    if args.config4 and not distributed:
+        detail["sparse_config4"] = sparse_config4(torch, q, args)
+    if args.adjoint and not distributed:
+        sv = q.StateVector(n_local, cdtype, device=local_rank, external_ptr=buf.data_ptr())
 
     # ---- end to end through the public API with host buffers ----------------------------------
     e2e = None
@@ -356,6 +376,121 @@ def single_gate_sweeps(torch, q, sv, n, amp_bytes, hbm_peak):
     return out
 
 
+def adjoint_config3(torch, q, args):
+    """BASELINE config 3: 24-qubit hardware-efficient ansatz (4 layers, 192 parameters), 100-term Pauli
+    Hamiltonian, adjoint Jacobian; wall seconds through the public API (device sync on both sides)."""
+    n = args.adjoint_qubits
+    ops, n_par = workloads.hardware_efficient_ansatz(n, layers=4, seed=11)
+    words, wires, coeffs = workloads.random_pauli_hamiltonian(n, 100, seed=5)
+    ham = q.Observable.from_tuple(workloads.hamiltonian_tuple(words, wires, coeffs))
+    rec = q.Ops(ops)
+    sv = q.StateVector(n, np.complex128)
+    out = {"n_qubits": n, "n_params": n_par, "n_ops": len(ops), "n_terms": 100, "dtype": "complex128"}
+
+    def run():
+        sv.set_basis_state(0)
+        sv.apply_ops(rec, fuse=True)
+        e = sv.expval(ham)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        jac = sv.adjoint_jacobian(rec, [ham], list(range(n_par)))
+        torch.cuda.synchronize()
+        return e, jac, time.perf_counter() - t0
+
+    run()
+    best = None
+    for _ in range(3):
+        e, jac, dt = run()
+        best = dt if best is None else min(best, dt)
+    out["jacobian_s"] = best
+    out["expval"] = e
+    out["jac_norm"] = float(np.linalg.norm(jac))
+    # self-check without an oracle at this size: central finite difference on two parameters
+    idx_par = [i for i, o in enumerate(ops) if o["params"]]
+    fd_err = 0.0
+    for p in (0, n_par - 1):
+        vals = []
+        for sgn in (+1, -1):
+            ops2 = [dict(o) for o in ops]
+            ops2[idx_par[p]] = dict(ops2[idx_par[p]], params=[ops[idx_par[p]]["params"][0] + sgn * 1e-4])
+            sv.set_basis_state(0)
+            sv.apply_ops(q.Ops(ops2), fuse=True)
+            vals.append(sv.expval(ham))
+        fd_err = max(fd_err, abs((vals[0] - vals[1]) / 2e-4 - jac[0, p]))
+    out["finite_difference_max_abs_err"] = fd_err
+    # algorithmic bytes per SURVEY.md 8d with n_bra = 1: P * 2BN * 2 + Q * BN * 2
+    B, N = 16, 1 << n
+    alg = len(ops) * 2 * B * N * 2 + n_par * B * N * 2
+    out["algorithmic_gb"] = alg / 1e9
+    out["algorithmic_gbs"] = alg / best / 1e9
+    if args.cpu_baseline:
+        try:
+            from oracle import lq_port as lq
+
+            lq.set_num_threads(os.cpu_count() or 1)
+            st = lq.LQState(n)
+            st.apply_ops(ops)
+            ham_t = workloads.hamiltonian_tuple(words, wires, coeffs)
+            t0 = time.perf_counter()
+
+            # Hamiltonian bra through the Pauli-sum kernel of the port (one bra, as the GPU path does)
+            lam = st.copy()
+            bra = lam.apply_pauli_hamiltonian(words, wires, coeffs)
+            jac_cpu = _cpu_adjoint(lq, lam, bra, ops, n_par)
+            out["cpu_port_jacobian_s"] = time.perf_counter() - t0
+            out["cpu_cores"] = os.cpu_count()
+            out["gpu_vs_cpu_port_max_abs_diff"] = float(np.max(np.abs(jac_cpu - jac[0])))
+        except Exception as ex:  # the CPU leg must never break the GPU numbers
+            out["cpu_port_error"] = repr(ex)
+    return out
+
+
+def _cpu_adjoint(lq, lam, bra, ops, n_par):
+    """lightning.qubit-style reverse sweep with one bra (oracle/lq_port.py's loop, inlined for one bra)."""
+    from oracle import np_oracle as orc
+
+    jac = np.zeros(n_par)
+    cur = n_par - 1
+    for op in reversed(ops):
+        params = op.get("params", ())
+        mu = lam.copy() if len(params) else None
+        lam.apply_op(op["name"], op["wires"], params, True, op.get("matrix"))
+        if len(params):
+            g, s = orc.generator(op["name"], len(op["wires"]))
+            mu.apply_matrix(g, op["wires"])
+            jac[cur] = -2.0 * s * bra.inner(mu).imag
+            cur -= 1
+        bra.apply_op(op["name"], op["wires"], params, True, op.get("matrix"))
+    return jac
+
+
+def sparse_config4(torch, q, args):
+    """BASELINE config 4: 22-qubit molecular-style sparse Hamiltonian, <H> by CSR SpMV fused with the dot."""
+    n = args.config4_qubits
+    t0 = time.perf_counter()
+    m, (words, wires, coeffs) = workloads.molecular_style_sparse_hamiltonian(n, 400, 30, seed=3)
+    build_s = time.perf_counter() - t0
+    ops, _ = workloads.hardware_efficient_ansatz(n, layers=4, seed=11)
+    sv = q.StateVector(n, np.complex128)
+    sv.apply_ops(q.Ops(ops), fuse=True)
+    obs = q.Observable.sparse(m.indptr, m.indices, m.data)
+    e_csr = sv.expval_csr(m.indptr, m.indices, m.data)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e_csr = sv.expval_csr(m.indptr, m.indices, m.data)
+    torch.cuda.synchronize()
+    t_csr = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    e_pw = sv.expval_pauli_words(words, wires, coeffs)
+    torch.cuda.synchronize()
+    t_pw = time.perf_counter() - t0
+    B, I, N = 16, 8, 1 << n
+    alg = m.nnz * (B + I) + (N + 1) * I + 2 * B * N
+    return {"n_qubits": n, "nnz": int(m.nnz), "csr_gb": m.nnz * 24 / 1e9, "host_build_s": build_s,
+            "expval_csr": e_csr, "expval_pauli_words": e_pw, "abs_diff": abs(e_csr - e_pw),
+            "csr_call_s_including_h2d": t_csr, "pauli_words_call_s": t_pw, "algorithmic_gb": alg / 1e9}
+
+
 def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, args):
     """StatePrep(host state) -> circuit -> <Z0> on the host, all through the public API."""
     try:
@@ -400,6 +535,10 @@ def main():
     ap.add_argument("--sweeps", type=int, default=1)
     ap.add_argument("--e2e", type=int, default=1)
     ap.add_argument("--cpu-baseline", dest="cpu_baseline", type=int, default=1)
+    ap.add_argument("--adjoint", type=int, default=1, help="also time BASELINE config 3 (24q adjoint Jacobian)")
+    ap.add_argument("--adjoint-qubits", dest="adjoint_qubits", type=int, default=24)
+    ap.add_argument("--config4", type=int, default=0, help="also run BASELINE config 4 (22q sparse Hamiltonian)")
+    ap.add_argument("--config4-qubits", dest="config4_qubits", type=int, default=22)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -75,6 +75,53 @@ __global__ void __launch_bounds__(NT)
     }
 }
 
+// 2x2 gate on index bit 0: both partners sit in one 32-byte (complex128) / 16-byte (complex64) element,
+// moved with a single 256-bit (LDG.E.ENL2.256) / 128-bit access per thread and element.
+__device__ __forceinline__ void load_pair(double (&c)[4], const void *base, uint64_t e) {
+    const double *p = reinterpret_cast<const double *>(base) + 4 * e;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c[0]), "=d"(c[1]), "=d"(c[2]), "=d"(c[3]) : "l"(p));
+}
+__device__ __forceinline__ void store_pair(void *base, uint64_t e, const double (&c)[4]) {
+    double *p = reinterpret_cast<double *>(base) + 4 * e;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(c[0]), "d"(c[1]), "d"(c[2]), "d"(c[3]) : "memory");
+}
+__device__ __forceinline__ void load_pair(float (&c)[4], const void *base, uint64_t e) {
+    const float4 v = reinterpret_cast<const float4 *>(base)[e];
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+}
+__device__ __forceinline__ void store_pair(void *base, uint64_t e, const float (&c)[4]) {
+    reinterpret_cast<float4 *>(base)[e] = make_float4(c[0], c[1], c[2], c[3]);
+}
+
+template <typename T, int U, int NT>
+__global__ void __launch_bounds__(NT)
+    k_apply_dense_bit0(void *single, void *const *table, uint64_t n_elems, Holes holes, uint64_t ctrl, MatP<T, 1> m) {
+    void *sv = table ? table[blockIdx.y] : single;
+    const uint64_t g0 = (uint64_t)blockIdx.x * (uint64_t)(NT * U) + threadIdx.x;
+    T x[U][4];
+    uint64_t e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint64_t g = g0 + (uint64_t)u * NT;
+        if (g < n_elems) {
+            e[u] = expand_index(g, holes) | ctrl;
+            load_pair(x[u], sv, e[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint64_t g = g0 + (uint64_t)u * NT;
+        if (g < n_elems) {
+            T y[4];
+            y[0] = m.re[0] * x[u][0] - m.im[0] * x[u][1] + m.re[1] * x[u][2] - m.im[1] * x[u][3];
+            y[1] = m.re[0] * x[u][1] + m.im[0] * x[u][0] + m.re[1] * x[u][3] + m.im[1] * x[u][2];
+            y[2] = m.re[2] * x[u][0] - m.im[2] * x[u][1] + m.re[3] * x[u][2] - m.im[3] * x[u][3];
+            y[3] = m.re[2] * x[u][1] + m.im[2] * x[u][0] + m.re[3] * x[u][3] + m.im[3] * x[u][2];
+            store_pair(sv, e[u], y);
+        }
+    }
+}
+
 // Generic dense block for k > 4 targets: one CTA per group, amplitudes staged in shared memory,
 // one warp per output row, matrix streamed from L2.  Correctness path for large QubitUnitary;
 // such blocks are FP-bound, not HBM-bound.
@@ -249,6 +296,27 @@ void launch_dense_k(State &sv, const LoweredGate &g, void *const *table, int n_v
 }
 
 template <typename T>
+void launch_dense_bit0(State &sv, const LoweredGate &g, void *const *table, int n_vecs) {
+    // element = the (2g, 2g+1) pair; remaining holes are the control bits, shifted down by one
+    std::vector<int> cpos;
+    for (int h : g.holes)
+        if (h != 0) cpos.push_back(h);
+    QSV_CHECK((int)cpos.size() <= MAX_HOLES, "too many control wires for one gate");
+    Holes holes = make_holes(cpos.data(), (int)cpos.size(), 1);
+    const uint64_t n_elems = 1ull << (sv.n - 1 - (int)cpos.size());
+    MatP<T, 1> m;
+    for (int j = 0; j < 4; ++j) {
+        m.re[j] = (T)g.mat[j].real();
+        m.im[j] = (T)g.mat[j].imag();
+    }
+    constexpr int U = 4, NT = 256;
+    dim3 grid(grid_for(n_elems, (uint64_t)NT * U), (unsigned)n_vecs);
+    k_apply_dense_bit0<T, U, NT><<<grid, NT, 0, sv.stream>>>(table ? nullptr : sv.data, table, n_elems, holes,
+                                                            g.ctrl_mask >> 1, m);
+    QSV_CUDA(cudaGetLastError());
+}
+
+template <typename T>
 void launch_dense_large(State &sv, const LoweredGate &g, void *const *table, int n_vecs) {
     const int k = g.k;
     QSV_CHECK(k <= 10, "dense gates on more than 10 target wires are not supported");
@@ -317,6 +385,13 @@ void launch_any(State &sv, const LoweredGate &g, void *const *table, int n_vecs)
             return;
         }
         const bool bit0 = !g.holes.empty() && g.holes[0] == 0;
+        if (g.k == 1 && g.offs[0] == 0 && g.offs[1] == 1 && sv.n >= 2) {
+            if (f32)
+                launch_dense_bit0<float>(sv, g, table, n_vecs);
+            else
+                launch_dense_bit0<double>(sv, g, table, n_vecs);
+            return;
+        }
         if (!f32)
             launch_dense_k<double, 1>(sv, g, table, n_vecs);
         else if (bit0 || sv.n < 1)
