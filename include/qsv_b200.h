@@ -183,6 +183,9 @@ int qsv_dist_allreduce_f64(qsv_state *local, double *host_values, int count);
 /* NVLink bytes sent by this rank and device milliseconds of the last exchange / of all exchanges */
 int qsv_dist_last_swap_stats(const qsv_state *local, uint64_t *bytes_sent, float *ms);
 int qsv_dist_total_swap_stats(qsv_state *local, int *n_swaps, uint64_t *bytes_sent, float *ms, int reset);
+/* 1 when the exchanges run as direct NVLink load/store kernels on CUDA-IPC peer mappings (the default; NCCL
+ * then only carries the handshakes), 0 when they fall back to staged NCCL send/recv (QSV_DIST_P2P=0) */
+int qsv_dist_uses_peer_access(const qsv_state *local);
 /* host-only (no GPU, no NCCL): the exchanges qsv_dist_apply_ops would perform.  steps receives triples
  * (kind, a, b): kind 0 = swap physical global bit a with local bit b, kind 1 = apply op number a */
 int qsv_dist_plan(const qsv_ops *ops, int n_total, int n_local, int *steps, int max_steps, int *n_steps,

@@ -93,6 +93,7 @@ SIGNATURES = {
     "qsv_dist_last_swap_stats": (_I, [_P, _U64P, C.POINTER(C.c_float)]),
     "qsv_dist_total_swap_stats": (_I, [_P, _IP, _U64P, C.POINTER(C.c_float), _I]),
     "qsv_dist_plan": (_I, [_P, _I, _I, _IP, _I, _IP, _IP]),
+    "qsv_dist_uses_peer_access": (_I, [_P]),
 }
 
 

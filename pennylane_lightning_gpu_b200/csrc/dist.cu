@@ -43,7 +43,15 @@ struct DistCtx {
     float last_ms = 0.f, total_ms = 0.f;
     int n_swaps = 0;
     double *red_dev = nullptr;
+    // direct peer access (CUDA IPC): the partner's shard mapped into this process
+    bool p2p = false;
+    void *registered = nullptr;            // sv.data at registration time
+    std::vector<void *> peer;              // peer[r] = rank r's shard, mapped here (null for r == rank)
+    std::vector<void *> peer_map_base;     // what cudaIpcOpenMemHandle returned (for closing)
+    int *hs_dev = nullptr;                 // 2 ints for the handshakes
 };
+
+void setup_peer_access(State &sv);
 
 namespace {
 
@@ -166,6 +174,77 @@ void ensure_stage(State &sv, size_t bytes) {
     d.stage_bytes = bytes;
 }
 
+// In-place exchange with the partner GPU through its peer-mapped shard (NVLink load/store, no staging):
+//     mine[idx with bit l = !a]  <->  partner[idx with bit l = a]        (a = this rank's value of the global bit)
+// Each GPU of the pair runs this kernel on one half of the index range, so both NVLink directions carry
+// half of the traffic as remote loads of one kernel and half as remote stores of the other.
+template <int U>
+__global__ void __launch_bounds__(256)
+    k_peer_swap(uint4 *__restrict__ mine, uint4 *__restrict__ theirs, uint64_t first, uint64_t count, int l_vec,
+                uint64_t my_bit_vec, uint64_t their_bit_vec) {
+    // indices are in 16-byte units; l_vec is the position of the swapped bit in those units
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * U;
+    const uint64_t low = (1ull << l_vec) - 1ull;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 * U + threadIdx.x; i0 < count; i0 += stride) {
+        uint4 a[U], b[U];
+        uint64_t im[U], it[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = first + i0 + (uint64_t)u * 256;
+            const uint64_t e = ((i >> l_vec) << (l_vec + 1)) | (i & low);
+            im[u] = e | my_bit_vec;
+            it[u] = e | their_bit_vec;
+            if (i0 + (uint64_t)u * 256 < count) {
+                a[u] = mine[im[u]];
+                b[u] = theirs[it[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + (uint64_t)u * 256 < count) {
+                mine[im[u]] = b[u];
+                theirs[it[u]] = a[u];
+            }
+        }
+    }
+}
+
+void handshake(State &sv, int peer) {
+    DistCtx &d = *sv.dist;
+    QSV_NCCL(ncclGroupStart());
+    QSV_NCCL(ncclSend(d.hs_dev, 1, ncclInt, peer, d.comm, sv.stream));
+    QSV_NCCL(ncclRecv(d.hs_dev + 1, 1, ncclInt, peer, d.comm, sv.stream));
+    QSV_NCCL(ncclGroupEnd());
+}
+
+void swap_p2p(State &sv, int gphys, int l) {
+    DistCtx &d = *sv.dist;
+    const int n_local = sv.n;
+    const int gb = gphys - n_local;
+    const int peer = d.rank ^ (1 << gb);
+    const uint64_t a = (d.rank >> gb) & 1;
+    QSV_CHECK(sv.data == d.registered, "the shard was re-allocated after qsv_dist_init; peer mappings are stale");
+    // 16-byte units: complex128 = 1 unit, complex64 = half a unit (two amplitudes per unit, so l >= 1)
+    const int shift = sv.dtype == QSV_C128 ? 0 : 1;
+    QSV_CHECK(l >= shift, "internal: cannot swap index bit 0 of a complex64 shard through 16-byte units");
+    const int l_vec = l - shift;
+    const uint64_t pairs = (sv.length() >> shift) >> 1;  // 16-byte units in the exchanged half
+    const uint64_t half = pairs / 2;
+    const uint64_t first = a == 0 ? 0 : half;
+    const uint64_t count = a == 0 ? half : pairs - half;
+    QSV_CUDA(cudaEventRecord(d.ev_t0, sv.stream));
+    handshake(sv, peer);  // the partner has finished everything queued before its own handshake
+    if (count > 0) {
+        constexpr int U = 4;
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), 148 * 16));
+        k_peer_swap<U><<<grid, 256, 0, sv.stream>>>((uint4 *)sv.data, (uint4 *)d.peer[peer], first, count, l_vec,
+                                                    (a ^ 1) << l_vec, a << l_vec);
+        QSV_CUDA(cudaGetLastError());
+    }
+    handshake(sv, peer);  // the partner's kernel has finished writing into this shard
+    QSV_CUDA(cudaEventRecord(d.ev_t1, sv.stream));
+}
+
 }  // namespace
 
 // physical swap of global bit gphys (>= n_local) with local bit l
@@ -179,6 +258,18 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     const int peer = d.rank ^ (1 << gb);
     const int mybit = (d.rank >> gb) & 1;
     const size_t ab = sv.amp_bytes();
+    if (d.p2p && !(sv.dtype == QSV_C64 && l == 0)) {
+        swap_p2p(sv, gphys, l);
+        QSV_CUDA(cudaEventSynchronize(d.ev_t1));
+        float ms = 0.f;
+        QSV_CUDA(cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
+        d.last_ms = ms;
+        d.last_bytes = (uint64_t)(sv.length() / 2) * ab;
+        d.total_ms += ms;
+        d.total_bytes += d.last_bytes;
+        d.n_swaps += 1;
+        return;
+    }
     const uint64_t block_amps = 1ull << l;
     const uint64_t n_blocks = 1ull << (n_local - 1 - l);
     if (chunk_bytes == 0) chunk_bytes = (size_t)256 << 20;
@@ -388,9 +479,79 @@ void dist_free(State &sv) {
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->red_dev) cudaFree(d->red_dev);
+    if (d->hs_dev) cudaFree(d->hs_dev);
+    for (void *p : d->peer_map_base)
+        if (p) cudaIpcCloseMemHandle(p);
     delete d;
     sv.dist = nullptr;
     sv.index_hi = 0;
+}
+
+}  // namespace qsv
+
+namespace qsv {
+
+// Map every other rank's shard into this process with CUDA IPC.  The handles travel through NCCL itself
+// (all-gather of 80 bytes per rank), so no other rendezvous is needed.  Falls back to the NCCL
+// send/recv exchange (all ranks together) when any mapping fails.
+void setup_peer_access(State &sv) {
+    DistCtx &d = *sv.dist;
+    struct Msg {
+        cudaIpcMemHandle_t handle;
+        uint64_t offset;
+        uint64_t ok;
+    };
+    static_assert(sizeof(Msg) == 80, "IPC message layout");
+    Msg mine;
+    memset(&mine, 0, sizeof(mine));
+    // base of the allocation that contains the shard (the shard may be a view into a torch block)
+    typedef int (*GetRangeFn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    unsigned long long base = 0;
+    size_t size = 0;
+    bool ok = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr &&
+              ((GetRangeFn)fn)(&base, &size, (unsigned long long)(uintptr_t)sv.data) == 0;
+    if (ok) ok = cudaIpcGetMemHandle(&mine.handle, (void *)(uintptr_t)base) == cudaSuccess;
+    cudaGetLastError();
+    mine.offset = ok ? (uint64_t)((uintptr_t)sv.data - base) : 0;
+    mine.ok = ok ? 1 : 0;
+    Msg *dev = nullptr;
+    QSV_CUDA(cudaMalloc(&dev, sizeof(Msg) * (size_t)d.world));
+    QSV_CUDA(cudaMemcpyAsync(dev + d.rank, &mine, sizeof(Msg), cudaMemcpyHostToDevice, sv.stream));
+    QSV_NCCL(ncclAllGather(dev + d.rank, dev, sizeof(Msg), ncclChar, d.comm, sv.stream));
+    std::vector<Msg> all(d.world);
+    QSV_CUDA(cudaMemcpyAsync(all.data(), dev, sizeof(Msg) * (size_t)d.world, cudaMemcpyDeviceToHost, sv.stream));
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    QSV_CUDA(cudaFree(dev));
+    bool all_ok = true;
+    for (const Msg &m : all) all_ok = all_ok && m.ok == 1;
+    d.peer.assign(d.world, nullptr);
+    d.peer_map_base.assign(d.world, nullptr);
+    int mapped_ok = all_ok ? 1 : 0;
+    if (all_ok) {
+        for (int r = 0; r < d.world && mapped_ok; ++r) {
+            if (r == d.rank) continue;
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                mapped_ok = 0;
+                break;
+            }
+            d.peer_map_base[r] = p;
+            d.peer[r] = (char *)p + all[r].offset;
+        }
+    }
+    // agree on the outcome
+    int *flag = nullptr;
+    QSV_CUDA(cudaMalloc(&flag, sizeof(int)));
+    QSV_CUDA(cudaMemcpyAsync(flag, &mapped_ok, sizeof(int), cudaMemcpyHostToDevice, sv.stream));
+    QSV_NCCL(ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, d.comm, sv.stream));
+    QSV_CUDA(cudaMemcpyAsync(&mapped_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, sv.stream));
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    QSV_CUDA(cudaFree(flag));
+    d.p2p = mapped_ok == 1;
+    d.registered = sv.data;
 }
 
 }  // namespace qsv
@@ -452,8 +613,12 @@ int qsv_dist_init(qsv_state *sv, const void *id128, int rank, int world_size) {
     QSV_CUDA(cudaEventCreate(&d->ev_t0));
     QSV_CUDA(cudaEventCreate(&d->ev_t1));
     QSV_CUDA(cudaMalloc(&d->red_dev, 4096 * sizeof(double)));
+    QSV_CUDA(cudaMalloc(&d->hs_dev, 2 * sizeof(int)));
+    QSV_CUDA(cudaMemset(d->hs_dev, 0, 2 * sizeof(int)));
     sv->index_hi = (uint64_t)rank << sv->n;
     sv->dist = d.release();
+    const char *p2p_env = std::getenv("QSV_DIST_P2P");
+    if (world_size > 1 && !(p2p_env && std::atoi(p2p_env) == 0)) setup_peer_access(*sv);
     QSV_API_END
 }
 
@@ -544,6 +709,8 @@ int qsv_dist_last_swap_stats(const qsv_state *sv, uint64_t *bytes_sent, float *m
     if (ms) *ms = sv->dist->last_ms;
     QSV_API_END
 }
+
+int qsv_dist_uses_peer_access(const qsv_state *sv) { return sv && sv->dist && sv->dist->p2p ? 1 : 0; }
 
 int qsv_dist_total_swap_stats(qsv_state *sv, int *n_swaps, uint64_t *bytes_sent, float *ms, int reset) {
     QSV_API_BEGIN

@@ -76,6 +76,10 @@ class DistributedStateVector:
         _check(lib().qsv_dist_total_swap_stats(self.local._h, C.byref(n), C.byref(b), C.byref(ms), int(reset)))
         return n.value, b.value, ms.value
 
+    @property
+    def uses_peer_access(self) -> bool:
+        return bool(lib().qsv_dist_uses_peer_access(self.local._h))
+
     def qubit_map(self):
         m = (C.c_int * self.n_total)()
         _check(lib().qsv_dist_qubit_map(self.local._h, m, self.n_total))
