@@ -178,6 +178,35 @@ int qsv_dist_qubit_map(const qsv_state *local, int *phys_of_logical_bit, int n_t
 /* getExpectationValuePauliWords on a sharded register (MPI.hpp:1296-1445): local reduction + all-reduce */
 int qsv_dist_expval_pauli_words(qsv_state *local, int n_terms, const char *letters, const int *wires,
                                 const int *offsets, const double *coeffs_re_im, double *per_term, double *out);
+/* setBasisState / setStateVector on the sharded register (MPI.hpp:332-381): indices address the whole register; the
+ * qubit map is reset to the identity; every rank passes the same arguments and keeps the amplitudes of its shard */
+int qsv_dist_set_basis_state(qsv_state *local, uint64_t index);
+int qsv_dist_set_state_vector(qsv_state *local, const int64_t *indices, const void *values, size_t count);
+/* expval(name, wires, ...) / expval(wires, matrix) on the sharded register (MPI.hpp:957-1035): target qubits are made
+ * local, local reduction + all-reduce; out = {re, im}, identical on all ranks */
+int qsv_dist_expval_named(qsv_state *local, const char *name, const int *wires, int n_wires, const double *params,
+                          int n_params, double *out_re_im);
+int qsv_dist_expval_matrix(qsv_state *local, const double *matrix_re_im, const int *wires, int n_wires, double *out_re_im);
+/* getExpectationValueOnSparseSpMV on the sharded register (MPI.hpp:1050-1176, util/CSRMatrix.hpp:91-216): every rank
+ * passes the whole CSR matrix (int64 indices) and uploads only its own row block; x is gathered from the other
+ * shards over NVLink through their peer mappings (all-gather fallback without peer access) */
+int qsv_dist_expval_csr(qsv_state *local, const int64_t *row_offsets, const int64_t *col_indices,
+                        const double *values_re_im, int64_t nnz, double *out);
+/* probability(wires) on the sharded register (MPI.hpp:1187-1290); same output convention as qsv_probs */
+int qsv_dist_probs(qsv_state *local, const int *wires, int n_wires, double *out);
+/* generate_samples on the sharded register (MPI.hpp:1454-1595): same definition as qsv_sample over the amplitude order
+ * of the whole register; out[shot * n_total + w], identical on all ranks */
+int qsv_dist_sample(qsv_state *local, const double *uniforms, int64_t shots, uint64_t *out);
+/* ObservableGPUMPI<T> family (algorithms/ObservablesGPUMPI.hpp): wires of the observable address the whole register */
+int qsv_dist_obs_expval(const qsv_obs *obs, qsv_state *local, double *out);
+int qsv_dist_obs_apply(const qsv_obs *obs, qsv_state *local);
+/* AdjointJacobianGPUMPI::adjointJacobian (algorithms/AdjointDiffGPUMPI.hpp:248-437): lambda and the bras are sharded
+ * like the register and follow every exchange; one all-reduce of the Jacobian at the end; jac identical on all ranks */
+int qsv_dist_adjoint_jacobian(qsv_state *local, const qsv_ops *ops, qsv_obs *const *observables, int n_obs,
+                              const int64_t *trainable, int n_trainable, int apply_operations, double *jac);
+int qsv_dist_rank(const qsv_state *local);
+int qsv_dist_world_size(const qsv_state *local);
+int qsv_dist_total_qubits(const qsv_state *local);
 /* MPI_Allreduce(sum) of small host vectors (MPI.hpp:1176, :1426, :2361): ncclAllReduce on a device buffer */
 int qsv_dist_allreduce_f64(qsv_state *local, double *host_values, int count);
 /* NVLink bytes sent by this rank and device milliseconds of the last exchange / of all exchanges */

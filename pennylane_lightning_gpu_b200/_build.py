@@ -29,6 +29,23 @@ NVCC_FLAGS = [
 ]
 
 
+def _nccl_dirs() -> tuple[str | None, str | None]:
+    """(include dir, lib dir) of the NCCL that PyTorch itself loads (the `nvidia-nccl` wheel): linking the same
+    libnccl.so.2 keeps one NCCL in the process whichever of torch / libqsv_b200 is loaded first; the system libnccl
+    is the fallback."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            lib, inc = os.path.join(base, "lib"), os.path.join(base, "include")
+            if os.path.exists(os.path.join(lib, "libnccl.so.2")) and os.path.exists(os.path.join(inc, "nccl.h")):
+                return inc, lib
+    except Exception:
+        pass
+    return None, None
+
+
 def _newer(target: str, deps: list[str]) -> bool:
     if not os.path.exists(target):
         return True
@@ -53,18 +70,21 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     jobs = []
     objs = []
+    nccl_inc, nccl_lib = _nccl_dirs()
     for s in sources:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJDIR, s[:-3] + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
-            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + NVCC_FLAGS + (["-I", nccl_inc] if nccl_inc else []) + \
+                (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(_run, jobs))
     if jobs or not os.path.exists(LIB):
-        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lnccl"])
+        link = ["-L", nccl_lib, "-l:libnccl.so.2", "-Xlinker", "-rpath=" + nccl_lib] if nccl_lib else ["-lnccl"]
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + link)
     return LIB
 
 

@@ -94,6 +94,19 @@ SIGNATURES = {
     "qsv_dist_total_swap_stats": (_I, [_P, _IP, _U64P, C.POINTER(C.c_float), _I]),
     "qsv_dist_plan": (_I, [_P, _I, _I, _IP, _I, _IP, _IP]),
     "qsv_dist_uses_peer_access": (_I, [_P]),
+    "qsv_dist_set_basis_state": (_I, [_P, C.c_uint64]),
+    "qsv_dist_set_state_vector": (_I, [_P, _I64P, _P, C.c_size_t]),
+    "qsv_dist_expval_named": (_I, [_P, C.c_char_p, _IP, _I, _DP, _I, _DP]),
+    "qsv_dist_expval_matrix": (_I, [_P, _DP, _IP, _I, _DP]),
+    "qsv_dist_expval_csr": (_I, [_P, _I64P, _I64P, _DP, C.c_int64, _DP]),
+    "qsv_dist_probs": (_I, [_P, _IP, _I, _DP]),
+    "qsv_dist_sample": (_I, [_P, _DP, C.c_int64, _U64P]),
+    "qsv_dist_obs_expval": (_I, [_P, _P, _DP]),
+    "qsv_dist_obs_apply": (_I, [_P, _P]),
+    "qsv_dist_adjoint_jacobian": (_I, [_P, _P, C.POINTER(_P), _I, _I64P, _I, _I, _DP]),
+    "qsv_dist_rank": (_I, [_P]),
+    "qsv_dist_world_size": (_I, [_P]),
+    "qsv_dist_total_qubits": (_I, [_P]),
 }
 
 

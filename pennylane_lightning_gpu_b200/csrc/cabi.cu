@@ -10,11 +10,6 @@ const std::string &last_error_ref();
 
 using namespace qsv;
 
-struct qsv_state : State {};
-struct qsv_ops : Ops {};
-struct qsv_obs {
-    std::shared_ptr<Obs> p;
-};
 
 #define QSV_API_BEGIN try {
 #define QSV_API_END                                                                                \

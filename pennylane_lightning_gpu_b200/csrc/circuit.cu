@@ -17,27 +17,6 @@
 
 namespace qsv {
 
-namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    explicit DevBuf(size_t bytes) { QSV_CUDA(cudaMalloc(&p, bytes)); }
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-};
-
-LoweredGate lower_op(const State &sv, const Op &op, bool extra_adjoint) {
-    const bool adj = op.inverse != extra_adjoint;
-    if (find_gate(op.name) != nullptr) return lower_named(sv.n, op.name, op.wires, op.params, adj);
-    if (op.matrix.empty()) fail("Currently unsupported gate: " + op.name);
-    const size_t dim = 1ull << op.wires.size();
-    QSV_CHECK(op.matrix.size() == dim * dim, "matrix of gate " + op.name + " does not match its wires");
-    return lower_matrix(sv.n, op.matrix.data(), {}, op.wires, adj);
-}
-
 // Pauli word view of an observable: Named X/Y/Z/Identity or a tensor product of those on
 // distinct wires
 bool as_pauli_word(const Obs &o, int n, uint64_t &x, uint64_t &z, int &ny) {
@@ -82,6 +61,27 @@ bool hamiltonian_of_pauli_words(const Obs &o, int n, std::vector<uint64_t> &xs, 
         cf.push_back(ph * o.coeffs[t]);
     }
     return true;
+}
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t bytes) { QSV_CUDA(cudaMalloc(&p, bytes)); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+LoweredGate lower_op(const State &sv, const Op &op, bool extra_adjoint) {
+    const bool adj = op.inverse != extra_adjoint;
+    if (find_gate(op.name) != nullptr) return lower_named(sv.n, op.name, op.wires, op.params, adj);
+    if (op.matrix.empty()) fail("Currently unsupported gate: " + op.name);
+    const size_t dim = 1ull << op.wires.size();
+    QSV_CHECK(op.matrix.size() == dim * dim, "matrix of gate " + op.name + " does not match its wires");
+    return lower_matrix(sv.n, op.matrix.data(), {}, op.wires, adj);
 }
 
 struct CsrDev {

@@ -29,6 +29,14 @@ namespace qsv {
             ::qsv::fail(std::string("NCCL error: ") + ncclGetErrorString(r__) + " in " #expr);      \
     } while (0)
 
+// a device buffer of shard size together with its CUDA-IPC mappings on every other rank
+struct PeerBuf {
+    void *local = nullptr;
+    std::vector<void *> peer;      // peer[r] = rank r's buffer mapped here (local for r == rank)
+    std::vector<void *> map_base;  // what cudaIpcOpenMemHandle returned (for closing)
+    bool ok = false;
+};
+
 struct DistCtx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, n_total = 0, n_global = 0;
@@ -43,13 +51,25 @@ struct DistCtx {
     float last_ms = 0.f, total_ms = 0.f;
     int n_swaps = 0;
     double *red_dev = nullptr;
-    // direct peer access (CUDA IPC): the partner's shard mapped into this process
+    // direct peer access (CUDA IPC): the partners' shards mapped into this process
     bool p2p = false;
-    void *registered = nullptr;            // sv.data at registration time
-    std::vector<void *> peer;              // peer[r] = rank r's shard, mapped here (null for r == rank)
-    std::vector<void *> peer_map_base;     // what cudaIpcOpenMemHandle returned (for closing)
+    PeerBuf main;                          // the register's own shard (sv.data at registration time)
     int *hs_dev = nullptr;                 // 2 ints for the handshakes
+    // companions: further vectors of shard size that share the qubit map and therefore follow every exchange
+    // (lambda and the bras of the adjoint method, temporaries of observables)
+    struct Companion {
+        void *data;
+        PeerBuf pb;
+    };
+    std::vector<Companion> comp;
+    bool skip_main = false;                // adjoint sweep: the register itself stays where it is
+    void **tab_dev = nullptr;              // device table of vector pointers for batched launches
+    std::vector<void *> tab_cache;
 };
+
+void setup_peer_access(State &sv);
+PeerBuf register_peer_buffer(State &sv, void *data);
+void release_peer_buffer(PeerBuf &pb);
 
 void setup_peer_access(State &sv);
 
@@ -217,13 +237,25 @@ void handshake(State &sv, int peer) {
     QSV_NCCL(ncclGroupEnd());
 }
 
-void swap_p2p(State &sv, int gphys, int l) {
+// the vectors an exchange has to move: the register (unless frozen) and every companion
+struct SwapItem {
+    char *data;
+    const PeerBuf *pb;
+};
+std::vector<SwapItem> swap_set(State &sv) {
+    DistCtx &d = *sv.dist;
+    std::vector<SwapItem> v;
+    if (!d.skip_main) v.push_back({(char *)sv.data, &d.main});
+    for (auto &c : d.comp) v.push_back({(char *)c.data, &c.pb});
+    return v;
+}
+
+void swap_p2p(State &sv, const std::vector<SwapItem> &items, int gphys, int l) {
     DistCtx &d = *sv.dist;
     const int n_local = sv.n;
     const int gb = gphys - n_local;
     const int peer = d.rank ^ (1 << gb);
     const uint64_t a = (d.rank >> gb) & 1;
-    QSV_CHECK(sv.data == d.registered, "the shard was re-allocated after qsv_dist_init; peer mappings are stale");
     // 16-byte units: complex128 = 1 unit, complex64 = half a unit (two amplitudes per unit, so l >= 1)
     const int shift = sv.dtype == QSV_C128 ? 0 : 1;
     QSV_CHECK(l >= shift, "internal: cannot swap index bit 0 of a complex64 shard through 16-byte units");
@@ -237,17 +269,19 @@ void swap_p2p(State &sv, int gphys, int l) {
     if (count > 0) {
         constexpr int U = 4;
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), 148 * 16));
-        k_peer_swap<U><<<grid, 256, 0, sv.stream>>>((uint4 *)sv.data, (uint4 *)d.peer[peer], first, count, l_vec,
-                                                    (a ^ 1) << l_vec, a << l_vec);
-        QSV_CUDA(cudaGetLastError());
+        for (const SwapItem &it : items) {
+            k_peer_swap<U><<<grid, 256, 0, sv.stream>>>((uint4 *)it.data, (uint4 *)it.pb->peer[peer], first, count, l_vec,
+                                                        (a ^ 1) << l_vec, a << l_vec);
+            QSV_CUDA(cudaGetLastError());
+        }
     }
-    handshake(sv, peer);  // the partner's kernel has finished writing into this shard
+    handshake(sv, peer);  // the partner's kernels have finished writing into this rank's vectors
     QSV_CUDA(cudaEventRecord(d.ev_t1, sv.stream));
 }
 
 }  // namespace
 
-// physical swap of global bit gphys (>= n_local) with local bit l
+// physical swap of global bit gphys (>= n_local) with local bit l, applied to the register and its companions
 void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     sv.use();
     QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
@@ -258,13 +292,19 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     const int peer = d.rank ^ (1 << gb);
     const int mybit = (d.rank >> gb) & 1;
     const size_t ab = sv.amp_bytes();
-    if (d.p2p && !(sv.dtype == QSV_C64 && l == 0)) {
-        swap_p2p(sv, gphys, l);
+    const std::vector<SwapItem> items = swap_set(sv);
+    if (items.empty()) return;
+    bool all_mapped = d.p2p && !(sv.dtype == QSV_C64 && l == 0);
+    for (const SwapItem &it : items) all_mapped = all_mapped && it.pb->ok;
+    if (!d.skip_main)
+        QSV_CHECK(!d.p2p || sv.data == d.main.local, "the shard was re-allocated after qsv_dist_init; peer mappings are stale");
+    if (all_mapped) {
+        swap_p2p(sv, items, gphys, l);
         QSV_CUDA(cudaEventSynchronize(d.ev_t1));
         float ms = 0.f;
         QSV_CUDA(cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
         d.last_ms = ms;
-        d.last_bytes = (uint64_t)(sv.length() / 2) * ab;
+        d.last_bytes = (uint64_t)(sv.length() / 2) * ab * items.size();
         d.total_ms += ms;
         d.total_bytes += d.last_bytes;
         d.n_swaps += 1;
@@ -281,22 +321,24 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     QSV_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
     QSV_CUDA(cudaEventRecord(d.ev_t0, d.comm_stream));
     uint64_t counter = 0;
-    char *base = (char *)sv.data;
-    for (uint64_t blk = 0; blk < n_blocks; ++blk) {
-        const uint64_t start = (blk << (l + 1)) | ((uint64_t)(mybit ^ 1) << l);
-        for (uint64_t off = 0; off < block_amps; off += chunk_amps, ++counter) {
-            const int k = (int)(counter & 1);
-            const size_t bytes = (size_t)std::min<uint64_t>(chunk_amps, block_amps - off) * ab;
-            char *ptr = base + (start + off) * ab;
-            if (counter >= 2) QSV_CUDA(cudaStreamWaitEvent(d.comm_stream, d.ev_copy[k], 0));
-            QSV_NCCL(ncclGroupStart());
-            QSV_NCCL(ncclSend(ptr, bytes, ncclChar, peer, d.comm, d.comm_stream));
-            QSV_NCCL(ncclRecv(d.stage[k], bytes, ncclChar, peer, d.comm, d.comm_stream));
-            QSV_NCCL(ncclGroupEnd());
-            QSV_CUDA(cudaEventRecord(d.ev_xfer[k], d.comm_stream));
-            QSV_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_xfer[k], 0));
-            QSV_CUDA(cudaMemcpyAsync(ptr, d.stage[k], bytes, cudaMemcpyDeviceToDevice, d.copy_stream));
-            QSV_CUDA(cudaEventRecord(d.ev_copy[k], d.copy_stream));
+    for (const SwapItem &it : items) {
+        char *base = it.data;
+        for (uint64_t blk = 0; blk < n_blocks; ++blk) {
+            const uint64_t start = (blk << (l + 1)) | ((uint64_t)(mybit ^ 1) << l);
+            for (uint64_t off = 0; off < block_amps; off += chunk_amps, ++counter) {
+                const int k = (int)(counter & 1);
+                const size_t bytes = (size_t)std::min<uint64_t>(chunk_amps, block_amps - off) * ab;
+                char *ptr = base + (start + off) * ab;
+                if (counter >= 2) QSV_CUDA(cudaStreamWaitEvent(d.comm_stream, d.ev_copy[k], 0));
+                QSV_NCCL(ncclGroupStart());
+                QSV_NCCL(ncclSend(ptr, bytes, ncclChar, peer, d.comm, d.comm_stream));
+                QSV_NCCL(ncclRecv(d.stage[k], bytes, ncclChar, peer, d.comm, d.comm_stream));
+                QSV_NCCL(ncclGroupEnd());
+                QSV_CUDA(cudaEventRecord(d.ev_xfer[k], d.comm_stream));
+                QSV_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_xfer[k], 0));
+                QSV_CUDA(cudaMemcpyAsync(ptr, d.stage[k], bytes, cudaMemcpyDeviceToDevice, d.copy_stream));
+                QSV_CUDA(cudaEventRecord(d.ev_copy[k], d.copy_stream));
+            }
         }
     }
     QSV_CUDA(cudaEventRecord(d.ev_t1, d.comm_stream));
@@ -307,7 +349,7 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     float ms = 0.f;
     QSV_CUDA(cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
     d.last_ms = ms;
-    d.last_bytes = (uint64_t)(sv.length() / 2) * ab;
+    d.last_bytes = (uint64_t)(sv.length() / 2) * ab * items.size();
     d.total_ms += ms;
     d.total_bytes += d.last_bytes;
     d.n_swaps += 1;
@@ -371,45 +413,6 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     flush();
 }
 
-// restore the identity qubit map (physical bit b holds logical bit b)
-void dist_canonicalize(State &sv, size_t chunk_bytes) {
-    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
-    DistCtx &d = *sv.dist;
-    const int n_local = sv.n;
-    // local-local permutations are done with SWAP gates, global ones with exchanges
-    for (int gp = n_local; gp < d.n_total; ++gp) {
-        if (d.log_of[gp] == gp) continue;
-        // logical qubit gp lives somewhere else: if it is global, first bring it local
-        int p = d.phys_of[gp];
-        if (p >= n_local) {
-            // find a local slot holding a qubit that is not a global-home qubit if possible
-            int l = n_local - 1;
-            swap_logical_in(sv, p, l, chunk_bytes);
-            p = d.phys_of[gp];
-        }
-        swap_logical_in(sv, gp, p, chunk_bytes);
-    }
-    // now all global positions are right; fix the local part with local SWAPs
-    for (int b = 0; b < n_local; ++b) {
-        while (d.log_of[b] != b) {
-            const int other = d.phys_of[b];  // where logical b currently sits (local)
-            // SWAP physical bits b and other
-            LoweredGate g;
-            g.kind = LoweredGate::DENSE;
-            g.k = 1;
-            g.holes = {std::min(b, other), std::max(b, other)};
-            g.offs = {1ull << b, 1ull << other};
-            g.mat = {0.0, 1.0, 1.0, 0.0};
-            launch_gate(sv, g);
-            const int qa = d.log_of[b], qb = d.log_of[other];
-            d.log_of[b] = qb;
-            d.log_of[other] = qa;
-            d.phys_of[qa] = other;
-            d.phys_of[qb] = b;
-        }
-    }
-}
-
 void dist_allreduce(State &sv, double *host, int count) {
     sv.use();
     QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
@@ -462,6 +465,605 @@ void dist_expval_pauli(State &sv, int n_terms, const uint64_t *x_log, const uint
     if (out) *out = tot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Everything below: measurements, observables and the adjoint method on the sharded register
+// (StateVectorCudaMPI.hpp:957-1595, ObservablesGPUMPI.hpp, AdjointDiffGPUMPI.hpp:248-437 of the reference).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+void allreduce_vec(State &sv, double *host, size_t count) {
+    for (size_t off = 0; off < count; off += 4096) dist_allreduce(sv, host + off, (int)std::min<size_t>(4096, count - off));
+}
+
+// stream barrier across all ranks: everything queued before it on every rank has completed when it completes
+void stream_barrier(State &sv) {
+    DistCtx &d = *sv.dist;
+    QSV_NCCL(ncclAllReduce(d.hs_dev, d.hs_dev, 1, ncclInt, ncclMax, d.comm, sv.stream));
+}
+
+// make the logical qubits in `need` local; victims are local qubits outside `need`, highest physical bit first
+void dist_localize(State &sv, uint64_t need, size_t chunk_bytes) {
+    DistCtx &d = *sv.dist;
+    const int n_local = sv.n;
+    QSV_CHECK(__builtin_popcountll(need) <= n_local, "operation acts on more wires than a shard holds");
+    for (int lb = 0; lb < d.n_total; ++lb) {
+        if (!(need >> lb & 1) || d.phys_of[lb] < n_local) continue;
+        int best = -1;
+        for (int l = n_local - 1; l >= 0; --l)
+            if (!(need >> d.log_of[l] & 1)) {
+                best = l;
+                break;
+            }
+        QSV_CHECK(best >= 0, "no local qubit can be evicted");
+        swap_logical_in(sv, d.phys_of[lb], best, chunk_bytes);
+    }
+}
+
+// device table of vector pointers for launch_gate_multi (re-uploaded only when it changes)
+void *const *pointer_table(State &sv, const std::vector<void *> &vecs) {
+    DistCtx &d = *sv.dist;
+    QSV_CHECK(vecs.size() <= 256, "too many vectors in one batched launch");
+    if (!d.tab_dev) QSV_CUDA(cudaMalloc(&d.tab_dev, 256 * sizeof(void *)));
+    if (d.tab_cache != vecs) {
+        QSV_CUDA(cudaMemcpyAsync(d.tab_dev, vecs.data(), vecs.size() * sizeof(void *), cudaMemcpyHostToDevice, sv.stream));
+        d.tab_cache = vecs;
+    }
+    return d.tab_dev;
+}
+
+// gate given on LOGICAL bits of the whole register -> gate on this rank's shard (NOP when a global control is 0)
+LoweredGate dist_prepare_gate(State &sv, const LoweredGate &g, size_t chunk_bytes) {
+    DistCtx &d = *sv.dist;
+    if (g.kind == LoweredGate::NOP) return g;
+    if (g.kind == LoweredGate::DENSE) dist_localize(sv, touched_mask(g), chunk_bytes);
+    return localize_gate(remap_gate(g, d.phys_of), sv.n, sv.index_hi);
+}
+
+void dist_apply_gate(State &sv, const LoweredGate &g_logical, const std::vector<void *> &vecs, size_t chunk_bytes) {
+    const LoweredGate g = dist_prepare_gate(sv, g_logical, chunk_bytes);
+    if (g.kind == LoweredGate::NOP) return;
+    if (vecs.size() == 1 && vecs[0] == sv.data)
+        launch_gate(sv, g);
+    else
+        launch_gate_multi(sv, g, pointer_table(sv, vecs), (int)vecs.size());
+}
+
+// a shard-sized temporary that follows every exchange of the register (collective: all ranks create / destroy
+// their temporaries in the same order)
+struct TempVec {
+    State &sv;
+    void *data = nullptr;
+    TempVec(State &s, const void *copy_from) : sv(s) {
+        DistCtx &d = *sv.dist;
+        // at least 2 MiB: smaller cudaMalloc blocks are sub-allocated and would share one IPC handle
+        QSV_CUDA(cudaMalloc(&data, std::max<size_t>(sv.bytes(), (size_t)2 << 20)));
+        if (copy_from)
+            QSV_CUDA(cudaMemcpyAsync(data, copy_from, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        else
+            QSV_CUDA(cudaMemsetAsync(data, 0, sv.bytes(), sv.stream));
+        DistCtx::Companion c;
+        c.data = data;
+        if (d.p2p) c.pb = register_peer_buffer(sv, data);
+        d.comp.push_back(std::move(c));
+    }
+    ~TempVec() {
+        DistCtx &d = *sv.dist;
+        cudaStreamSynchronize(sv.stream);
+        for (size_t i = 0; i < d.comp.size(); ++i)
+            if (d.comp[i].data == data) {
+                release_peer_buffer(d.comp[i].pb);
+                d.comp.erase(d.comp.begin() + i);
+                break;
+            }
+        d.tab_cache.clear();
+        cudaFree(data);
+    }
+    TempVec(const TempVec &) = delete;
+    TempVec &operator=(const TempVec &) = delete;
+};
+
+const PeerBuf *peer_buf_of(State &sv, const void *data) {
+    DistCtx &d = *sv.dist;
+    if (data == sv.data) return &d.main;
+    for (auto &c : d.comp)
+        if (c.data == data) return &c.pb;
+    return nullptr;
+}
+
+void canonicalize_all(State &sv, size_t chunk_bytes);
+
+// rows [rank * 2^n_local, (rank + 1) * 2^n_local) of a CSR matrix on the device, offsets rebased to 0
+struct CsrBlock {
+    void *indptr = nullptr, *indices = nullptr, *values = nullptr;
+    int64_t nnz = 0;
+    CsrBlock(State &sv, const int64_t *indptr_h, const int64_t *indices_h, const cplx *values_h) {
+        DistCtx &d = *sv.dist;
+        const int64_t rows = (int64_t)sv.length();
+        const int64_t r0 = (int64_t)d.rank * rows;
+        const int64_t lo = indptr_h[r0];
+        nnz = indptr_h[r0 + rows] - lo;
+        std::vector<int64_t> ptr(rows + 1);
+        for (int64_t i = 0; i <= rows; ++i) ptr[i] = indptr_h[r0 + i] - lo;
+        QSV_CUDA(cudaMalloc(&indptr, (rows + 1) * 8));
+        QSV_CUDA(cudaMalloc(&indices, std::max<int64_t>(nnz, 1) * 8));
+        QSV_CUDA(cudaMalloc(&values, std::max<int64_t>(nnz, 1) * 16));
+        QSV_CUDA(cudaMemcpyAsync(indptr, ptr.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, sv.stream));
+        if (nnz) {
+            QSV_CUDA(cudaMemcpyAsync(indices, indices_h + lo, nnz * 8, cudaMemcpyHostToDevice, sv.stream));
+            QSV_CUDA(cudaMemcpyAsync(values, values_h + lo, nnz * 16, cudaMemcpyHostToDevice, sv.stream));
+        }
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));  // ptr goes out of scope
+    }
+    ~CsrBlock() {
+        cudaFree(indptr);
+        cudaFree(indices);
+        cudaFree(values);
+    }
+    CsrBlock(const CsrBlock &) = delete;
+    CsrBlock &operator=(const CsrBlock &) = delete;
+};
+
+// y (may be null) = H x restricted to this rank's rows and / or accumulate <x|Hx> (local part) into red[0..1].
+// The register must be in the canonical layout.  x is gathered from the other ranks' shards over NVLink through
+// their peer mappings; without peer access the whole vector is all-gathered first (small registers only).
+void dist_csr(State &sv, const void *x, void *y, const int64_t *indptr_h, const int64_t *indices_h, const cplx *values_h,
+              double *red) {
+    DistCtx &d = *sv.dist;
+    const int64_t rows = (int64_t)sv.length();
+    CsrBlock blk(sv, indptr_h, indices_h, values_h);
+    const PeerBuf *pb = peer_buf_of(sv, x);
+    if (d.p2p && pb && pb->ok) {
+        void **tab = nullptr;
+        QSV_CUDA(cudaMalloc(&tab, d.world * sizeof(void *)));
+        QSV_CUDA(cudaMemcpyAsync(tab, pb->peer.data(), d.world * sizeof(void *), cudaMemcpyHostToDevice, sv.stream));
+        stream_barrier(sv);  // every rank's x is complete
+        launch_csr_sharded(sv, tab, sv.n, x, y, blk.indptr, blk.indices, blk.values, rows, blk.nnz, 8, red, 0);
+        stream_barrier(sv);  // nobody reads this rank's x any more
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));
+        QSV_CUDA(cudaFree(tab));
+        return;
+    }
+    void *full = nullptr;
+    QSV_CHECK(d.n_total <= 30, "sparse Hamiltonians on a sharded register need peer access between the GPUs");
+    QSV_CUDA(cudaMalloc(&full, sv.bytes() * (size_t)d.world));
+    QSV_NCCL(ncclAllGather(x, full, sv.bytes(), ncclChar, d.comm, sv.stream));
+    void **tab = nullptr;
+    std::vector<void *> ptrs(d.world);
+    for (int r = 0; r < d.world; ++r) ptrs[r] = (char *)full + (size_t)r * sv.bytes();
+    QSV_CUDA(cudaMalloc(&tab, d.world * sizeof(void *)));
+    QSV_CUDA(cudaMemcpyAsync(tab, ptrs.data(), d.world * sizeof(void *), cudaMemcpyHostToDevice, sv.stream));
+    launch_csr_sharded(sv, tab, sv.n, x, y, blk.indptr, blk.indices, blk.values, rows, blk.nnz, 8, red, 0);
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    QSV_CUDA(cudaFree(tab));
+    QSV_CUDA(cudaFree(full));
+}
+
+// target <- O target, where target is the register's shard or one of its companions
+void dist_apply_observable(State &sv, const Obs &o, void *target, size_t chunk_bytes) {
+    DistCtx &d = *sv.dist;
+    const int n_total = d.n_total;
+    switch (o.kind) {
+    case Obs::NAMED: {
+        if (o.name == "Identity") return;
+        Op op;
+        op.name = o.name;
+        op.wires = o.wires;
+        op.params = o.params;
+        op.matrix = o.matrix;
+        dist_apply_gate(sv, lower_op_total(n_total, op, false), {target}, chunk_bytes);
+        return;
+    }
+    case Obs::HERMITIAN: {
+        const size_t dim = 1ull << o.wires.size();
+        QSV_CHECK(o.matrix.size() == dim * dim, "Hermitian matrix does not match its wires");
+        dist_apply_gate(sv, lower_matrix(n_total, o.matrix.data(), {}, o.wires, false), {target}, chunk_bytes);
+        return;
+    }
+    case Obs::TENSOR:
+        for (const auto &c : o.children) dist_apply_observable(sv, *c, target, chunk_bytes);
+        return;
+    case Obs::HAMILTONIAN: {
+        std::vector<uint64_t> xs, zs;
+        std::vector<cplx> cf;
+        TempVec acc(sv, nullptr);
+        if (hamiltonian_of_pauli_words(o, n_total, xs, zs, cf)) {
+            // groups of terms whose X/Y letters are all on local qubits under one layout; each group is one
+            // gather launch accumulating into acc
+            const uint64_t hi_mask = ~((1ull << sv.n) - 1ull);
+            std::vector<char> left(xs.size(), 1);
+            size_t n_left = xs.size();
+            while (n_left) {
+                size_t first = 0;
+                while (!left[first]) ++first;
+                dist_localize(sv, xs[first], chunk_bytes);
+                std::vector<uint64_t> gx, gz;
+                std::vector<cplx> gc;
+                for (size_t t = first; t < xs.size(); ++t) {
+                    if (!left[t]) continue;
+                    const uint64_t x = remap_mask(xs[t], d.phys_of);
+                    if (x & hi_mask) continue;
+                    const uint64_t z = remap_mask(zs[t], d.phys_of);
+                    const double sgn = (__builtin_popcountll(sv.index_hi & z & hi_mask) & 1) ? -1.0 : 1.0;
+                    gx.push_back(x);
+                    gz.push_back(z & ~hi_mask);
+                    gc.push_back(sgn * cf[t]);
+                    left[t] = 0;
+                    --n_left;
+                }
+                launch_pauli_sum_apply(sv, target, acc.data, (int)gx.size(), gx.data(), gz.data(), gc.data(), true);
+            }
+        } else {
+            for (size_t i = 0; i < o.children.size(); ++i) {
+                TempVec tmp(sv, target);
+                dist_apply_observable(sv, *o.children[i], tmp.data, chunk_bytes);
+                launch_axpy(sv, cplx(o.coeffs[i], 0.0), tmp.data, acc.data);
+            }
+        }
+        QSV_CUDA(cudaMemcpyAsync(target, acc.data, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        return;
+    }
+    case Obs::SPARSE: {
+        QSV_CHECK(o.indptr.size() == (1ull << n_total) + 1, "sparse Hamiltonian dimension does not match the register");
+        canonicalize_all(sv, chunk_bytes);
+        TempVec y(sv, nullptr);
+        dist_csr(sv, target, y.data, o.indptr.data(), o.indices.data(), o.values.data(), nullptr);
+        QSV_CUDA(cudaMemcpyAsync(target, y.data, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        return;
+    }
+    }
+}
+
+// <sv| M |sv> for a dense / diagonal operator on logical bits: local part, not yet reduced
+void dist_expval_gate_local(State &sv, const LoweredGate &g_logical, double out[2], size_t chunk_bytes) {
+    out[0] = out[1] = 0.0;
+    const LoweredGate g = dist_prepare_gate(sv, g_logical, chunk_bytes);
+    if (g.kind == LoweredGate::NOP) return;
+    double *red = sv.reduction_buffer(2);
+    reduction_zero(sv, red, 2);
+    launch_bra_op_ket(sv, sv.data, sv.data, g, red, 0);
+    reduction_read(sv, red, out, 2);
+}
+
+}  // namespace
+
+// restore the identity qubit map for the register and its companions
+namespace {
+void canonicalize_all(State &sv, size_t chunk_bytes) {
+    DistCtx &d = *sv.dist;
+    const int n_local = sv.n;
+    for (int gp = n_local; gp < d.n_total; ++gp) {
+        if (d.log_of[gp] == gp) continue;
+        int p = d.phys_of[gp];
+        if (p >= n_local) {
+            swap_logical_in(sv, p, n_local - 1, chunk_bytes);
+            p = d.phys_of[gp];
+        }
+        swap_logical_in(sv, gp, p, chunk_bytes);
+    }
+    std::vector<void *> vecs;
+    if (!d.skip_main) vecs.push_back(sv.data);
+    for (auto &c : d.comp) vecs.push_back(c.data);
+    for (int b = 0; b < n_local; ++b) {
+        while (d.log_of[b] != b) {
+            const int other = d.phys_of[b];
+            LoweredGate g;
+            g.kind = LoweredGate::DENSE;
+            g.k = 1;
+            g.holes = {std::min(b, other), std::max(b, other)};
+            g.offs = {1ull << b, 1ull << other};
+            g.mat = {0.0, 1.0, 1.0, 0.0};
+            if (vecs.size() == 1 && vecs[0] == sv.data)
+                launch_gate(sv, g);
+            else if (!vecs.empty())
+                launch_gate_multi(sv, g, pointer_table(sv, vecs), (int)vecs.size());
+            const int qa = d.log_of[b], qb = d.log_of[other];
+            d.log_of[b] = qb;
+            d.log_of[other] = qa;
+            d.phys_of[qa] = other;
+            d.phys_of[qb] = b;
+        }
+    }
+}
+}  // namespace
+
+void dist_canonicalize(State &sv, size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    canonicalize_all(sv, chunk_bytes);
+}
+
+// Re <sv|O|sv> on the sharded register
+double dist_obs_expval(State &sv, const Obs &o, size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    DistCtx &d = *sv.dist;
+    const int n_total = d.n_total;
+    uint64_t x = 0, z = 0;
+    int ny = 0;
+    if (as_pauli_word(o, n_total, x, z, ny)) {
+        const double one[2] = {1.0, 0.0};
+        double out = 0;
+        dist_expval_pauli(sv, 1, &x, &z, &ny, one, nullptr, &out, chunk_bytes);
+        return out;
+    }
+    switch (o.kind) {
+    case Obs::NAMED:
+    case Obs::HERMITIAN: {
+        std::vector<cplx> m = o.matrix;
+        if (o.kind == Obs::NAMED && find_gate(o.name) != nullptr) m = named_gate_matrix(o.name, o.params, (int)o.wires.size());
+        QSV_CHECK(!m.empty(), "Currently unsupported observable: " + o.name);
+        const size_t dim = 1ull << o.wires.size();
+        QSV_CHECK(m.size() == dim * dim, "observable matrix does not match its wires");
+        double h[2];
+        dist_expval_gate_local(sv, lower_matrix(n_total, m.data(), {}, o.wires, false), h, chunk_bytes);
+        allreduce_vec(sv, h, 2);
+        return h[0];
+    }
+    case Obs::HAMILTONIAN: {
+        std::vector<uint64_t> xs, zs;
+        std::vector<cplx> cf;
+        if (hamiltonian_of_pauli_words(o, n_total, xs, zs, cf)) {
+            // cf carries i^ny; dist_expval_pauli applies i^ny itself, so pass the plain coefficients
+            std::vector<int> nys(xs.size());
+            std::vector<double> c2(2 * xs.size(), 0.0);
+            for (size_t t = 0; t < xs.size(); ++t) {
+                nys[t] = __builtin_popcountll(xs[t] & zs[t]);
+                c2[2 * t] = o.coeffs[t];
+            }
+            double out = 0;
+            dist_expval_pauli(sv, (int)xs.size(), xs.data(), zs.data(), nys.data(), c2.data(), nullptr, &out, chunk_bytes);
+            return out;
+        }
+        double tot = 0;
+        for (size_t i = 0; i < o.children.size(); ++i) tot += o.coeffs[i] * dist_obs_expval(sv, *o.children[i], chunk_bytes);
+        return tot;
+    }
+    case Obs::TENSOR: {
+        TempVec tmp(sv, sv.data);
+        dist_apply_observable(sv, o, tmp.data, chunk_bytes);
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        LoweredGate id;
+        launch_bra_op_ket(sv, sv.data, tmp.data, id, red, 0);
+        double h[2];
+        reduction_read(sv, red, h, 2);
+        allreduce_vec(sv, h, 2);
+        return h[0];
+    }
+    case Obs::SPARSE: {
+        QSV_CHECK(o.indptr.size() == (1ull << n_total) + 1, "sparse Hamiltonian dimension does not match the register");
+        canonicalize_all(sv, chunk_bytes);
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        dist_csr(sv, sv.data, nullptr, o.indptr.data(), o.indices.data(), o.values.data(), red);
+        double h[2];
+        reduction_read(sv, red, h, 2);
+        allreduce_vec(sv, h, 2);
+        return h[0];
+    }
+    }
+    return 0.0;
+}
+
+void dist_obs_apply(State &sv, const Obs &o, size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    dist_apply_observable(sv, o, sv.data, chunk_bytes);
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+}
+
+void dist_expval_matrix(State &sv, const cplx *matrix, const std::vector<int> &wires, double out[2], size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    dist_expval_gate_local(sv, lower_matrix(sv.dist->n_total, matrix, {}, wires, false), out, chunk_bytes);
+    allreduce_vec(sv, out, 2);
+}
+
+// probability(wires) on the sharded register (MPI.hpp:1187-1290): local marginal over the measured qubits that are
+// local, placed at the output positions given by this rank's values of the measured global qubits, all-reduced.
+// out has 2^k entries, first listed wire = least significant bit (the reference's cuStateVec bit order).
+void dist_probs(State &sv, const std::vector<int> &wires, double *out) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    DistCtx &d = *sv.dist;
+    const int k = (int)wires.size();
+    QSV_CHECK(k >= 1 && k <= 26, "probability needs between 1 and 26 wires on a sharded register");
+    std::vector<int> local_bits, local_pos;
+    uint64_t fixed = 0;
+    for (int i = 0; i < k; ++i) {
+        QSV_CHECK(wires[i] >= 0 && wires[i] < d.n_total, "wire out of range");
+        for (int j = 0; j < i; ++j) QSV_CHECK(wires[i] != wires[j], "repeated wire in probability");
+        const int p = d.phys_of[d.n_total - 1 - wires[i]];
+        if (p < sv.n) {
+            local_bits.push_back(p);
+            local_pos.push_back(i);
+        } else if (sv.index_hi >> p & 1) {
+            fixed |= 1ull << i;
+        }
+    }
+    const size_t nb = 1ull << k;
+    std::vector<double> full(nb, 0.0);
+    if (local_bits.empty()) {
+        double *red = sv.reduction_buffer(2);
+        reduction_zero(sv, red, 2);
+        LoweredGate id;
+        launch_bra_op_ket(sv, sv.data, sv.data, id, red, 0);
+        double h[2];
+        reduction_read(sv, red, h, 2);
+        full[fixed] = h[0];
+    } else {
+        std::vector<double> loc(1ull << local_bits.size());
+        launch_probs(sv, local_bits, loc.data());
+        for (size_t t = 0; t < loc.size(); ++t) {
+            uint64_t idx = fixed;
+            for (size_t q = 0; q < local_pos.size(); ++q) idx |= (uint64_t)((t >> q) & 1) << local_pos[q];
+            full[idx] = loc[t];
+        }
+    }
+    allreduce_vec(sv, full.data(), nb);
+    for (size_t t = 0; t < nb; ++t) out[t] = full[t];
+}
+
+// generate_samples on the sharded register (MPI.hpp:1454-1595): the inverse CDF over the canonical amplitude
+// order, i.e. rank by rank; every rank samples the shots whose target mass falls into its own shard.
+// out[shot * n_total + w] = bit of wire w (identical on all ranks after the all-reduce).
+void dist_sample(State &sv, const double *uniforms, int64_t shots, uint64_t *out, size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    DistCtx &d = *sv.dist;
+    if (shots <= 0) return;
+    canonicalize_all(sv, chunk_bytes);
+    std::vector<double> mass(d.world, 0.0);
+    mass[d.rank] = state_mass(sv);
+    allreduce_vec(sv, mass.data(), d.world);
+    std::vector<double> cdf(d.world + 1, 0.0);
+    for (int r = 0; r < d.world; ++r) cdf[r + 1] = cdf[r] + mass[r];
+    const double total = cdf[d.world];
+    std::vector<int64_t> mine;
+    std::vector<double> targets;
+    for (int64_t s = 0; s < shots; ++s) {
+        const double t = uniforms[s] * total;
+        int r = (int)(std::upper_bound(cdf.begin() + 1, cdf.end(), t) - (cdf.begin() + 1));
+        if (r >= d.world) r = d.world - 1;
+        if (r == d.rank) {
+            mine.push_back(s);
+            targets.push_back(t - cdf[r]);
+        }
+    }
+    std::vector<uint64_t> idx(mine.size());
+    if (!mine.empty()) launch_sample_indices(sv, targets.data(), (int64_t)mine.size(), idx.data(), true);
+    const int n = d.n_total;
+    const size_t count = (size_t)shots * n;
+    for (size_t i = 0; i < count; ++i) out[i] = 0;
+    for (size_t q = 0; q < mine.size(); ++q) {
+        const uint64_t g = ((uint64_t)d.rank << sv.n) | idx[q];
+        for (int w = 0; w < n; ++w) out[mine[q] * n + w] = (g >> (n - 1 - w)) & 1ull;
+    }
+    uint64_t *dev = nullptr;
+    QSV_CUDA(cudaMalloc(&dev, count * sizeof(uint64_t)));
+    QSV_CUDA(cudaMemcpyAsync(dev, out, count * sizeof(uint64_t), cudaMemcpyHostToDevice, sv.stream));
+    QSV_NCCL(ncclAllReduce(dev, dev, count, ncclUint64, ncclSum, d.comm, sv.stream));
+    QSV_CUDA(cudaMemcpyAsync(out, dev, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, sv.stream));
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    QSV_CUDA(cudaFree(dev));
+}
+
+// setBasisState / setStateVector on the sharded register (MPI.hpp:332-381): indices address the whole register;
+// the qubit map is reset to the identity
+void dist_set_state(State &sv, const int64_t *indices, const void *values, size_t count) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    DistCtx &d = *sv.dist;
+    for (int b = 0; b < d.n_total; ++b) d.phys_of[b] = d.log_of[b] = b;
+    const size_t ab = sv.amp_bytes();
+    std::vector<int64_t> li;
+    std::vector<char> lv;
+    for (size_t i = 0; i < count; ++i) {
+        QSV_CHECK(indices[i] >= 0 && (uint64_t)indices[i] < (1ull << d.n_total), "state-vector index out of range");
+        if ((int)((uint64_t)indices[i] >> sv.n) != d.rank) continue;
+        li.push_back(indices[i] & (int64_t)(sv.length() - 1));
+        lv.insert(lv.end(), (const char *)values + i * ab, (const char *)values + (i + 1) * ab);
+    }
+    QSV_CUDA(cudaMemsetAsync(sv.data, 0, sv.bytes(), sv.stream));
+    if (!li.empty()) {
+        const size_t vb = li.size() * ab;
+        const size_t vb_al = (vb + 15) / 16 * 16;
+        char *scr = (char *)sv.scratch_buffer(vb_al + li.size() * 8);
+        QSV_CUDA(cudaMemcpyAsync(scr, lv.data(), vb, cudaMemcpyHostToDevice, sv.stream));
+        QSV_CUDA(cudaMemcpyAsync(scr + vb_al, li.data(), li.size() * 8, cudaMemcpyHostToDevice, sv.stream));
+        launch_scatter(sv, (const int64_t *)(scr + vb_al), scr, li.size());
+    }
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjoint Jacobian on the sharded register (AdjointDiffGPUMPI.hpp:248-437): lambda and the bras are sharded like
+// the register and share its qubit map, so they follow every exchange; the register itself stays where it is.
+// Jacobian entries are reduced over the ranks once, at the end (the reference all-reduces per (observable,
+// parameter), AdjointDiffGPUMPI.hpp:126-129).
+// ------------------------------------------------------------------------------------------------
+void dist_adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
+                           const std::vector<int64_t> &trainable, bool apply_operations, double *jac, size_t chunk_bytes) {
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    sv.use();
+    DistCtx &d = *sv.dist;
+    const int n_total = d.n_total;
+    QSV_CHECK(!trainable.empty(), "No trainable parameters provided.");
+    const size_t n_obs = obs.size(), n_tp = trainable.size();
+    for (size_t i = 0; i < n_obs * n_tp; ++i) jac[i] = 0.0;
+    if (n_obs == 0) return;
+    for (const auto &op : ops.ops)
+        QSV_CHECK(op.params.size() <= 1, "The operation is not supported using the adjoint differentiation method");
+
+    const std::vector<int> saved_phys = d.phys_of, saved_log = d.log_of;
+    struct Restore {
+        DistCtx &d;
+        const std::vector<int> &p, &l;
+        ~Restore() {
+            d.skip_main = false;
+            d.phys_of = p;
+            d.log_of = l;
+        }
+    } restore{d, saved_phys, saved_log};
+    d.skip_main = true;
+
+    TempVec lambda(sv, sv.data);
+    if (apply_operations)
+        for (const auto &op : ops.ops) {
+            if (op.name == "Identity") continue;
+            dist_apply_gate(sv, lower_op_total(n_total, op, false), {lambda.data}, chunk_bytes);
+        }
+    std::vector<std::unique_ptr<TempVec>> bras;
+    for (size_t i = 0; i < n_obs; ++i) {
+        bras.push_back(std::make_unique<TempVec>(sv, lambda.data));
+        dist_apply_observable(sv, *obs[i], bras.back()->data, chunk_bytes);
+    }
+    std::vector<void *> all_vecs = {lambda.data};
+    for (auto &b : bras) all_vecs.push_back(b->data);
+
+    const size_t n_slots = 2 * n_obs * n_tp;
+    double *red = sv.reduction_buffer(2 * n_slots);
+    reduction_zero(sv, red, 2 * n_slots);
+    std::vector<double> factor(n_tp, 0.0), extra(n_tp, 0.0);
+    size_t n_par_ops = 0;
+    for (const auto &op : ops.ops) n_par_ops += op.params.empty() ? 0 : 1;
+    int64_t tp_pos = (int64_t)n_tp - 1;
+    int64_t cur = (int64_t)n_par_ops - 1;
+    for (int64_t idx = (int64_t)ops.ops.size() - 1; idx >= 0; --idx) {
+        const Op &op = ops.ops[idx];
+        if (op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState") continue;
+        if (tp_pos < 0) break;
+        if (!op.params.empty()) {
+            if (cur == trainable[tp_pos]) {
+                LoweredGenerator g = lower_generator(n_total, op.name, op.wires);
+                factor[tp_pos] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
+                extra[tp_pos] = g.extra_identity;
+                const LoweredGate gl = dist_prepare_gate(sv, g.op, chunk_bytes);
+                for (size_t i = 0; i < n_obs; ++i) {
+                    if (gl.kind != LoweredGate::NOP || g.op.kind == LoweredGate::NOP)
+                        launch_bra_op_ket(sv, bras[i]->data, lambda.data, gl, red, (int)((tp_pos * n_obs + i) * 2));
+                    if (g.extra_identity != 0.0) {
+                        LoweredGate id;
+                        launch_bra_op_ket(sv, bras[i]->data, lambda.data, id, red, (int)((tp_pos * n_obs + i) * 2 + 1));
+                    }
+                }
+                --tp_pos;
+            }
+            --cur;
+        }
+        if (op.name != "Identity") dist_apply_gate(sv, lower_op_total(n_total, op, true), all_vecs, chunk_bytes);
+    }
+    std::vector<double> h(2 * n_slots);
+    reduction_read(sv, red, h.data(), 2 * n_slots);
+    allreduce_vec(sv, h.data(), h.size());
+    for (size_t p = 0; p < n_tp; ++p)
+        for (size_t i = 0; i < n_obs; ++i) {
+            const size_t s = (p * n_obs + i) * 2;
+            const double im = h[2 * s + 1] + extra[p] * h[2 * (s + 1) + 1];
+            jac[i * n_tp + p] = factor[p] * im;
+        }
+}
+
 void dist_free(State &sv) {
     if (!sv.dist) return;
     DistCtx *d = sv.dist;
@@ -480,8 +1082,9 @@ void dist_free(State &sv) {
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->red_dev) cudaFree(d->red_dev);
     if (d->hs_dev) cudaFree(d->hs_dev);
-    for (void *p : d->peer_map_base)
-        if (p) cudaIpcCloseMemHandle(p);
+    release_peer_buffer(d->main);
+    for (auto &c : d->comp) release_peer_buffer(c.pb);
+    if (d->tab_dev) cudaFree(d->tab_dev);
     delete d;
     sv.dist = nullptr;
     sv.index_hi = 0;
@@ -491,11 +1094,13 @@ void dist_free(State &sv) {
 
 namespace qsv {
 
-// Map every other rank's shard into this process with CUDA IPC.  The handles travel through NCCL itself
-// (all-gather of 80 bytes per rank), so no other rendezvous is needed.  Falls back to the NCCL
-// send/recv exchange (all ranks together) when any mapping fails.
-void setup_peer_access(State &sv) {
+// Map a shard-sized buffer of every other rank into this process with CUDA IPC (collective: every rank calls it
+// for its own buffer, in the same order).  The handles travel through NCCL itself (all-gather of 80 bytes per
+// rank), so no other rendezvous is needed.  ok == false on all ranks when any mapping failed.
+PeerBuf register_peer_buffer(State &sv, void *data) {
     DistCtx &d = *sv.dist;
+    PeerBuf pb;
+    pb.local = data;
     struct Msg {
         cudaIpcMemHandle_t handle;
         uint64_t offset;
@@ -504,17 +1109,17 @@ void setup_peer_access(State &sv) {
     static_assert(sizeof(Msg) == 80, "IPC message layout");
     Msg mine;
     memset(&mine, 0, sizeof(mine));
-    // base of the allocation that contains the shard (the shard may be a view into a torch block)
+    // base of the allocation that contains the buffer (it may be a view into a torch block)
     typedef int (*GetRangeFn)(unsigned long long *, size_t *, unsigned long long);
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     unsigned long long base = 0;
     size_t size = 0;
     bool ok = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr &&
-              ((GetRangeFn)fn)(&base, &size, (unsigned long long)(uintptr_t)sv.data) == 0;
+              ((GetRangeFn)fn)(&base, &size, (unsigned long long)(uintptr_t)data) == 0;
     if (ok) ok = cudaIpcGetMemHandle(&mine.handle, (void *)(uintptr_t)base) == cudaSuccess;
     cudaGetLastError();
-    mine.offset = ok ? (uint64_t)((uintptr_t)sv.data - base) : 0;
+    mine.offset = ok ? (uint64_t)((uintptr_t)data - base) : 0;
     mine.ok = ok ? 1 : 0;
     Msg *dev = nullptr;
     QSV_CUDA(cudaMalloc(&dev, sizeof(Msg) * (size_t)d.world));
@@ -526,8 +1131,9 @@ void setup_peer_access(State &sv) {
     QSV_CUDA(cudaFree(dev));
     bool all_ok = true;
     for (const Msg &m : all) all_ok = all_ok && m.ok == 1;
-    d.peer.assign(d.world, nullptr);
-    d.peer_map_base.assign(d.world, nullptr);
+    pb.peer.assign(d.world, nullptr);
+    pb.map_base.assign(d.world, nullptr);
+    pb.peer[d.rank] = data;
     int mapped_ok = all_ok ? 1 : 0;
     if (all_ok) {
         for (int r = 0; r < d.world && mapped_ok; ++r) {
@@ -538,8 +1144,8 @@ void setup_peer_access(State &sv) {
                 mapped_ok = 0;
                 break;
             }
-            d.peer_map_base[r] = p;
-            d.peer[r] = (char *)p + all[r].offset;
+            pb.map_base[r] = p;
+            pb.peer[r] = (char *)p + all[r].offset;
         }
     }
     // agree on the outcome
@@ -550,15 +1156,29 @@ void setup_peer_access(State &sv) {
     QSV_CUDA(cudaMemcpyAsync(&mapped_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, sv.stream));
     QSV_CUDA(cudaStreamSynchronize(sv.stream));
     QSV_CUDA(cudaFree(flag));
-    d.p2p = mapped_ok == 1;
-    d.registered = sv.data;
+    pb.ok = mapped_ok == 1;
+    if (!pb.ok) release_peer_buffer(pb);
+    return pb;
+}
+
+void release_peer_buffer(PeerBuf &pb) {
+    for (void *&p : pb.map_base)
+        if (p) {
+            cudaIpcCloseMemHandle(p);
+            p = nullptr;
+        }
+    pb.ok = false;
+}
+
+void setup_peer_access(State &sv) {
+    DistCtx &d = *sv.dist;
+    d.main = register_peer_buffer(sv, sv.data);
+    d.p2p = d.main.ok;
 }
 
 }  // namespace qsv
 
 using namespace qsv;
-struct qsv_state : State {};
-struct qsv_ops : Ops {};
 
 #define QSV_API_BEGIN try {
 #define QSV_API_END                                                                                \
@@ -701,6 +1321,117 @@ int qsv_dist_expval_pauli_words(qsv_state *sv, int n_terms, const char *letters,
     dist_expval_pauli(*sv, n_terms, xs.data(), zs.data(), nys.data(), coeffs, per_term, out, 0);
     QSV_API_END
 }
+
+int qsv_dist_set_basis_state(qsv_state *sv, uint64_t index) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    const int64_t idx = (int64_t)index;
+    if (sv->dtype == QSV_C128) {
+        const double one[2] = {1.0, 0.0};
+        dist_set_state(*sv, &idx, one, 1);
+    } else {
+        const float one[2] = {1.0f, 0.0f};
+        dist_set_state(*sv, &idx, one, 1);
+    }
+    QSV_API_END
+}
+
+int qsv_dist_set_state_vector(qsv_state *sv, const int64_t *indices, const void *values, size_t count) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    QSV_CHECK(count == 0 || (indices && values), "null index/value arrays");
+    dist_set_state(*sv, indices, values, count);
+    QSV_API_END
+}
+
+int qsv_dist_expval_named(qsv_state *sv, const char *name, const int *wires, int n_wires, const double *params,
+                          int n_params, double *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && name && out, "null argument");
+    QSV_CHECK(find_gate(name) != nullptr, std::string("Currently unsupported observable: ") + name);
+    std::vector<cplx> m = named_gate_matrix(name, std::vector<double>(params, params + n_params), n_wires);
+    dist_expval_matrix(*sv, m.data(), std::vector<int>(wires, wires + n_wires), out, 0);
+    QSV_API_END
+}
+
+int qsv_dist_expval_matrix(qsv_state *sv, const double *matrix, const int *wires, int n_wires, double *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && matrix && out, "null argument");
+    QSV_CHECK(n_wires >= 1 && n_wires <= 10, "dense observables act on 1..10 wires");
+    const size_t dim = 1ull << n_wires;
+    std::vector<cplx> m(dim * dim);
+    for (size_t i = 0; i < dim * dim; ++i) m[i] = cplx(matrix[2 * i], matrix[2 * i + 1]);
+    dist_expval_matrix(*sv, m.data(), std::vector<int>(wires, wires + n_wires), out, 0);
+    QSV_API_END
+}
+
+int qsv_dist_expval_csr(qsv_state *sv, const int64_t *row_offsets, const int64_t *col_indices, const double *values,
+                        int64_t nnz, double *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && row_offsets && out, "null argument");
+    Obs o;
+    o.kind = Obs::SPARSE;
+    const size_t rows = 1ull << sv->dist->n_total;
+    o.indptr.assign(row_offsets, row_offsets + rows + 1);
+    QSV_CHECK(o.indptr[rows] == nnz, "CSR offsets do not match nnz");
+    if (nnz) {
+        o.indices.assign(col_indices, col_indices + nnz);
+        o.values.resize(nnz);
+        for (int64_t i = 0; i < nnz; ++i) o.values[i] = cplx(values[2 * i], values[2 * i + 1]);
+    }
+    *out = dist_obs_expval(*sv, o, 0);
+    QSV_API_END
+}
+
+int qsv_dist_probs(qsv_state *sv, const int *wires, int n_wires, double *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && wires && out, "null argument");
+    dist_probs(*sv, std::vector<int>(wires, wires + n_wires), out);
+    QSV_API_END
+}
+
+int qsv_dist_sample(qsv_state *sv, const double *uniforms, int64_t shots, uint64_t *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    QSV_CHECK(shots >= 0 && (shots == 0 || (uniforms && out)), "invalid sampling arguments");
+    dist_sample(*sv, uniforms, shots, out, 0);
+    QSV_API_END
+}
+
+int qsv_dist_obs_expval(const qsv_obs *obs, qsv_state *sv, double *out) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && obs && out, "null argument");
+    *out = dist_obs_expval(*sv, *obs->p, 0);
+    QSV_API_END
+}
+
+int qsv_dist_obs_apply(const qsv_obs *obs, qsv_state *sv) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && obs, "null argument");
+    dist_obs_apply(*sv, *obs->p, 0);
+    QSV_API_END
+}
+
+int qsv_dist_adjoint_jacobian(qsv_state *sv, const qsv_ops *ops, qsv_obs *const *observables, int n_obs,
+                              const int64_t *trainable, int n_trainable, int apply_operations, double *jac) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && ops, "null argument");
+    QSV_CHECK(n_obs >= 0 && n_trainable >= 0, "negative sizes");
+    std::vector<const Obs *> o;
+    for (int i = 0; i < n_obs; ++i) {
+        QSV_CHECK(observables[i] != nullptr, "null observable");
+        o.push_back(observables[i]->p.get());
+    }
+    std::vector<int64_t> tp(trainable, trainable + n_trainable);
+    QSV_CHECK(n_trainable == 0 || jac != nullptr, "null Jacobian output");
+    dist_adjoint_jacobian(*sv, *ops, o, tp, apply_operations != 0, jac, 0);
+    QSV_API_END
+}
+
+int qsv_dist_rank(const qsv_state *sv) { return sv && sv->dist ? sv->dist->rank : -1; }
+int qsv_dist_world_size(const qsv_state *sv) { return sv && sv->dist ? sv->dist->world : -1; }
+int qsv_dist_total_qubits(const qsv_state *sv) { return sv && sv->dist ? sv->dist->n_total : -1; }
+
 
 int qsv_dist_last_swap_stats(const qsv_state *sv, uint64_t *bytes_sent, float *ms) {
     QSV_API_BEGIN

@@ -208,7 +208,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     k_pauli_sum_apply(const void *__restrict__ in, void *__restrict__ out, uint64_t length, int n_terms,
                       const uint64_t *__restrict__ xm, const uint64_t *__restrict__ zm,
-                      const double2 *__restrict__ cf) {
+                      const double2 *__restrict__ cf, int accumulate) {
     const uint64_t stride = (uint64_t)gridDim.x * 256;
     for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < length; i += stride) {
         double yr = 0, yi = 0;
@@ -220,6 +220,12 @@ __global__ void __launch_bounds__(256)
             const double s = (__popcll(j & zm[t]) & 1) ? -1.0 : 1.0;
             yr += s * (w.x * (double)c[0] - w.y * (double)c[1]);
             yi += s * (w.x * (double)c[1] + w.y * (double)c[0]);
+        }
+        if (accumulate) {
+            T o[2];
+            load_elem<T, 1>(o, out, i);
+            yr += (double)o[0];
+            yi += (double)o[1];
         }
         T y[2] = {(T)yr, (T)yi};
         store_elem<T, 1>(out, i, y);
@@ -371,6 +377,52 @@ __global__ void __launch_bounds__(256)
     if (out != nullptr) block_accumulate<256>(acc_re, acc_im, out);
 }
 
+// Row block of a sharded CSR product: the vector x is spread over shards (peer-mapped device pointers), column c
+// lives in shard c >> n_local at offset c & mask; the gathers travel over NVLink as plain loads.
+template <typename T, typename I, int LPR>
+__global__ void __launch_bounds__(256)
+    k_csr_sharded(void *const *__restrict__ x_shards, int n_local, const void *__restrict__ x_local, void *y,
+                  const I *__restrict__ indptr, const I *__restrict__ indices, const double2 *__restrict__ values,
+                  int64_t n_rows, double *out) {
+    const int sub = threadIdx.x % LPR;
+    const int64_t rows_per_block = 256 / LPR;
+    const uint64_t mask = (1ull << n_local) - 1ull;
+    double acc_re = 0, acc_im = 0;
+    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_rows;
+         row0 += (int64_t)gridDim.x * rows_per_block) {
+        const int64_t row = row0 + threadIdx.x / LPR;
+        const bool active = row < n_rows;
+        const int64_t lo = active ? (int64_t)indptr[row] : 0, hi = active ? (int64_t)indptr[row + 1] : 0;
+        double yr = 0, yi = 0;
+        for (int64_t j = lo + sub; j < hi; j += LPR) {
+            const double2 v = values[j];
+            const uint64_t c = (uint64_t)indices[j];
+            T a[2];
+            load_elem<T, 1>(a, x_shards[c >> n_local], c & mask);
+            yr += v.x * (double)a[0] - v.y * (double)a[1];
+            yi += v.x * (double)a[1] + v.y * (double)a[0];
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            yr += __shfl_down_sync(0xffffffffu, yr, o, LPR);
+            yi += __shfl_down_sync(0xffffffffu, yi, o, LPR);
+        }
+        if (sub == 0 && active) {
+            if (y != nullptr) {
+                T o2[2] = {(T)yr, (T)yi};
+                store_elem<T, 1>(y, (uint64_t)row, o2);
+            }
+            if (out != nullptr) {
+                T c[2];
+                load_elem<T, 1>(c, x_local, (uint64_t)row);
+                acc_re += (double)c[0] * yr + (double)c[1] * yi;
+                acc_im += (double)c[0] * yi - (double)c[1] * yr;
+            }
+        }
+    }
+    if (out != nullptr) block_accumulate<256>(acc_re, acc_im, out);
+}
+
 unsigned red_grid(uint64_t items) {
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((items + RNT - 1) / RNT, RGRID));
 }
@@ -508,7 +560,7 @@ void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t 
 }
 
 void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
-                            const uint64_t *zmasks, const cplx *coeffs) {
+                            const uint64_t *zmasks, const cplx *coeffs, bool accumulate) {
     sv.use();
     QSV_CHECK(in != out, "internal: pauli-sum apply is out of place");
     sv.stat_launches += 1;
@@ -521,11 +573,11 @@ void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, c
     if (sv.dtype == QSV_C128)
         k_pauli_sum_apply<double><<<grid, 256, 0, sv.stream>>>(in, out, sv.length(), n_terms, (const uint64_t *)scr,
                                                               (const uint64_t *)(scr + nt * 8),
-                                                              (const double2 *)(scr + nt * 16));
+                                                              (const double2 *)(scr + nt * 16), accumulate ? 1 : 0);
     else
         k_pauli_sum_apply<float><<<grid, 256, 0, sv.stream>>>(in, out, sv.length(), n_terms, (const uint64_t *)scr,
                                                              (const uint64_t *)(scr + nt * 8),
-                                                             (const double2 *)(scr + nt * 16));
+                                                             (const double2 *)(scr + nt * 16), accumulate ? 1 : 0);
     QSV_CUDA(cudaGetLastError());
     QSV_CUDA(cudaStreamSynchronize(sv.stream));
 }
@@ -579,52 +631,73 @@ void launch_probs(State &sv, const std::vector<int> &bits, double *out_host) {
     QSV_CUDA(cudaStreamSynchronize(sv.stream));
 }
 
-void launch_sample(State &sv, const double *uniforms, int64_t shots, uint64_t *out_host) {
+// block masses of the vector on the host (sequential FP64 prefix, deterministic)
+static void block_cdf(State &sv, std::vector<double> &cdf, double *&mass_dev, uint64_t &nblk, size_t extra_bytes = 0) {
+    const uint64_t len = sv.length();
+    nblk = (len + SBLK - 1) / SBLK;
+    mass_dev = (double *)sv.scratch_buffer(nblk * sizeof(double) + extra_bytes);  // extra area follows the masses
+    if (sv.dtype == QSV_C64)
+        k_block_mass<float><<<(unsigned)nblk, 256, 0, sv.stream>>>(sv.data, len, mass_dev);
+    else
+        k_block_mass<double><<<(unsigned)nblk, 256, 0, sv.stream>>>(sv.data, len, mass_dev);
+    QSV_CUDA(cudaGetLastError());
+    std::vector<double> h_mass(nblk);
+    QSV_CUDA(cudaMemcpyAsync(h_mass.data(), mass_dev, nblk * sizeof(double), cudaMemcpyDeviceToHost, sv.stream));
+    QSV_CUDA(cudaStreamSynchronize(sv.stream));
+    cdf.assign(nblk + 1, 0.0);
+    for (uint64_t b = 0; b < nblk; ++b) cdf[b + 1] = cdf[b] + h_mass[b];
+}
+
+double state_mass(State &sv) {
+    sv.use();
+    std::vector<double> cdf;
+    double *mass_dev;
+    uint64_t nblk;
+    block_cdf(sv, cdf, mass_dev, nblk);
+    return cdf[nblk];
+}
+
+// two-level inverse CDF: index_host[s] = first index whose cumulative |amp|^2 exceeds the target mass
+// (targets[s] * total when the targets are uniform numbers, targets[s] itself when they are masses)
+void launch_sample_indices(State &sv, const double *targets, int64_t shots, uint64_t *index_host, bool targets_are_mass) {
     sv.use();
     if (shots <= 0) return;
     sv.stat_launches += 2;
     const uint64_t len = sv.length();
-    const uint64_t nblk = (len + SBLK - 1) / SBLK;
-    const size_t bytes = nblk * sizeof(double) + (size_t)shots * (sizeof(uint64_t) * 2 + sizeof(double));
-    char *scr = (char *)sv.scratch_buffer(bytes);
-    double *mass = (double *)scr;
-    uint64_t *d_block = (uint64_t *)(scr + nblk * sizeof(double));
-    double *d_resid = (double *)(d_block + shots);
-    uint64_t *d_index = (uint64_t *)(d_resid + shots);
-    const bool f32 = sv.dtype == QSV_C64;
-    if (f32)
-        k_block_mass<float><<<(unsigned)nblk, 256, 0, sv.stream>>>(sv.data, len, mass);
-    else
-        k_block_mass<double><<<(unsigned)nblk, 256, 0, sv.stream>>>(sv.data, len, mass);
-    QSV_CUDA(cudaGetLastError());
-    std::vector<double> h_mass(nblk);
-    QSV_CUDA(cudaMemcpyAsync(h_mass.data(), mass, nblk * sizeof(double), cudaMemcpyDeviceToHost, sv.stream));
-    QSV_CUDA(cudaStreamSynchronize(sv.stream));
-    // exclusive prefix over blocks (sequential FP64, deterministic)
-    std::vector<double> cdf(nblk + 1, 0.0);
-    for (uint64_t b = 0; b < nblk; ++b) cdf[b + 1] = cdf[b] + h_mass[b];
+    std::vector<double> cdf;
+    double *mass_dev;
+    uint64_t nblk;
+    block_cdf(sv, cdf, mass_dev, nblk, (size_t)shots * (sizeof(uint64_t) * 2 + sizeof(double)));
     const double total = cdf[nblk];
     std::vector<uint64_t> h_block(shots);
     std::vector<double> h_resid(shots);
     for (int64_t s = 0; s < shots; ++s) {
-        const double target = uniforms[s] * total;
+        const double target = targets_are_mass ? targets[s] : targets[s] * total;
         // first block whose cumulative mass exceeds the target
         uint64_t b = (uint64_t)(std::upper_bound(cdf.begin() + 1, cdf.end(), target) - (cdf.begin() + 1));
         if (b >= nblk) b = nblk - 1;
         h_block[s] = b;
         h_resid[s] = target - cdf[b];
     }
+    uint64_t *d_block = (uint64_t *)(mass_dev + nblk);
+    double *d_resid = (double *)(d_block + shots);
+    uint64_t *d_index = (uint64_t *)(d_resid + shots);
     QSV_CUDA(cudaMemcpyAsync(d_block, h_block.data(), shots * sizeof(uint64_t), cudaMemcpyHostToDevice, sv.stream));
     QSV_CUDA(cudaMemcpyAsync(d_resid, h_resid.data(), shots * sizeof(double), cudaMemcpyHostToDevice, sv.stream));
     const unsigned grid = (unsigned)((shots + 127) / 128);
-    if (f32)
+    if (sv.dtype == QSV_C64)
         k_sample_in_block<float><<<grid, 128, 0, sv.stream>>>(sv.data, len, shots, d_block, d_resid, d_index);
     else
         k_sample_in_block<double><<<grid, 128, 0, sv.stream>>>(sv.data, len, shots, d_block, d_resid, d_index);
     QSV_CUDA(cudaGetLastError());
-    std::vector<uint64_t> h_index(shots);
-    QSV_CUDA(cudaMemcpyAsync(h_index.data(), d_index, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, sv.stream));
+    QSV_CUDA(cudaMemcpyAsync(index_host, d_index, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, sv.stream));
     QSV_CUDA(cudaStreamSynchronize(sv.stream));
+}
+
+void launch_sample(State &sv, const double *uniforms, int64_t shots, uint64_t *out_host) {
+    if (shots <= 0) return;
+    std::vector<uint64_t> h_index(shots);
+    launch_sample_indices(sv, uniforms, shots, h_index.data(), false);
     const int n = sv.n;
     for (int64_t s = 0; s < shots; ++s)
         for (int w = 0; w < n; ++w) out_host[s * n + w] = (h_index[s] >> (n - 1 - w)) & 1ull;
@@ -667,6 +740,44 @@ void launch_csr(State &sv, const void *x, void *y, const void *dev_indptr, const
     }
 #undef QSV_CSR_L
 #undef QSV_CSR_LAUNCH
+    QSV_CUDA(cudaGetLastError());
+}
+
+void launch_csr_sharded(State &sv, void *const *x_shards_dev, int n_local, const void *x_local, void *y,
+                        const void *dev_indptr, const void *dev_indices, const void *dev_values, int64_t n_rows,
+                        int64_t nnz, int index_bytes, double *out_dev, int slot) {
+    sv.use();
+    sv.stat_launches += 1;
+    QSV_CHECK(index_bytes == 4 || index_bytes == 8, "CSR index width must be 4 or 8 bytes");
+    double *out = out_dev ? out_dev + 2 * (size_t)slot : nullptr;
+    const double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
+    const int lpr = avg > 12 ? 32 : (avg > 3 ? 8 : 1);
+    const double2 *vals = (const double2 *)dev_values;
+    const bool f32 = sv.dtype == QSV_C64, i32 = index_bytes == 4;
+#define QSV_CSRS(T, I, L)                                                                                              \
+    k_csr_sharded<T, I, L><<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + (256 / L) - 1) / (256 / L),     \
+                                                                              NUM_SMS * 16)),                           \
+                             256, 0, sv.stream>>>(x_shards_dev, n_local, x_local, y, (const I *)dev_indptr,             \
+                                                  (const I *)dev_indices, vals, n_rows, out)
+#define QSV_CSRS_L(T, I)                                                                                               \
+    if (lpr == 32) {                                                                                                   \
+        QSV_CSRS(T, I, 32);                                                                                            \
+    } else if (lpr == 8) {                                                                                             \
+        QSV_CSRS(T, I, 8);                                                                                             \
+    } else {                                                                                                           \
+        QSV_CSRS(T, I, 1);                                                                                             \
+    }
+    if (f32 && i32) {
+        QSV_CSRS_L(float, int32_t)
+    } else if (f32) {
+        QSV_CSRS_L(float, int64_t)
+    } else if (i32) {
+        QSV_CSRS_L(double, int32_t)
+    } else {
+        QSV_CSRS_L(double, int64_t)
+    }
+#undef QSV_CSRS_L
+#undef QSV_CSRS
     QSV_CUDA(cudaGetLastError());
 }
 

@@ -166,13 +166,22 @@ void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t 
                           int ny, double *out_dev, int slot);
 // out[i] = sum_t coeff_t (P_t in)[i]   (out-of-place, in != out)
 void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
-                            const uint64_t *zmasks, const cplx *coeffs_with_phase);
+                            const uint64_t *zmasks, const cplx *coeffs_with_phase, bool accumulate = false);
 void launch_probs(State &sv, const std::vector<int> &bits_lsb_first, double *out_host);
 void launch_sample(State &sv, const double *uniforms, int64_t shots, uint64_t *out_host);
 // CSR: y = H x (y may be null) and/or accumulate <x|Hx> into out_dev[2*slot..]
 void launch_csr(State &sv, const void *x, void *y, const void *dev_indptr, const void *dev_indices,
                 const void *dev_values, int64_t n_rows, int64_t nnz, int index_bytes, double *out_dev,
                 int slot);
+// row block of a sharded CSR product: x is spread over 2^(n_total - n_local) shards whose device pointers are
+// x_shards[r] (peer-mapped); this rank's rows are [row_base, row_base + n_rows); column c lives in shard
+// c >> n_local at offset c & (2^n_local - 1).  indptr is local (n_rows + 1 entries starting at 0).
+void launch_csr_sharded(State &sv, void *const *x_shards_dev, int n_local, const void *x_local, void *y,
+                        const void *dev_indptr, const void *dev_indices, const void *dev_values, int64_t n_rows,
+                        int64_t nnz, int index_bytes, double *out_dev, int slot);
+// index of each sample only (no bit expansion); *total_out receives the probability mass of the vector
+void launch_sample_indices(State &sv, const double *targets, int64_t shots, uint64_t *index_host, bool targets_are_mass);
+double state_mass(State &sv);
 // zero `count` doubles of the reduction buffer / read them back (one sync)
 void reduction_zero(State &sv, double *dev, size_t count);
 void reduction_read(State &sv, const double *dev, double *host, size_t count);
@@ -182,12 +191,29 @@ void apply_op(State &sv, const Op &op, bool extra_adjoint);
 void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
 // same, on several vectors at once (dev_table = device array of n_vecs pointers, or null for sv.data)
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs);
+// register-blocked tile kernel (tile_regs.cu)
+bool regs_fusable(const LoweredGate &g, int n_local);
+uint64_t regs_need_bits(const LoweredGate &g);
+void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,
+                    void *const *table, int n_vecs);
 void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
 double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>
 void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
                       const std::vector<int64_t> &trainable, bool apply_operations, double *jac);
 
+// Pauli-word views of observables (circuit.cu)
+bool as_pauli_word(const Obs &o, int n, uint64_t &x, uint64_t &z, int &ny);
+bool hamiltonian_of_pauli_words(const Obs &o, int n, std::vector<uint64_t> &xs, std::vector<uint64_t> &zs,
+                                std::vector<cplx> &cf);
+
 // dist.cu
 void dist_free(State &sv);
 
 }  // namespace qsv
+
+// the opaque handles of include/qsv_b200.h
+struct qsv_state : qsv::State {};
+struct qsv_ops : qsv::Ops {};
+struct qsv_obs {
+    std::shared_ptr<qsv::Obs> p;
+};

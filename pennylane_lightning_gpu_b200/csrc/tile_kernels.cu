@@ -541,8 +541,61 @@ std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> 
 
 }  // namespace
 
+// Register-blocked executor (tile_regs.cu): same sweep packing, but the tile has 12 - L arbitrary high bits with
+// L as small as one warp-wide access allows, and the gates of a sweep are list-scheduled into register passes.
+static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
+    const bool f32 = sv.dtype == QSV_C64;
+    int L = env_int("QSV_REGS_LOW", f32 ? 6 : 5);
+    L = std::max(1, std::min(L, 11));
+    const int max_hi = 12 - L;
+    const bool merge = env_int("QSV_MERGE_1Q", 1) != 0;
+    const int max_gates = std::min(48, env_int("QSV_REGS_MAX_GATES", 48));
+    const std::vector<LoweredGate> merged = merge ? merge_single_qubit_runs(gates_in) : gates_in;
+    std::vector<const LoweredGate *> cur;
+    uint64_t cur_need = 0;
+    int cur_pool = 0;
+    auto single = [&](const LoweredGate &g) {
+        if (dev_table)
+            launch_gate_multi(sv, g, dev_table, n_vecs);
+        else
+            launch_gate(sv, g);
+    };
+    auto flush = [&]() {
+        if (cur.empty()) return;
+        if (cur.size() == 1)
+            single(*cur[0]);  // a lone gate: the one-sweep kernel touches only what the gate changes
+        else
+            run_sweep_regs(sv, cur, cur_need, L, dev_table, n_vecs);
+        cur.clear();
+        cur_need = 0;
+        cur_pool = 0;
+    };
+    const uint64_t low = (1ull << L) - 1ull;
+    for (const LoweredGate &g : merged) {
+        if (g.kind == LoweredGate::NOP) continue;
+        if (!regs_fusable(g, sv.n)) {
+            flush();
+            single(g);
+            continue;
+        }
+        const uint64_t need = regs_need_bits(g) & ~low;
+        const int pn = (g.kind == LoweredGate::DENSE && !(g.k == 1 && g.tgt_bits.size() == 1)) ? 32 : 8;
+        const bool fits = __builtin_popcountll(cur_need | need) <= max_hi && (int)cur.size() < max_gates &&
+                          cur_pool + pn <= 1280;
+        if (!fits) flush();
+        cur.push_back(&g);
+        cur_need |= need;
+        cur_pool += pn;
+    }
+    flush();
+}
+
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
     sv.use();
+    if (sv.n >= 12 && env_int("QSV_TILE_KERNEL", 1) == 1) {
+        apply_gates_regs(sv, gates_in, dev_table, n_vecs);
+        return;
+    }
     const bool f32 = sv.dtype == QSV_C64;
     int tb = env_int("QSV_TILE_BITS", f32 ? 13 : 12);
     int L = env_int("QSV_TILE_LOW", f32 ? 8 : 7);

@@ -102,6 +102,75 @@ class DistributedStateVector:
                                                  terms.ctypes.data_as(_cabi._DP), C.byref(out)))
         return (out.value, terms[: len(words)]) if return_terms else out.value
 
+    def set_basis_state(self, index: int = 0):
+        """setBasisState on the whole register (MPI.hpp:332-345); resets the qubit map."""
+        _check(lib().qsv_dist_set_basis_state(self.local._h, index))
+
+    def set_state_vector(self, indices, values):
+        """setStateVector (MPI.hpp:357-381): global indices, every rank keeps those of its shard."""
+        ia = np.ascontiguousarray(indices, dtype=np.int64)
+        va = np.ascontiguousarray(values, dtype=self.local.np_dtype)
+        _check(lib().qsv_dist_set_state_vector(self.local._h, ia.ctypes.data_as(_cabi._I64P), va.ctypes.data_as(_cabi._P),
+                                               len(ia)))
+
+    def apply(self, name: str, wires, params=(), adjoint=False, matrix=None):
+        """One gate on the whole register (applyOperation, MPI.hpp:392-470)."""
+        self.apply_ops(Ops([{"name": name, "wires": list(wires), "params": list(params), "adjoint": adjoint,
+                             "matrix": matrix}]), fuse=False)
+
+    def expval_named(self, name, wires, params=()) -> complex:
+        wa, wp = _cabi._ints(wires)
+        pa, pp = _cabi._dbls(params)
+        out = (C.c_double * 2)()
+        _check(lib().qsv_dist_expval_named(self.local._h, name.encode(), wp, len(wa), pp, len(pa), out))
+        return complex(out[0], out[1])
+
+    def expval_matrix(self, matrix, wires) -> complex:
+        wa, wp = _cabi._ints(wires)
+        ma, mp = _cabi._cmat(matrix)
+        out = (C.c_double * 2)()
+        _check(lib().qsv_dist_expval_matrix(self.local._h, mp, wp, len(wa), out))
+        return complex(out[0], out[1])
+
+    def expval_csr(self, indptr, indices, data) -> float:
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int64)
+        va, vp = _cabi._cmat(data)
+        out = C.c_double(0)
+        _check(lib().qsv_dist_expval_csr(self.local._h, ip.ctypes.data_as(_cabi._I64P), ix.ctypes.data_as(_cabi._I64P),
+                                         vp, len(ix), C.byref(out)))
+        return out.value
+
+    def expval(self, obs) -> float:
+        out = C.c_double(0)
+        _check(lib().qsv_dist_obs_expval(obs._h, self.local._h, C.byref(out)))
+        return out.value
+
+    def apply_observable(self, obs):
+        _check(lib().qsv_dist_obs_apply(obs._h, self.local._h))
+
+    def probs(self, wires) -> np.ndarray:
+        """Marginal probabilities of the whole register; first listed wire = LSB (as StateVector.probs)."""
+        wa, wp = _cabi._ints(wires)
+        out = np.zeros(1 << len(wa), dtype=np.float64)
+        _check(lib().qsv_dist_probs(self.local._h, wp, len(wa), out.ctypes.data_as(_cabi._DP)))
+        return out
+
+    def sample(self, uniforms) -> np.ndarray:
+        ua, up = _cabi._dbls(uniforms)
+        out = np.zeros((len(ua), self.n_total), dtype=np.uint64)
+        _check(lib().qsv_dist_sample(self.local._h, up, len(ua), out.ctypes.data_as(_cabi._U64P)))
+        return out
+
+    def adjoint_jacobian(self, ops: Ops, observables, trainable, apply_operations: bool = False) -> np.ndarray:
+        tp = np.ascontiguousarray(list(trainable), dtype=np.int64)
+        jac = np.zeros((len(observables), len(tp)), dtype=np.float64)
+        arr = (_cabi._P * max(len(observables), 1))(*[o._h for o in observables])
+        _check(lib().qsv_dist_adjoint_jacobian(self.local._h, ops._h, arr, len(observables),
+                                               tp.ctypes.data_as(_cabi._I64P), len(tp), int(bool(apply_operations)),
+                                               jac.ctypes.data_as(_cabi._DP)))
+        return jac
+
     def norm2(self) -> float:
         v = np.array([self.local.inner_product(self.local).real], dtype=np.float64)
         _check(lib().qsv_dist_allreduce_f64(self.local._h, v.ctypes.data_as(_cabi._DP), 1))

@@ -35,6 +35,138 @@ def circuit(n, seed, n_gates=60):
     return ops
 
 
+def _obs_zoo(rng, n):
+    h2 = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    h2 = h2 + h2.conj().T
+    h1 = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    h1 = h1 + h1.conj().T
+    return [
+        ("Named", "PauliZ", [0]),
+        ("Named", "PauliX", [0]),
+        ("Named", "PauliY", [n - 1]),
+        ("Named", "Hadamard", [0]),
+        ("Hermitian", h1, [1]),
+        ("Hermitian", h2, [n - 1, 0]),
+        ("TensorProd", [("Named", "PauliX", [0]), ("Named", "PauliY", [2]), ("Named", "PauliZ", [n - 1])]),
+        ("TensorProd", [("Named", "PauliZ", [1]), ("Hermitian", h1, [0])]),
+        ("Hamiltonian", [0.3, -1.1, 0.7],
+         [("Named", "PauliZ", [0]), ("TensorProd", [("Named", "PauliX", [1]), ("Named", "PauliX", [0])]),
+          ("TensorProd", [("Named", "PauliY", [0]), ("Named", "PauliZ", [n - 1])])]),
+        ("Hamiltonian", [0.9, 0.4], [("Hermitian", h2, [1, 0]), ("Named", "Hadamard", [0])]),
+    ]
+
+
+def measurements_and_adjoint(rank, local_rank, world, g):
+    """Sharded measurements, observables and adjoint Jacobian against the oracle (the reference's own pattern:
+    src/tests/mpi/Test_StateVectorCudaMPI_NonParam.cpp:836-927, Test_AdjointDiffGPUMPI.cpp)."""
+    failures = []
+    n = g + 8
+    rng = np.random.default_rng(77)
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 5e-5)):
+        ops = workloads.random_gate_circuit(n, 40, seed=5 + n)
+        ops += [{"name": "Hadamard", "wires": [0], "params": []}, {"name": "CNOT", "wires": [0, n - 1], "params": []},
+                {"name": "RY", "wires": [1], "params": [0.37]}]
+        psi0 = orc.apply_ops(orc.basis_state(n), [{"name": "Hadamard", "wires": [w], "params": []} for w in range(n)])
+        want = orc.apply_ops(psi0, ops)
+        sv = DistributedStateVector(n, dtype, device=local_rank)
+        # state preparation on the whole register, then the circuit
+        sv.set_basis_state(5)
+        probe = sv.probs([n - 1, n - 3, 0])  # index 5 = wires n-1 and n-3 set; first listed wire = LSB
+        if abs(probe[0b011] - 1.0) > 1e-12:
+            failures.append(f"set_basis_state/probs: {probe}")
+        idx = np.arange(1 << n, dtype=np.int64)
+        sv.set_state_vector(idx, psi0.astype(dtype))
+        sv.apply_ops(q.Ops(ops), fuse=True)
+
+        def check(what, got, ref, scale=10.0):
+            err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
+            if not err <= tol * scale:
+                failures.append(f"{np.dtype(dtype).name} {what}: err {err:.2e}")
+            if rank == 0:
+                print(f"[dist_check] {np.dtype(dtype).name} {what}: err={err:.2e}", flush=True)
+
+        for wires in ([0], [n - 1], [0, n - 1], [2, 0, 1], [n - 2, 1, 0, 3], list(range(g))):
+            check(f"probs{wires}", sv.probs(wires), orc.probs_custatevec_order(want, wires))
+        h1 = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+        h2 = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+        check("expval_named RX(0)", sv.expval_named("RX", [0], [0.4]), orc.expval_matrix(want, orc.gate_matrix("RX", [0.4]), [0]))
+        check("expval_matrix 1q", sv.expval_matrix(h1, [0]), orc.expval_matrix(want, h1, [0]))
+        check("expval_matrix 2q", sv.expval_matrix(h2, [n - 1, 0]), orc.expval_matrix(want, h2, [n - 1, 0]), 40.0)
+        zoo = _obs_zoo(np.random.default_rng(3), n)
+        for i, t in enumerate(zoo):
+            check(f"obs[{i}] expval", sv.expval(q.Observable.from_tuple(t)), orc.expval_obs(want, t), 40.0)
+        # sparse Hamiltonian: row blocks + gathers from the other shards
+        m, (w2, ws2, c2) = workloads.molecular_style_sparse_hamiltonian(n, n_terms=40, n_flip_masks=6, seed=3)
+        ref_sparse = orc.expval_csr(want, m.indptr, m.indices, m.data)
+        check("expval_csr", sv.expval_csr(m.indptr, m.indices, m.data), ref_sparse, 40.0)
+        check("expval sparse obs", sv.expval(q.Observable.sparse(m.indptr, m.indices, m.data)), ref_sparse, 40.0)
+        check("pauli words vs csr", sv.expval_pauli_words(w2, ws2, c2), ref_sparse, 40.0)
+        # sampling: same definition as the single-GPU sampler over the whole register
+        shots = 2000
+        u = np.random.default_rng(1234).random(shots)
+        got = sv.sample(u)
+        ref = orc.sample(want.astype(dtype), shots, seed=1234)
+        cdf = np.cumsum(np.abs(want) ** 2)
+        near = np.min(np.abs(cdf[None, :] - (u * cdf[-1])[:, None]), axis=1) < (1e-12 if dtype == np.complex128 else 1e-6)
+        same = np.all(got == ref, axis=1)
+        if not (np.all(same | near) and same.mean() > 0.99):
+            failures.append(f"{np.dtype(dtype).name} sampling: {same.mean():.4f} identical")
+        # observable application
+        for i in (5, 8, 9):
+            a = DistributedStateVector(n, dtype, device=local_rank)
+            a.set_state_vector(idx, want.astype(dtype))
+            a.apply_observable(q.Observable.from_tuple(zoo[i]))
+            a.canonicalize()
+            shard = a.local_state().astype(np.complex128)
+            ref_shard = orc.apply_observable(want, zoo[i])[rank << (n - g):(rank + 1) << (n - g)]
+            check(f"obs[{i}] apply", shard, ref_shard, 100.0)
+            a.close()
+        spo = DistributedStateVector(n, dtype, device=local_rank)
+        spo.set_state_vector(idx, want.astype(dtype))
+        spo.apply_observable(q.Observable.sparse(m.indptr, m.indices, m.data))
+        spo.canonicalize()
+        ref_shard = orc.csr_matvec(m.indptr, m.indices, m.data, want)[rank << (n - g):(rank + 1) << (n - g)]
+        check("sparse apply", spo.local_state().astype(np.complex128), ref_shard, 400.0)
+        spo.close()
+        sv.close()
+
+        # adjoint Jacobian: every parametric gate family, wires hitting global and local qubits
+        aops = [{"name": "RX", "wires": [0], "params": [0.3]}, {"name": "RY", "wires": [n - 1], "params": [-0.7]},
+                {"name": "CNOT", "wires": [0, 1], "params": []}, {"name": "RZ", "wires": [0], "params": [1.1]},
+                {"name": "PhaseShift", "wires": [0], "params": [0.2]}, {"name": "CRX", "wires": [0, 2], "params": [0.5]},
+                {"name": "CRY", "wires": [3, 0], "params": [-0.4]}, {"name": "CRZ", "wires": [1, 0], "params": [0.9]},
+                {"name": "IsingXX", "wires": [0, n - 1], "params": [0.6]}, {"name": "IsingYY", "wires": [1, 0], "params": [0.8]},
+                {"name": "IsingZZ", "wires": [0, 2], "params": [-1.2]}, {"name": "Hadamard", "wires": [0], "params": []},
+                {"name": "ControlledPhaseShift", "wires": [0, 1], "params": [0.33]},
+                {"name": "SingleExcitation", "wires": [0, 3], "params": [0.21]},
+                {"name": "SingleExcitationPlus", "wires": [1, 0], "params": [-0.5]},
+                {"name": "DoubleExcitation", "wires": [0, 1, 2, 3], "params": [0.44]},
+                {"name": "DoubleExcitationMinus", "wires": [n - 1, 0, 2, 1], "params": [0.15]},
+                {"name": "MultiRZ", "wires": [0, 1, n - 1], "params": [0.77]}, {"name": "RX", "wires": [0], "params": [0.9], "adjoint": True},
+                {"name": "RY", "wires": [2], "params": [0.1]}]
+        n_par = sum(1 for o in aops if o["params"])
+        obs_t = [zoo[0], zoo[5], zoo[6], zoo[8], zoo[9], ("Sparse", m.indptr, m.indices, m.data)]
+        psi_a = orc.apply_ops(psi0, aops)
+        jref = orc.adjoint_jacobian(psi_a, aops, obs_t, list(range(n_par)))
+        a = DistributedStateVector(n, dtype, device=local_rank)
+        a.set_state_vector(idx, psi0.astype(dtype))
+        rec = q.Ops(aops)
+        a.apply_ops(rec, fuse=False)
+        before = a.norm2()
+        jac = a.adjoint_jacobian(rec, [q.Observable.from_tuple(t) for t in obs_t], list(range(n_par)))
+        check("adjoint jacobian (all params)", jac, jref, 400.0)
+        tp = [0, 3, 7, n_par - 1]
+        jac2 = a.adjoint_jacobian(rec, [q.Observable.from_tuple(obs_t[3])], tp)
+        check("adjoint jacobian (subset)", jac2[0], jref[3][tp], 400.0)
+        # the register itself is untouched by the adjoint sweep
+        a.canonicalize()
+        check("state after adjoint", a.local_state().astype(np.complex128), psi_a[rank << (n - g):(rank + 1) << (n - g)], 40.0)
+        if abs(before - 1) > tol * 100:
+            failures.append("norm before adjoint")
+        a.close()
+    return failures
+
+
 def main():
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -73,6 +205,7 @@ def main():
                     if rank == 0:
                         print(f"[dist_check] {tag}: err={err:.2e} expval_err={abs(ev - ev_want):.2e} swaps={n_swaps}", flush=True)
                     sv.close()
+    failures += measurements_and_adjoint(rank, local_rank, world, g)
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
