@@ -207,6 +207,16 @@ int qsv_dist_adjoint_jacobian(qsv_state *local, const qsv_ops *ops, qsv_obs *con
 int qsv_dist_rank(const qsv_state *local);
 int qsv_dist_world_size(const qsv_state *local);
 int qsv_dist_total_qubits(const qsv_state *local);
+/* CopyHostDataToGpu / CopyGpuDataToHost / updateData of StateVectorCudaMPI (StateVectorCudaBase.hpp:104-228): the local
+ * shard in the canonical layout (h2d resets the qubit map, d2h canonicalises first); copy = shard + qubit map */
+int qsv_dist_h2d(qsv_state *local, const void *host, size_t n_amps);
+int qsv_dist_d2h(qsv_state *local, void *host, size_t n_amps);
+int qsv_dist_copy(qsv_state *dst, const qsv_state *src);
+/* MPIManager::Barrier / Bcast / Scatter (util/MPIManager.hpp) over the register's NCCL communicator */
+int qsv_dist_barrier(qsv_state *local);
+int qsv_dist_bcast_bytes(qsv_state *local, void *host, size_t bytes, int root);
+int qsv_dist_scatter_host(qsv_state *local, const void *send_host, void *recv_host, size_t bytes_per_rank, int root);
+int qsv_dist_nccl_version(int *version);
 /* MPI_Allreduce(sum) of small host vectors (MPI.hpp:1176, :1426, :2361): ncclAllReduce on a device buffer */
 int qsv_dist_allreduce_f64(qsv_state *local, double *host_values, int count);
 /* NVLink bytes sent by this rank and device milliseconds of the last exchange / of all exchanges */

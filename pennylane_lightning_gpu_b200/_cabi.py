@@ -104,6 +104,13 @@ SIGNATURES = {
     "qsv_dist_obs_expval": (_I, [_P, _P, _DP]),
     "qsv_dist_obs_apply": (_I, [_P, _P]),
     "qsv_dist_adjoint_jacobian": (_I, [_P, _P, C.POINTER(_P), _I, _I64P, _I, _I, _DP]),
+    "qsv_dist_h2d": (_I, [_P, _P, C.c_size_t]),
+    "qsv_dist_d2h": (_I, [_P, _P, C.c_size_t]),
+    "qsv_dist_copy": (_I, [_P, _P]),
+    "qsv_dist_barrier": (_I, [_P]),
+    "qsv_dist_bcast_bytes": (_I, [_P, _P, C.c_size_t, _I]),
+    "qsv_dist_scatter_host": (_I, [_P, _P, _P, C.c_size_t, _I]),
+    "qsv_dist_nccl_version": (_I, [_IP]),
     "qsv_dist_rank": (_I, [_P]),
     "qsv_dist_world_size": (_I, [_P]),
     "qsv_dist_total_qubits": (_I, [_P]),

@@ -1433,6 +1433,111 @@ int qsv_dist_world_size(const qsv_state *sv) { return sv && sv->dist ? sv->dist-
 int qsv_dist_total_qubits(const qsv_state *sv) { return sv && sv->dist ? sv->dist->n_total : -1; }
 
 
+/* local shard <-> host in the canonical layout (CopyHostDataToGpu / CopyGpuDataToHost of StateVectorCudaMPI) */
+int qsv_dist_h2d(qsv_state *sv, const void *host, size_t n_amps) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && host, "null argument");
+    QSV_CHECK(n_amps <= sv->length(), "host buffer larger than the local shard");
+    sv->use();
+    DistCtx &d = *sv->dist;
+    for (int b = 0; b < d.n_total; ++b) d.phys_of[b] = d.log_of[b] = b;
+    QSV_CUDA(cudaMemcpyAsync(sv->data, host, n_amps * sv->amp_bytes(), cudaMemcpyHostToDevice, sv->stream));
+    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    QSV_API_END
+}
+
+int qsv_dist_d2h(qsv_state *sv, void *host, size_t n_amps) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && host, "null argument");
+    QSV_CHECK(n_amps <= sv->length(), "host buffer larger than the local shard");
+    dist_canonicalize(*sv, 0);
+    QSV_CUDA(cudaMemcpyAsync(host, sv->data, n_amps * sv->amp_bytes(), cudaMemcpyDeviceToHost, sv->stream));
+    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    QSV_API_END
+}
+
+/* updateData(other) of StateVectorCudaMPI: shard and qubit map */
+int qsv_dist_copy(qsv_state *dst, const qsv_state *src) {
+    QSV_API_BEGIN
+    QSV_CHECK(dst && src && dst->dist && src->dist, "null argument");
+    QSV_CHECK(dst->n == src->n && dst->dtype == src->dtype && dst->dist->n_total == src->dist->n_total,
+              "sharded registers differ in size or precision");
+    dst->use();
+    if (src->stream != dst->stream) QSV_CUDA(cudaStreamSynchronize(src->stream));
+    QSV_CUDA(cudaMemcpyAsync(dst->data, src->data, dst->bytes(), cudaMemcpyDefault, dst->stream));
+    QSV_CUDA(cudaStreamSynchronize(dst->stream));
+    dst->dist->phys_of = src->dist->phys_of;
+    dst->dist->log_of = src->dist->log_of;
+    QSV_API_END
+}
+
+int qsv_dist_barrier(qsv_state *sv) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    sv->use();
+    stream_barrier(*sv);
+    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    QSV_API_END
+}
+
+/* MPI_Bcast of a small host buffer (MPIManager::Bcast, util/MPIManager.hpp) */
+int qsv_dist_bcast_bytes(qsv_state *sv, void *host, size_t bytes, int root) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && host, "null argument");
+    sv->use();
+    DistCtx &d = *sv->dist;
+    void *dev = nullptr;
+    QSV_CUDA(cudaMalloc(&dev, std::max<size_t>(bytes, 16)));
+    if (d.rank == root) QSV_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, sv->stream));
+    QSV_NCCL(ncclBroadcast(dev, dev, bytes, ncclChar, root, d.comm, sv->stream));
+    QSV_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, sv->stream));
+    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    QSV_CUDA(cudaFree(dev));
+    QSV_API_END
+}
+
+/* MPI_Scatter of a host buffer held by `root` (MPIManager::Scatter, bindings/Bindings.cpp:905-928): rank r receives
+ * bytes [r * bytes_per_rank, (r + 1) * bytes_per_rank), staged through device memory in <= 64 MiB pieces */
+int qsv_dist_scatter_host(qsv_state *sv, const void *send_host, void *recv_host, size_t bytes_per_rank, int root) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr && recv_host, "null argument");
+    sv->use();
+    DistCtx &d = *sv->dist;
+    QSV_CHECK(d.rank != root || send_host != nullptr, "null send buffer on the root rank");
+    const size_t piece = (size_t)64 << 20;
+    void *dev = nullptr;
+    QSV_CUDA(cudaMalloc(&dev, std::min(piece, std::max<size_t>(bytes_per_rank, 16))));
+    for (size_t off = 0; off < bytes_per_rank; off += piece) {
+        const size_t nb = std::min(piece, bytes_per_rank - off);
+        if (d.rank == root) {
+            for (int r = 0; r < d.world; ++r) {
+                const char *src = (const char *)send_host + (size_t)r * bytes_per_rank + off;
+                if (r == root) {
+                    memcpy((char *)recv_host + off, src, nb);
+                    continue;
+                }
+                QSV_CUDA(cudaMemcpyAsync(dev, src, nb, cudaMemcpyHostToDevice, sv->stream));
+                QSV_NCCL(ncclSend(dev, nb, ncclChar, r, d.comm, sv->stream));
+                QSV_CUDA(cudaStreamSynchronize(sv->stream));
+            }
+        } else {
+            QSV_NCCL(ncclRecv(dev, nb, ncclChar, root, d.comm, sv->stream));
+            QSV_CUDA(cudaMemcpyAsync((char *)recv_host + off, dev, nb, cudaMemcpyDeviceToHost, sv->stream));
+            QSV_CUDA(cudaStreamSynchronize(sv->stream));
+        }
+    }
+    QSV_CUDA(cudaFree(dev));
+    QSV_API_END
+}
+
+int qsv_dist_nccl_version(int *version) {
+    QSV_API_BEGIN
+    QSV_CHECK(version != nullptr, "null argument");
+    QSV_NCCL(ncclGetVersion(version));
+    QSV_API_END
+}
+
+
 int qsv_dist_last_swap_stats(const qsv_state *sv, uint64_t *bytes_sent, float *ms) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
