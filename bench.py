@@ -267,20 +267,27 @@ def run_ours(args):
     bytes_per_launch = alg_bytes_total / world * args.steps / max(launches, 1)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     sweep_bytes = 2 * amp_bytes * (1 << n_local)
+    regs_kernel = os.environ.get("QSV_TILE_KERNEL", "1") == "1" and n_local >= 12
+    fused_kernel = ("k_tile_regs (register-blocked fused tile kernel: 16 amplitudes per thread, list-scheduled passes, "
+                    "swizzled shared-memory transposes)") if regs_kernel else \
+        "k_tile_sweep (first-generation fused shared-memory tile kernel, TMA-staged)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": sweep_bytes if fused else None,
-                "traffic_source": ("ncu dram__bytes_read+write per k_tile_sweep launch = 34.3 GB = 2*B*N at 30q c128 "
+                "traffic_source": ("ncu dram__bytes_read+write per fused sweep launch = 34.3 GB = 2*B*N at 30q c128 "
                                    "(profiles/r1_ncu_summary.txt)") if fused else
                                   "ncu: 34.4 GB per full-state gate launch (profiles/r1_ncu_summary.txt); controlled gates move less",
-                "kernel": "k_tile_sweep (fused shared-memory tile kernel, TMA-staged)" if fused else
-                          "k_apply_dense / k_apply_diag (one sweep per gate)",
+                "kernel": fused_kernel if fused else "k_apply_dense / k_apply_diag (one sweep per gate)",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "gates_per_launch": len(ops) * args.steps / max(launches, 1)}
     if fused:
         roofline["hbm_actual_gbs"] = sweep_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
-        roofline["note"] = ("fused sweeps are shared-memory-bandwidth-bound (1024 clk per gate per 64 KiB tile), not "
-                            "HBM-bound: see DESIGN.md 4.2; --fuse 0 gives the HBM-bound one-sweep-per-gate kernels")
+        roofline["note"] = ("a fused sweep applies ~14-17 gates per read+write of the state, so it is bound by FP64 issue "
+                            "(64 DFMA/clk/SM) and instruction overhead rather than by HBM: see DESIGN.md 4.2; "
+                            "detail.unfused_gate_by_gate and detail.single_gate_sweeps are the HBM-bound one-sweep-per-gate kernels") \
+            if regs_kernel else \
+            ("fused sweeps are shared-memory-bandwidth-bound (1024 clk per gate per 64 KiB tile), not "
+             "HBM-bound: see DESIGN.md 4.2; --fuse 0 gives the HBM-bound one-sweep-per-gate kernels")
 
     detail = {}
     if distributed:
@@ -304,6 +311,38 @@ def run_ours(args):
                 roofline["hbm_actual_gbs"] = sweep_bytes / (roofline["ms_per_launch"] * 1e-3) / 1e9
                 roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
             roofline["exchange_note"] = "exchange time (NCCL stream) subtracted from the region before dividing by launches"
+    # ---- the same circuit gate by gate (one HBM sweep per gate) and in complex64 ----------------
+    if args.sweeps and not distributed and args.fuse:
+        def timed_circuit(vec, fuse, reps=2):
+            for _ in range(3):
+                vec.apply_ops(rec, fuse=fuse)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                vec.apply_ops(rec, fuse=fuse)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        t = timed_circuit(sv, False)
+        detail["unfused_gate_by_gate"] = {"ms_per_step": t, "value_gbs": alg_bytes_total / (t * 1e-3) / 1e9,
+                                          "frac_of_peak": alg_bytes_total / (t * 1e-3) / 1e9 / hbm_peak,
+                                          "kernel": "k_apply_dense / k_apply_diag, HBM-bound"}
+        if args.dtype == "c128":
+            buf32 = torch.empty((1 << n_local) * 2, dtype=torch.float32, device=dev)
+            for s0 in range(0, buf32.numel(), chunk):
+                buf32[s0:s0 + chunk].copy_(buf[s0:s0 + chunk])
+            sv32 = q.StateVector(n_local, np.complex64, device=local_rank, external_ptr=buf32.data_ptr())
+            b32 = circuit_bytes(ops, n_total, 8)
+            t = timed_circuit(sv32, True, reps=3)
+            l32, _ = sv32.last_apply_stats()
+            detail["config2_complex64"] = {"ms_per_step": t, "value_gbs": b32 / (t * 1e-3) / 1e9, "launches_per_step": l32,
+                                           "hbm_actual_frac": 2 * 8 * (1 << n_local) * l32 / (t * 1e-3) / 1e9 / hbm_peak}
+            t = timed_circuit(sv32, False)
+            detail["config2_complex64"]["unfused_ms_per_step"] = t
+            detail["config2_complex64"]["unfused_frac_of_peak"] = b32 / (t * 1e-3) / 1e9 / hbm_peak
+            del sv32, buf32
     # ---- single-gate sweeps: C2(i), every target wire individually ----------------------------
     if args.sweeps and not distributed:
         detail["single_gate_sweeps"] = single_gate_sweeps(torch, q, sv, n_local, amp_bytes, hbm_peak)

@@ -167,6 +167,87 @@ def measurements_and_adjoint(rank, local_rank, world, g):
     return failures
 
 
+def pybind_twins(rank, local_rank, world, g):
+    """The reference's Python-visible MPI classes (bindings/Bindings.cpp:890-1720) driven the way lightning_gpu.py
+    does (:286-294, :429, :840-852), against the oracle."""
+    from pennylane_lightning_gpu_b200 import lightning_gpu_qubit_ops as m
+
+    failures = []
+    n = g + 7
+    mgr = m.MPIManager()
+    if (mgr.getRank(), mgr.getSize()) != (rank, world) or mgr.getVendor() != "NCCL":
+        failures.append("MPIManager rank/size")
+    mgr.Barrier()
+    rng = np.random.default_rng(21)
+    psi0 = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi0 /= np.linalg.norm(psi0)
+    for bits, dtype, tol in (("128", np.complex128, 1e-10), ("64", np.complex64, 5e-5)):
+        sv = getattr(m, "LightningGPUMPI_C" + bits)(mgr, m.DevTag(local_rank), 0, g, n - g)
+        if (sv.numLocalQubits(), sv.numGlobalQubits(), sv.dataLength()) != (n - g, g, 1 << (n - g)):
+            failures.append("MPI state-vector sizes")
+        # lightning_gpu.py:429: scatter the full state from rank 0, then HostToDevice of the local shard
+        local = np.zeros(1 << (n - g), dtype=dtype)
+        mgr.Scatter(psi0.astype(dtype) if rank == 0 else np.zeros(1 << n, dtype=dtype), local, 0)
+        sv.HostToDevice(local, False)
+        ops = [("Hadamard", [0], []), ("RX", [0], [0.3]), ("CNOT", [0, n - 1], []), ("RY", [n - 1], [0.7]),
+               ("CRZ", [1, 0], [0.2]), ("IsingXX", [0, 1], [0.5]), ("Toffoli", [0, 1, 2], []), ("Rot", [0], [0.1, 0.2, 0.3])]
+        want = psi0.copy()
+        for name, wires, params in ops:
+            getattr(sv, name)(wires, False, params)
+            want = orc.apply_op(want, name, wires, params)
+        mat = orc.gate_matrix("RY", [0.4])
+        sv.apply("QubitUnitary", [0], False, [], mat.ravel().astype(dtype))
+        want = orc.apply_op(want, "QubitUnitary", [0], [], matrix=mat)
+
+        def check(what, got, ref, scale=20.0):
+            err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
+            if not err <= tol * scale:
+                failures.append(f"pybind C{bits} {what}: err {err:.2e}")
+            if rank == 0:
+                print(f"[dist_check] pybind C{bits} {what}: err={err:.2e}", flush=True)
+
+        out = np.zeros(1 << (n - g), dtype=dtype)
+        sv.DeviceToHost(out, False)
+        check("state shard", out, want[rank << (n - g):(rank + 1) << (n - g)])
+        check("expval PauliZ(0)", sv.ExpectationValue("PauliZ", [0], [], np.zeros(0, dtype=dtype)), orc.expval_named(want, "PauliZ", [0]))
+        words, wires, coeffs = ["XZ", "Y", "ZZ"], [[0, 1], [n - 1], [0, 2]], np.array([0.3, -0.5, 0.9], dtype=dtype)
+        check("expval Pauli words", sv.ExpectationValue(words, wires, coeffs), orc.expval_pauli_words(want, words, wires, coeffs))
+        check("probability", sv.Probability([0, n - 1]), orc.probs_custatevec_order(want, [0, n - 1]))
+        samples = sv.GenerateSamples(n, 100)
+        if samples.shape != (100, n) or samples.max() > 1:
+            failures.append("GenerateSamples shape")
+        # sparse Hamiltonian given on rank 0 only (lightning_gpu.py:840-852)
+        sp, (w2, ws2, c2) = workloads.molecular_style_sparse_hamiltonian(n, n_terms=30, n_flip_masks=5, seed=3)
+        idt = np.int64 if bits == "128" else np.int32
+        if rank == 0:
+            got = sv.ExpectationValue(sp.indptr.astype(idt), sp.indices.astype(idt), sp.data.astype(dtype))
+        else:
+            got = sv.ExpectationValue(np.array([0, 1, 2], dtype=idt), np.array([0, 1], dtype=idt), np.ones(2, dtype=dtype))
+        check("sparse expval (rank-0 matrix)", got, orc.expval_csr(want, sp.indptr, sp.indices, sp.data), 100.0)
+        # adjoint Jacobian through the MPI twins
+        names = ["RX", "CNOT", "RY", "RZ", "CRX"]
+        params = [np.array([0.3]), np.array([]), np.array([-0.7]), np.array([1.1]), np.array([0.5])]
+        awires = [[0], [0, 1], [n - 1], [0], [0, 2]]
+        aops = [{"name": a, "wires": w, "params": list(p)} for a, w, p in zip(names, awires, params)]
+        adj = getattr(m, "AdjointJacobianGPUMPI_C" + bits)()
+        rdt = np.float64 if bits == "128" else np.float32
+        rec = adj.create_ops_list(names, [p.astype(rdt) for p in params], awires, [False] * 5, [np.zeros(0, dtype=dtype)] * 5)
+        sv2 = getattr(m, "LightningGPUMPI_C" + bits)(mgr, m.DevTag(local_rank), 0, g, n - g)
+        for a, w, p in zip(names, awires, params):
+            getattr(sv2, a)(w, False, list(p))
+        Named = getattr(m, "NamedObsGPUMPI_C" + bits)
+        Tensor = getattr(m, "TensorProdObsGPUMPI_C" + bits)
+        Ham = getattr(m, "HamiltonianGPUMPI_C" + bits)
+        obs = [Named("PauliZ", [0]), Ham(np.array([0.4, -0.8], dtype=rdt), [Named("PauliX", [0]), Tensor([Named("PauliZ", [0]), Named("PauliY", [n - 1])])])]
+        obs_t = [("Named", "PauliZ", [0]), ("Hamiltonian", [0.4, -0.8], [("Named", "PauliX", [0]), ("TensorProd", [("Named", "PauliZ", [0]), ("Named", "PauliY", [n - 1])])])]
+        fin = orc.apply_ops(orc.basis_state(n), aops)
+        jref = orc.adjoint_jacobian(fin, aops, obs_t, [0, 1, 2, 3])
+        check("adjoint_jacobian", adj.adjoint_jacobian(sv2, obs, rec, [0, 1, 2, 3]), jref, 100.0)
+        check("adjoint_jacobian_serial", adj.adjoint_jacobian_serial(sv2, obs, rec, [0, 1, 2, 3]), jref, 100.0)
+        del sv, sv2
+    return failures
+
+
 def main():
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -206,6 +287,7 @@ def main():
                         print(f"[dist_check] {tag}: err={err:.2e} expval_err={abs(ev - ev_want):.2e} swaps={n_swaps}", flush=True)
                     sv.close()
     failures += measurements_and_adjoint(rank, local_rank, world, g)
+    failures += pybind_twins(rank, local_rank, world, g)
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -90,3 +90,27 @@ def test_workload_generators():
     psi = np.random.default_rng(0).normal(size=256) + 1j * np.random.default_rng(1).normal(size=256)
     psi /= np.linalg.norm(psi)
     assert abs(orc.expval_csr(psi, m.indptr, m.indices, m.data) - orc.expval_pauli_words(psi, w2, ws2, c2)) < 1e-12
+
+
+def test_pybind_module_has_the_reference_names():
+    """Python-visible names of bindings/Bindings.cpp:67-877, 890-1720, 1727-1777 of the reference (import only)."""
+    from pennylane_lightning_gpu_b200 import lightning_gpu_qubit_ops as m
+
+    names = ["DevPool", "DevTag", "PLException", "MPIManager", "device_reset", "allToAllAccess", "is_gpu_supported",
+             "get_gpu_arch"]
+    for bits in ("64", "128"):
+        for mpi in ("", "MPI"):
+            names += [f"LightningGPU{mpi}_C{bits}", f"NamedObsGPU{mpi}_C{bits}", f"HermitianObsGPU{mpi}_C{bits}",
+                      f"TensorProdObsGPU{mpi}_C{bits}", f"HamiltonianGPU{mpi}_C{bits}", f"SparseHamiltonianGPU{mpi}_C{bits}",
+                      f"OpsStructGPU{mpi}_C{bits}", f"AdjointJacobianGPU{mpi}_C{bits}"]
+    missing = [n for n in names if not hasattr(m, n)]
+    assert not missing, missing
+    for cls in (m.LightningGPU_C128, m.LightningGPUMPI_C128):
+        for meth in ("setBasisState", "setStateVector", "apply", "ExpectationValue", "Probability", "GenerateSamples",
+                     "DeviceToHost", "HostToDevice", "DeviceToDevice", "RX", "CNOT", "DoubleExcitationPlus", "MultiRZ"):
+            assert hasattr(cls, meth), (cls, meth)
+    for meth in ("numLocalQubits", "numGlobalQubits", "dataLength", "resetGPU"):
+        assert hasattr(m.LightningGPUMPI_C128, meth)
+    for meth in ("Barrier", "getRank", "getSize", "getSizeNode", "getTime", "getVendor", "getVersion", "Scatter"):
+        assert hasattr(m.MPIManager, meth)
+    assert hasattr(m.AdjointJacobianGPUMPI_C128, "adjoint_jacobian_serial")
