@@ -1,0 +1,234 @@
+// Batched generator inner products for the adjoint method: Im/Re <bra| G_k |ket> for MANY generators G_k in one
+// read of (bra, ket).
+//
+// The reference evaluates one trainable parameter at a time (algorithms/AdjointDiffGPU.hpp:562-592: copy lambda to
+// mu, apply the generator to mu, one cuBLAS dot per observable, one D2H per parameter).  Generators of gates that
+// act on disjoint wires commute with each other and with each other's gates, so a whole layer of rotations can be
+// differentiated against the SAME pair of vectors (see adjoint_jacobian in circuit.cu).  This kernel does that:
+// a CTA stages a tile of `ket` in shared memory (the low L index bits plus arbitrary high bits, like the fused gate
+// kernels), keeps the matching `bra` amplitudes in registers, and accumulates conj(bra_i) * (G_k ket)_i for every
+// generator whose non-diagonal target bit lies inside the tile; diagonal / parity generators can sit on any bit.
+// One warp-shuffle reduction per generator and warp, one atomicAdd pair per generator and CTA.
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "qsv_internal.h"
+
+namespace qsv {
+
+namespace {
+
+constexpr int GT_TB = 11;        // tile bits: 2^11 amplitudes of ket in shared memory (32 KiB complex128)
+constexpr int GT_NT = 256;
+constexpr int GT_EPT = (1 << GT_TB) / GT_NT;  // 8 amplitudes per thread
+constexpr int GT_MAX = 32;       // generators per launch
+
+struct GenDesc {
+    int kind;            // 0: diagonal table (<= 1 table bit: parity of index & zmask), 1: 2x2 block on one tile bit
+    int slot;            // complex output slot
+    unsigned tbit;       // kind 1: tile-local position of the target bit
+    unsigned pad0;
+    uint64_t ctrl;       // global bits that must be 1
+    uint64_t zmask;      // kind 0: global bits whose parity selects the phase
+    double m[8];         // kind 1: row-major complex 2x2; kind 0: phase for even parity, phase for odd parity
+};
+
+struct GenProgram {
+    int n_gens;
+    int L;
+    unsigned char hi_bits[16];  // global positions of tile bits L..GT_TB-1
+    Holes tile_holes;
+    GenDesc g[GT_MAX];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GT_NT)
+    k_bra_gens_ket(const void *__restrict__ bra, const void *__restrict__ ket, double *out,
+                   const __grid_constant__ GenProgram P) {
+    using A = typename VecOf<T, 1>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A *s = reinterpret_cast<A *>(smem_raw);
+    __shared__ double s_acc[GT_MAX][2];
+    const uint64_t base = expand_index((uint64_t)blockIdx.x, P.tile_holes);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 2 * GT_MAX; i += GT_NT) (&s_acc[0][0])[i] = 0.0;
+
+    // element e of the tile (local index) lives at global index base | deposit(e)
+    A b[GT_EPT];
+    uint64_t gidx[GT_EPT];
+#pragma unroll
+    for (int j = 0; j < GT_EPT; ++j) {
+        const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
+        uint64_t off = e & ((1u << P.L) - 1u);
+        for (int q = P.L; q < GT_TB; ++q) off |= (uint64_t)((e >> q) & 1u) << P.hi_bits[q - P.L];
+        gidx[j] = base | off;
+        s[e] = reinterpret_cast<const A *>(ket)[gidx[j]];
+        b[j] = reinterpret_cast<const A *>(bra)[gidx[j]];
+    }
+    __syncthreads();
+
+    for (int k = 0; k < P.n_gens; ++k) {
+        const GenDesc &g = P.g[k];
+        double re = 0.0, im = 0.0;
+        if (g.kind == 0) {
+            const double e0r = g.m[0], e0i = g.m[1], e1r = g.m[2], e1i = g.m[3];
+#pragma unroll
+            for (int j = 0; j < GT_EPT; ++j) {
+                if ((gidx[j] & g.ctrl) != g.ctrl) continue;
+                const bool odd = __popcll(gidx[j] & g.zmask) & 1;
+                const double pr = odd ? e1r : e0r, pi = odd ? e1i : e0i;
+                const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
+                const double yr = pr * (double)x.x - pi * (double)x.y, yi = pr * (double)x.y + pi * (double)x.x;
+                re += (double)b[j].x * yr + (double)b[j].y * yi;
+                im += (double)b[j].x * yi - (double)b[j].y * yr;
+            }
+        } else {
+            const uint32_t bit = 1u << g.tbit;
+            const double m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
+            const double m4 = g.m[4], m5 = g.m[5], m6 = g.m[6], m7 = g.m[7];
+#pragma unroll
+            for (int j = 0; j < GT_EPT; ++j) {
+                if ((gidx[j] & g.ctrl) != g.ctrl) continue;
+                const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
+                const A x0 = s[e & ~bit], x1 = s[e | bit];
+                const bool hi = (e & bit) != 0;
+                const double ar = hi ? m4 : m0, ai = hi ? m5 : m1, br = hi ? m6 : m2, bi = hi ? m7 : m3;
+                const double yr = ar * (double)x0.x - ai * (double)x0.y + br * (double)x1.x - bi * (double)x1.y;
+                const double yi = ar * (double)x0.y + ai * (double)x0.x + br * (double)x1.y + bi * (double)x1.x;
+                re += (double)b[j].x * yr + (double)b[j].y * yi;
+                im += (double)b[j].x * yi - (double)b[j].y * yr;
+            }
+        }
+        re = warp_sum(re);
+        im = warp_sum(im);
+        if (lane == 0) {
+            atomicAdd(&s_acc[k][0], re);
+            atomicAdd(&s_acc[k][1], im);
+        }
+    }
+    __syncthreads();
+    if (tid < P.n_gens) {
+        atomicAdd(out + 2 * (size_t)P.g[tid].slot, s_acc[tid][0]);
+        atomicAdd(out + 2 * (size_t)P.g[tid].slot + 1, s_acc[tid][1]);
+    }
+}
+
+// which generators the tile kernel takes; everything else goes through launch_bra_op_ket one by one
+bool tile_gen_kind(const LoweredGate &g, int n, int &kind) {
+    if (g.kind == LoweredGate::PARITY) {
+        kind = 0;
+        return true;
+    }
+    if (g.kind == LoweredGate::DIAG && g.k <= 1) {
+        kind = 0;
+        return true;
+    }
+    if (g.kind == LoweredGate::DENSE && g.k == 1 && g.tgt_bits.size() == 1 && g.offs[0] == 0 && g.tgt_bits[0] < n) {
+        kind = 1;
+        return true;
+    }
+    return false;
+}
+
+template <typename T> void launch_gens_t(State &sv, const void *bra, const void *ket, double *out, const GenProgram &P) {
+    const size_t smem = ((size_t)1 << GT_TB) * sizeof(typename VecOf<T, 1>::type);
+    const unsigned grid = (unsigned)(1ull << (sv.n - GT_TB));
+    k_bra_gens_ket<T><<<grid, GT_NT, smem, sv.stream>>>(bra, ket, out, P);
+    QSV_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+// out_dev[2 * slots[k] ..] += <bra| gens[k] |ket> (re, im) for every k, with as few reads of the vectors as the
+// tile size allows.  Generators are LoweredGates used as operators (controls = projectors).
+void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std::vector<LoweredGate> &gens,
+                         const std::vector<int> &slots, double *out_dev) {
+    sv.use();
+    const int n = sv.n;
+    std::vector<size_t> todo;
+    for (size_t k = 0; k < gens.size(); ++k) {
+        int kind;
+        if (gens[k].kind == LoweredGate::NOP) continue;  // a projector that is zero on this shard
+        if (n >= GT_TB && tile_gen_kind(gens[k], n, kind))
+            todo.push_back(k);
+        else
+            launch_bra_op_ket(sv, bra, ket, gens[k], out_dev, slots[k]);
+    }
+    const int L = 4;
+    const int max_hi = GT_TB - L;
+    while (!todo.empty()) {
+        // one launch: up to GT_MAX generators whose non-diagonal target bits >= L number at most max_hi
+        GenProgram P;
+        memset(&P, 0, sizeof(P));
+        P.L = L;
+        uint64_t need = 0;
+        std::vector<size_t> rest, take;
+        for (size_t k : todo) {
+            int kind = 0;
+            tile_gen_kind(gens[k], n, kind);
+            uint64_t nb = 0;
+            if (kind == 1 && gens[k].tgt_bits[0] >= L) nb = 1ull << gens[k].tgt_bits[0];
+            if ((int)take.size() < GT_MAX && __builtin_popcountll(need | nb) <= max_hi) {
+                take.push_back(k);
+                need |= nb;
+            } else {
+                rest.push_back(k);
+            }
+        }
+        std::vector<int> hi;
+        for (int b = L; b < n; ++b)
+            if (need >> b & 1) hi.push_back(b);
+        for (int b = L; b < n && (int)hi.size() < max_hi; ++b)
+            if (!(need >> b & 1)) hi.push_back(b);
+        std::sort(hi.begin(), hi.end());
+        int pos[64];
+        for (int b = 0; b < 64; ++b) pos[b] = -1;
+        std::vector<int> tile_bits;
+        for (int b = 0; b < L; ++b) {
+            pos[b] = b;
+            tile_bits.push_back(b);
+        }
+        for (int j = 0; j < (int)hi.size(); ++j) {
+            pos[hi[j]] = L + j;
+            P.hi_bits[j] = (unsigned char)hi[j];
+            tile_bits.push_back(hi[j]);
+        }
+        P.tile_holes = make_holes(tile_bits.data(), (int)tile_bits.size(), 0);
+        for (size_t k : take) {
+            const LoweredGate &g = gens[k];
+            GenDesc &d = P.g[P.n_gens++];
+            int kind = 0;
+            tile_gen_kind(g, n, kind);
+            d.kind = kind;
+            d.slot = slots[k];
+            d.ctrl = g.ctrl_mask;
+            if (kind == 1) {
+                d.tbit = (unsigned)pos[g.tgt_bits[0]];
+                for (int q = 0; q < 4; ++q) {
+                    d.m[2 * q] = g.mat[q].real();
+                    d.m[2 * q + 1] = g.mat[q].imag();
+                }
+            } else if (g.kind == LoweredGate::PARITY) {
+                d.zmask = g.zmask;
+                d.m[0] = g.mat[0].real();
+                d.m[1] = g.mat[0].imag();
+                d.m[2] = g.mat[1].real();
+                d.m[3] = g.mat[1].imag();
+            } else {  // DIAG with 0 or 1 table bits
+                d.zmask = g.k == 1 ? (1ull << g.tgt_bits[0]) : 0;
+                d.m[0] = g.mat[0].real();
+                d.m[1] = g.mat[0].imag();
+                d.m[2] = g.k == 1 ? g.mat[1].real() : g.mat[0].real();
+                d.m[3] = g.k == 1 ? g.mat[1].imag() : g.mat[0].imag();
+            }
+        }
+        sv.stat_launches += 1;
+        if (sv.dtype == QSV_C128)
+            launch_gens_t<double>(sv, bra, ket, out_dev, P);
+        else
+            launch_gens_t<float>(sv, bra, ket, out_dev, P);
+        todo.swap(rest);
+    }
+}
+
+}  // namespace qsv

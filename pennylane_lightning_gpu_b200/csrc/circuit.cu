@@ -12,6 +12,8 @@
 //   * a Hamiltonian of Pauli words is applied by one gather kernel, not by per-term
 //     copy + apply + axpy (ObservablesGPU.hpp:346-362).
 #include <algorithm>
+#include <cstdlib>
+#include <functional>
 
 #include "qsv_internal.h"
 
@@ -320,6 +322,115 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
 
     size_t n_par_ops = 0;
     for (const auto &op : ops.ops) n_par_ops += op.params.empty() ? 0 : 1;
+    const char *batch_env = std::getenv("QSV_ADJOINT_BATCH");
+    if (!(batch_env && std::atoi(batch_env) == 0)) {
+        // ---- layered reverse sweep ---------------------------------------------------------------
+        // Gates on disjoint wires commute, and so do their generators.  An op is READY when every later op that
+        // shares a wire with it has already been undone; all ready ops are pairwise disjoint, so the generator
+        // inner products of the trainable ones can all be taken against the current (bra, lambda) -- one batched
+        // launch per observable -- and their U^dagger, followed by every non-trainable op that becomes ready
+        // behind them (e.g. a whole CNOT ladder), go into one fused multi-gate sweep over lambda and all bras.
+        const int64_t n_ops = (int64_t)ops.ops.size();
+        std::vector<int64_t> tp_of(n_ops, -1);
+        int64_t first_needed = n_ops;
+        {
+            int64_t cur = 0;
+            size_t t = 0;
+            for (int64_t idx = 0; idx < n_ops; ++idx) {
+                if (ops.ops[idx].params.empty()) continue;
+                while (t < n_tp && trainable[t] < cur) ++t;
+                if (t < n_tp && trainable[t] == cur) {
+                    tp_of[idx] = (int64_t)t;
+                    first_needed = std::min(first_needed, idx);
+                }
+                ++cur;
+            }
+        }
+        auto skipped = [&](const Op &op) {
+            return op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState";
+        };
+        // per wire: the ops that touch it, in program order; an op is ready when it is the last pending op on
+        // every one of its wires
+        std::vector<std::vector<int64_t>> on_wire(sv.n);
+        for (int64_t idx = first_needed; idx < n_ops; ++idx) {
+            if (skipped(ops.ops[idx])) continue;
+            for (int w : ops.ops[idx].wires) {
+                QSV_CHECK(w >= 0 && w < sv.n, "wire out of range");
+                on_wire[w].push_back(idx);
+            }
+        }
+        std::vector<char> done(n_ops, 0);
+        auto is_ready = [&](int64_t idx) {
+            for (int w : ops.ops[idx].wires)
+                if (on_wire[w].empty() || on_wire[w].back() != idx) return false;
+            return true;
+        };
+        auto retire = [&](int64_t idx) {
+            done[idx] = 1;
+            for (int w : ops.ops[idx].wires) on_wire[w].pop_back();
+        };
+        size_t pending = 0;
+        for (int64_t idx = first_needed; idx < n_ops; ++idx) pending += skipped(ops.ops[idx]) ? 0 : 1;
+        while (pending) {
+            std::vector<int64_t> ready;
+            for (int w = 0; w < sv.n; ++w)
+                if (!on_wire[w].empty() && is_ready(on_wire[w].back()) &&
+                    std::find(ready.begin(), ready.end(), on_wire[w].back()) == ready.end())
+                    ready.push_back(on_wire[w].back());
+            QSV_CHECK(!ready.empty(), "internal: adjoint scheduling made no progress");
+            std::sort(ready.begin(), ready.end(), std::greater<int64_t>());
+            // generator inner products of the trainable ready ops, all against the current vectors
+            std::vector<LoweredGate> gens;
+            std::vector<int> gen_slot0;
+            for (int64_t idx : ready) {
+                const int64_t tp = tp_of[idx];
+                if (tp < 0) continue;
+                const Op &op = ops.ops[idx];
+                LoweredGenerator g = lower_generator(sv.n, op.name, op.wires);
+                factor[tp] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
+                extra[tp] = g.extra_identity;
+                gens.push_back(std::move(g.op));
+                gen_slot0.push_back((int)(tp * n_obs * 2));
+                if (g.extra_identity != 0.0) {
+                    LoweredGate id;
+                    for (size_t i = 0; i < n_obs; ++i)
+                        launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
+                }
+            }
+            if (!gens.empty()) {
+                std::vector<int> slots(gens.size());
+                for (size_t i = 0; i < n_obs; ++i) {
+                    for (size_t k = 0; k < gens.size(); ++k) slots[k] = gen_slot0[k] + (int)(2 * i);
+                    launch_bra_gens_ket(sv, vecs[1 + i]->data, lambda.data, gens, slots, red);
+                }
+            }
+            // undo the ready ops and everything non-trainable that becomes ready behind them, in one fused batch
+            std::vector<LoweredGate> batch;
+            auto take = [&](int64_t idx) {
+                if (ops.ops[idx].name != "Identity") batch.push_back(lower_op(sv, ops.ops[idx], true));
+                retire(idx);
+                --pending;
+            };
+            for (int64_t idx : ready) take(idx);
+            bool grew = true;
+            while (grew && pending) {
+                grew = false;
+                for (int w = 0; w < sv.n; ++w) {
+                    if (on_wire[w].empty()) continue;
+                    const int64_t idx = on_wire[w].back();
+                    if (tp_of[idx] >= 0 || !is_ready(idx)) continue;
+                    take(idx);
+                    grew = true;
+                }
+            }
+            // is any trainable op left?  if not, the remaining daggers are not needed
+            if (!batch.empty()) apply_gates_tiled(sv, batch, (void *const *)d_table.p, (int)(1 + n_obs));
+            bool trainable_left = false;
+            for (int64_t idx = first_needed; idx < n_ops && !trainable_left; ++idx)
+                trainable_left = !done[idx] && tp_of[idx] >= 0;
+            if (!trainable_left) break;
+        }
+    } else {
     int64_t tp_pos = (int64_t)n_tp - 1;
     int64_t cur = (int64_t)n_par_ops - 1;
     for (int64_t idx = (int64_t)ops.ops.size() - 1; idx >= 0; --idx) {
@@ -346,6 +457,7 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
         // lambda <- U^dagger lambda and H_lambda[i] <- U^dagger H_lambda[i], one launch
         if (op.name != "Identity")
             launch_gate_multi(sv, lower_op(sv, op, true), (void *const *)d_table.p, (int)(1 + n_obs));
+    }
     }
     std::vector<double> h(2 * n_slots);
     reduction_read(sv, red, h.data(), 2 * n_slots);

@@ -161,6 +161,10 @@ void launch_axpy(State &sv, cplx alpha, const void *x, void *y);
 // results (re, im) are accumulated as doubles into out_dev[2*slot..] asynchronously.
 void launch_bra_op_ket(State &sv, const void *bra, const void *ket, const LoweredGate &op,
                        double *out_dev, int slot);
+// out_dev[2 * slots[k] ..] += <bra| gens[k] |ket> for many generators in as few reads of (bra, ket) as possible
+// (adjoint_kernels.cu)
+void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std::vector<LoweredGate> &gens,
+                         const std::vector<int> &slots, double *out_dev);
 // <bra| P |ket> for a Pauli word given by masks; result *(i^ny) applied on device
 void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t xmask, uint64_t zmask,
                           int ny, double *out_dev, int slot);

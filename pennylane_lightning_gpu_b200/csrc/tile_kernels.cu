@@ -545,7 +545,7 @@ std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> 
 // L as small as one warp-wide access allows, and the gates of a sweep are list-scheduled into register passes.
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
     const bool f32 = sv.dtype == QSV_C64;
-    int L = env_int("QSV_REGS_LOW", f32 ? 6 : 4);  // measured on B200 (profiles/r1_regs_ab.txt)
+    int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const int max_hi = 12 - L;
     const bool merge = env_int("QSV_MERGE_1Q", 1) != 0;

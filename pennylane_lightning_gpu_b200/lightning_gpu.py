@@ -67,7 +67,8 @@ _STATE_PREPS = ("QubitStateVector", "StatePrep", "BasisState")
 
 
 class LightningGPU(_Base):
-    """B200-native ``lightning.gpu`` device (single GPU)."""
+    """B200-native ``lightning.gpu`` device: one GPU, or with ``mpi=True`` one process per GPU (torchrun / mpirun)
+    sharing one register through NCCL / NVLink peer access."""
 
     name = "B200-native Lightning GPU device"
     short_name = "lightning.gpu"
@@ -81,9 +82,10 @@ class LightningGPU(_Base):
             self.use_csingle, self.R_DTYPE, self.C_DTYPE, bits = False, np.float64, np.complex128, "128"
         else:
             raise TypeError(f"Unsupported complex Type: {c_dtype}")
-        if mpi:
-            raise NotImplementedError("use pennylane_lightning_gpu_b200.distributed.DistributedStateVector "
-                                      "(torchrun + NCCL) for sharded registers")
+        if mpi_buf_size < 0:
+            raise TypeError(f"Unsupported mpi_buf_size value: {mpi_buf_size}")
+        if mpi_buf_size and mpi_buf_size & (mpi_buf_size - 1):
+            raise TypeError(f"Unsupported mpi_buf_size value: {mpi_buf_size}. mpi_buf_size should be power of 2.")
         if _Base is not object:
             super().__init__(wires, shots=shots, r_dtype=self.R_DTYPE, c_dtype=self.C_DTYPE)
         else:
@@ -94,7 +96,23 @@ class LightningGPU(_Base):
         self._batch_obs = batch_obs
         self._seed = seed
         self._dp = _ops.DevPool()
-        self._gpu_state = getattr(_ops, "LightningGPU_C" + bits)(self.num_wires)
+        self._mpi = bool(mpi)
+        if not mpi:
+            self._num_local_wires = self.num_wires
+            self._gpu_state = getattr(_ops, "LightningGPU_C" + bits)(self.num_wires)
+        else:
+            # lightning_gpu.py:298-324: one process per GPU (torchrun / mpirun), top log2(P) wires are global
+            self._mpi_manager = _ops.MPIManager()
+            if self._dp.getTotalDevices() < self._mpi_manager.getSizeNode():
+                raise ValueError("Number of devices should be larger than or equal to the number of processes on each node.")
+            if self._mpi_manager.getSize() > (1 << (self.num_wires - 1)):
+                raise ValueError("Number of processes should be smaller than the number of statevector elements.")
+            self._num_global_wires = self._mpi_manager.getSize().bit_length() - 1
+            self._num_local_wires = self.num_wires - self._num_global_wires
+            deviceid = self._mpi_manager.getRank() % self._mpi_manager.getSizeNode()
+            self._devtag = _ops.DevTag(deviceid)
+            self._gpu_state = getattr(_ops, "LightningGPUMPI_C" + bits)(self._mpi_manager, self._devtag, mpi_buf_size,
+                                                                        self._num_global_wires, self._num_local_wires)
         self._state_host = None
         self._samples = None
 
@@ -107,7 +125,8 @@ class LightningGPU(_Base):
 
     @property
     def state(self) -> np.ndarray:
-        out = np.zeros(1 << self.num_wires, dtype=self.C_DTYPE)
+        """The state vector; with mpi=True this rank's shard (doc/devices.rst:130-151 of the reference)."""
+        out = np.zeros(1 << self._num_local_wires, dtype=self.C_DTYPE)
         self._gpu_state.DeviceToHost(out, False)
         return out
 
@@ -126,6 +145,10 @@ class LightningGPU(_Base):
         state = np.asarray(state, dtype=self.C_DTYPE).reshape(-1)
         device_wires = list(device_wires)
         if len(device_wires) == self.num_wires and device_wires == sorted(device_wires):
+            if self._mpi:
+                local = np.zeros(1 << self._num_local_wires, dtype=self.C_DTYPE)
+                self._mpi_manager.Scatter(state, local, 0)  # lightning_gpu.py:427-431
+                state = local
             self.syncH2D(state, use_async)
             return
         n = self.num_wires
@@ -177,20 +200,23 @@ class LightningGPU(_Base):
 
     # ---- measurements ---------------------------------------------------------------------------
     def _serialize_obs(self, o: Obs):
-        b = self._bits
+        b = ("MPI_C" if self._mpi else "_C") + self._bits
+        return self._serialize_obs_as(o, b)
+
+    def _serialize_obs_as(self, o: Obs, b: str):
         if o.name in ("PauliX", "PauliY", "PauliZ", "Hadamard", "Identity"):
-            return getattr(_ops, "NamedObsGPU_C" + b)(o.name, list(o.wires))
+            return getattr(_ops, "NamedObsGPU" + b)(o.name, list(o.wires))
         if o.name == "Hermitian":
-            return getattr(_ops, "HermitianObsGPU_C" + b)(np.asarray(o.matrix, dtype=self.C_DTYPE).reshape(-1), list(o.wires))
+            return getattr(_ops, "HermitianObsGPU" + b)(np.asarray(o.matrix, dtype=self.C_DTYPE).reshape(-1), list(o.wires))
         if o.name == "Tensor":
-            return getattr(_ops, "TensorProdObsGPU_C" + b)([self._serialize_obs(t) for t in o.terms])
+            return getattr(_ops, "TensorProdObsGPU" + b)([self._serialize_obs_as(t, b) for t in o.terms])
         if o.name == "Hamiltonian":
-            return getattr(_ops, "HamiltonianGPU_C" + b)(np.asarray(o.coeffs, dtype=self.R_DTYPE),
-                                                         [self._serialize_obs(t) for t in o.terms])
+            return getattr(_ops, "HamiltonianGPU" + b)(np.asarray(o.coeffs, dtype=self.R_DTYPE),
+                                                        [self._serialize_obs_as(t, b) for t in o.terms])
         if o.name == "SparseHamiltonian":
             indptr, indices, data = o.csr
             idt = np.int32 if self.use_csingle else np.int64
-            return getattr(_ops, "SparseHamiltonianGPU_C" + b)(np.asarray(data, dtype=self.C_DTYPE),
+            return getattr(_ops, "SparseHamiltonianGPU" + b)(np.asarray(data, dtype=self.C_DTYPE),
                                                                np.asarray(indices, dtype=idt),
                                                                np.asarray(indptr, dtype=idt), list(range(self.num_wires)))
         raise ValueError(f"unsupported observable {o.name}")
@@ -268,7 +294,7 @@ class LightningGPU(_Base):
         word = self._pauli_word(observable)
         if word is None:
             raise NotImplementedError("sampling is implemented for Pauli words")
-        saved = getattr(_ops, "LightningGPU_C" + self._bits)(self._gpu_state)
+        saved = type(self._gpu_state)(self._gpu_state)
         for letter, w in zip(*word):
             if letter == "X":
                 self._gpu_state.Hadamard([w], False, [])
@@ -327,10 +353,13 @@ class LightningGPU(_Base):
         tp = list(range(n_par)) if trainable_params is None else sorted(trainable_params)
         if not tp:
             return np.zeros((len(observables), 0), dtype=self.R_DTYPE)
-        adj = getattr(_ops, "AdjointJacobianGPU_C" + self._bits)()
+        adj = getattr(_ops, ("AdjointJacobianGPUMPI_C" if self._mpi else "AdjointJacobianGPU_C") + self._bits)()
         rec = adj.create_ops_list(names, params, wires, invs, mats)
         obs = [self._serialize_obs(o) for o in observables]
-        fn = adj.adjoint_jacobian_batched if self._batch_obs else adj.adjoint_jacobian
+        if self._mpi:  # batch_obs = memory-saving one-observable-at-a-time sweep (lightning_gpu.py:704-737)
+            fn = adj.adjoint_jacobian_serial if self._batch_obs else adj.adjoint_jacobian
+        else:
+            fn = adj.adjoint_jacobian_batched if self._batch_obs else adj.adjoint_jacobian
         return np.asarray(fn(self._gpu_state, obs, rec, tp))
 
     def vjp(self, operations, observables, dy, trainable_params=None, **kw) -> np.ndarray:

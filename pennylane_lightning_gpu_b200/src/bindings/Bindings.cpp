@@ -296,6 +296,7 @@ template <class PrecisionT> void register_precision_mpi(py::module_ &m) {
                  return new SV(mpi_manager, devtag_local, mpi_buf_size, num_global_qubits, num_local_qubits);
              }),
              py::keep_alive<1, 2>())
+        .def(py::init<const SV &>())
         .def(
             "setBasisState", [](SV &sv, std::size_t index, bool use_async) { sv.setBasisState({1, 0}, index, use_async); },
             "Create Basis State on GPU.")

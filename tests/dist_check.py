@@ -248,6 +248,54 @@ def pybind_twins(rank, local_rank, world, g):
     return failures
 
 
+def device_mirror(rank, world, g):
+    """LightningGPU(wires, mpi=True): the reference's Python device call pattern (lightning_gpu.py:255-324, 392-447,
+    638-752, 820-960) on the sharded register."""
+    from pennylane_lightning_gpu_b200.lightning_gpu import LightningGPU, Obs, Op
+
+    failures = []
+    n = g + 6
+    rng = np.random.default_rng(5)
+    psi0 = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi0 /= np.linalg.norm(psi0)
+    dev = LightningGPU(n, mpi=True, c_dtype=np.complex128, seed=7)
+    ops = [Op("StatePrep", list(range(n)), [psi0]), Op("RX", [0], [0.4]), Op("CNOT", [0, n - 1]), Op("RY", [1], [0.3]),
+           Op("CRY", [n - 1, 0], [0.8]), Op("Rot", [0], [0.1, 0.2, 0.3])]
+    dev.apply(ops)
+    want = psi0.copy()
+    for o in ops[1:]:
+        want = orc.apply_op(want, o.name, list(o.wires), list(o.parameters))
+    sh = 1 << (n - g)
+
+    def check(what, got, ref, tol=1e-9):
+        err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
+        if not err <= tol:
+            failures.append(f"device {what}: err {err:.2e}")
+        if rank == 0:
+            print(f"[dist_check] device {what}: err={err:.2e}", flush=True)
+
+    check("state shard", dev.state, want[rank * sh:(rank + 1) * sh])
+    ham = Obs("Hamiltonian", coeffs=[0.5, -0.25], terms=[Obs("PauliZ", [0]), Obs("Tensor", terms=[Obs("PauliX", [0]), Obs("PauliY", [n - 1])])])
+    ham_t = ("Hamiltonian", [0.5, -0.25], [("Named", "PauliZ", [0]), ("TensorProd", [("Named", "PauliX", [0]), ("Named", "PauliY", [n - 1])])])
+    check("expval Hamiltonian", dev.expval(ham), orc.expval_obs(want, ham_t))
+    check("expval PauliX(0)", dev.expval(Obs("PauliX", [0])), orc.expval_named(want, "PauliX", [0]))
+    check("var PauliZ(0)", dev.var(Obs("PauliZ", [0])), 1 - orc.expval_named(want, "PauliZ", [0]) ** 2)
+    check("probability", dev.probability([0, 1, n - 1]), orc.probs(want, [0, 1, n - 1]))
+    aops = [Op("RX", [0], [0.4]), Op("CNOT", [0, n - 1]), Op("RY", [1], [0.3]), Op("Rot", [0], [0.1, 0.2, 0.3])]
+    jac = dev.adjoint_jacobian(aops, [Obs("PauliZ", [0]), ham])
+    ser = [{"name": "RX", "wires": [0], "params": [0.4]}, {"name": "CNOT", "wires": [0, n - 1], "params": []},
+           {"name": "RY", "wires": [1], "params": [0.3]}, {"name": "RZ", "wires": [0], "params": [0.1]},
+           {"name": "RY", "wires": [0], "params": [0.2]}, {"name": "RZ", "wires": [0], "params": [0.3]}]
+    fin = orc.apply_ops(orc.basis_state(n), ser)
+    check("adjoint_jacobian", jac, orc.adjoint_jacobian(fin, ser, [("Named", "PauliZ", [0]), ham_t], list(range(5))))
+    dev_s = LightningGPU(n, mpi=True, shots=500, seed=11)
+    dev_s.apply([Op("Hadamard", [0]), Op("CNOT", [0, n - 1])])
+    s = dev_s.generate_samples()
+    if s.shape != (500, n) or not np.array_equal(s[:, 0], s[:, n - 1]) or not 150 < s[:, 0].sum() < 350:
+        failures.append("device samples of a Bell pair on a global and a local wire")
+    return failures
+
+
 def main():
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -288,6 +336,7 @@ def main():
                     sv.close()
     failures += measurements_and_adjoint(rank, local_rank, world, g)
     failures += pybind_twins(rank, local_rank, world, g)
+    failures += device_mirror(rank, world, g)
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
