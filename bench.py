@@ -350,6 +350,7 @@ def run_ours(args):
     if args.adjoint and not distributed:
         del sv
         detail["adjoint_config3"] = adjoint_config3(torch, q, args)
+        detail["config1_sel20"] = config1_sel20(torch, q, args)
     if args.config4 and not distributed:
         detail["sparse_config4"] = sparse_config4(torch, q, args)
     if args.adjoint and not distributed:
@@ -484,6 +485,51 @@ def adjoint_config3(torch, q, args):
             out["cpu_port_jacobian_s"] = time.perf_counter() - t0
             out["cpu_cores"] = os.cpu_count()
             out["gpu_vs_cpu_port_max_abs_diff"] = float(np.max(np.abs(jac_cpu - jac[0])))
+        except Exception as ex:  # the CPU leg must never break the GPU numbers
+            out["cpu_port_error"] = repr(ex)
+    return out
+
+
+def config1_sel20(torch, q, args):
+    """BASELINE config 1: 20-qubit StronglyEntanglingLayers (2 layers, Rot expanded: 160 ops, 120 parameters),
+    expval(Z0) + adjoint Jacobian, complex128 -- the reference's own CPU-runnable case, timed on the GPU and on the
+    CPU port with all host cores and with one thread."""
+    n = 20
+    ops, n_par = workloads.strongly_entangling_layers(n, 2, 1337)
+    rec = q.Ops(ops)
+    z0 = q.Observable.named("PauliZ", [0])
+    sv = q.StateVector(n, np.complex128)
+    out = {"n_qubits": n, "n_params": n_par, "n_ops": len(ops), "dtype": "complex128"}
+
+    def run():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sv.set_basis_state(0)
+        sv.apply_ops(rec, fuse=True)
+        e = sv.expval(z0)
+        jac = sv.adjoint_jacobian(rec, [z0], list(range(n_par)))
+        torch.cuda.synchronize()
+        return e, jac, time.perf_counter() - t0
+
+    run()
+    best = None
+    for _ in range(5):
+        e, jac, dt = run()
+        best = dt if best is None else min(best, dt)
+    out.update({"gpu_circuit_expval_jacobian_s": best, "expval": e, "jac_norm": float(np.linalg.norm(jac))})
+    if args.cpu_baseline:
+        try:
+            from oracle import lq_port as lq
+
+            for threads in (os.cpu_count() or 1, 1):
+                lq.set_num_threads(threads)
+                t0 = time.perf_counter()
+                st = lq.LQState(n)
+                st.apply_ops(ops)
+                jac_cpu = lq.adjoint_jacobian(st, ops, [("Named", "PauliZ", [0])], list(range(n_par)))
+                out[f"cpu_port_{threads}_threads_s"] = time.perf_counter() - t0
+            out["gpu_vs_cpu_port_max_abs_diff"] = float(np.max(np.abs(np.asarray(jac_cpu).reshape(-1) - jac[0])))
+            lq.set_num_threads(os.cpu_count() or 1)
         except Exception as ex:  # the CPU leg must never break the GPU numbers
             out["cpu_port_error"] = repr(ex)
     return out

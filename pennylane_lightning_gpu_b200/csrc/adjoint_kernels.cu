@@ -24,13 +24,15 @@ constexpr int GT_EPT = (1 << GT_TB) / GT_NT;  // 8 amplitudes per thread
 constexpr int GT_MAX = 32;       // generators per launch
 
 struct GenDesc {
-    int kind;            // 0: diagonal table (<= 1 table bit: parity of index & zmask), 1: 2x2 block on one tile bit
+    int kind;            // 0: diagonal table (<= 1 table bit: parity of index & zmask), 1: 2x2 block on one tile bit,
+                         // 2: Pauli word (X/Y letters on tile bits, Z letters anywhere)
     int slot;            // complex output slot
-    unsigned tbit;       // kind 1: tile-local position of the target bit
+    unsigned tbit;       // kind 1: tile-local position of the target bit; kind 2: tile-local flip mask
     unsigned pad0;
     uint64_t ctrl;       // global bits that must be 1
-    uint64_t zmask;      // kind 0: global bits whose parity selects the phase
-    double m[8];         // kind 1: row-major complex 2x2; kind 0: phase for even parity, phase for odd parity
+    uint64_t zmask;      // kind 0 / 2: global bits whose parity selects the phase / the sign
+    uint64_t xg;         // kind 2: flip mask on global bits
+    double m[8];         // kind 1: row-major complex 2x2; kind 0: phases for even / odd parity; kind 2: i^ny
 };
 
 struct GenProgram {
@@ -78,6 +80,19 @@ __global__ void __launch_bounds__(GT_NT)
                 const bool odd = __popcll(gidx[j] & g.zmask) & 1;
                 const double pr = odd ? e1r : e0r, pi = odd ? e1i : e0i;
                 const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
+                const double yr = pr * (double)x.x - pi * (double)x.y, yi = pr * (double)x.y + pi * (double)x.x;
+                re += (double)b[j].x * yr + (double)b[j].y * yi;
+                im += (double)b[j].x * yi - (double)b[j].y * yr;
+            }
+        } else if (g.kind == 2) {
+            // (P ket)_i = i^ny * (-1)^{popc(j & z)} * ket_j with j = i ^ x
+            const double cr = g.m[0], ci = g.m[1];
+#pragma unroll
+            for (int j = 0; j < GT_EPT; ++j) {
+                const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
+                const A x = s[e ^ g.tbit];
+                const bool odd = __popcll((gidx[j] ^ g.xg) & g.zmask) & 1;
+                const double pr = odd ? -cr : cr, pi = odd ? -ci : ci;
                 const double yr = pr * (double)x.x - pi * (double)x.y, yi = pr * (double)x.y + pi * (double)x.x;
                 re += (double)b[j].x * yr + (double)b[j].y * yi;
                 im += (double)b[j].x * yi - (double)b[j].y * yr;
@@ -139,87 +154,65 @@ template <typename T> void launch_gens_t(State &sv, const void *bra, const void 
 
 }  // namespace
 
-// out_dev[2 * slots[k] ..] += <bra| gens[k] |ket> (re, im) for every k, with as few reads of the vectors as the
-// tile size allows.  Generators are LoweredGates used as operators (controls = projectors).
-void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std::vector<LoweredGate> &gens,
-                         const std::vector<int> &slots, double *out_dev) {
-    sv.use();
+namespace {
+
+// a generator / Pauli word waiting for a tile: `need` = non-diagonal bits >= L that must be tile bits; tgt / xg are
+// global positions that are translated to tile-local ones once the tile is chosen
+struct GenItem {
+    GenDesc d;
+    uint64_t need = 0;
+    int tgt = -1;  // kind 1
+};
+
+constexpr int GT_L = 4;
+
+void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem> &todo, double *out_dev) {
     const int n = sv.n;
-    std::vector<size_t> todo;
-    for (size_t k = 0; k < gens.size(); ++k) {
-        int kind;
-        if (gens[k].kind == LoweredGate::NOP) continue;  // a projector that is zero on this shard
-        if (n >= GT_TB && tile_gen_kind(gens[k], n, kind))
-            todo.push_back(k);
-        else
-            launch_bra_op_ket(sv, bra, ket, gens[k], out_dev, slots[k]);
-    }
-    const int L = 4;
-    const int max_hi = GT_TB - L;
+    const int max_hi = GT_TB - GT_L;
     while (!todo.empty()) {
-        // one launch: up to GT_MAX generators whose non-diagonal target bits >= L number at most max_hi
+        // one launch: up to GT_MAX items whose non-diagonal bits >= L number at most max_hi (first fit over all)
         GenProgram P;
         memset(&P, 0, sizeof(P));
-        P.L = L;
+        P.L = GT_L;
         uint64_t need = 0;
-        std::vector<size_t> rest, take;
-        for (size_t k : todo) {
-            int kind = 0;
-            tile_gen_kind(gens[k], n, kind);
-            uint64_t nb = 0;
-            if (kind == 1 && gens[k].tgt_bits[0] >= L) nb = 1ull << gens[k].tgt_bits[0];
-            if ((int)take.size() < GT_MAX && __builtin_popcountll(need | nb) <= max_hi) {
-                take.push_back(k);
-                need |= nb;
+        std::vector<GenItem> rest, take;
+        for (GenItem &it : todo) {
+            if ((int)take.size() < GT_MAX && __builtin_popcountll(need | it.need) <= max_hi) {
+                need |= it.need;
+                take.push_back(it);
             } else {
-                rest.push_back(k);
+                rest.push_back(it);
             }
         }
         std::vector<int> hi;
-        for (int b = L; b < n; ++b)
+        for (int b = GT_L; b < n; ++b)
             if (need >> b & 1) hi.push_back(b);
-        for (int b = L; b < n && (int)hi.size() < max_hi; ++b)
+        for (int b = GT_L; b < n && (int)hi.size() < max_hi; ++b)
             if (!(need >> b & 1)) hi.push_back(b);
         std::sort(hi.begin(), hi.end());
         int pos[64];
         for (int b = 0; b < 64; ++b) pos[b] = -1;
         std::vector<int> tile_bits;
-        for (int b = 0; b < L; ++b) {
+        for (int b = 0; b < GT_L; ++b) {
             pos[b] = b;
             tile_bits.push_back(b);
         }
         for (int j = 0; j < (int)hi.size(); ++j) {
-            pos[hi[j]] = L + j;
+            pos[hi[j]] = GT_L + j;
             P.hi_bits[j] = (unsigned char)hi[j];
             tile_bits.push_back(hi[j]);
         }
         P.tile_holes = make_holes(tile_bits.data(), (int)tile_bits.size(), 0);
-        for (size_t k : take) {
-            const LoweredGate &g = gens[k];
+        for (GenItem &it : take) {
             GenDesc &d = P.g[P.n_gens++];
-            int kind = 0;
-            tile_gen_kind(g, n, kind);
-            d.kind = kind;
-            d.slot = slots[k];
-            d.ctrl = g.ctrl_mask;
-            if (kind == 1) {
-                d.tbit = (unsigned)pos[g.tgt_bits[0]];
-                for (int q = 0; q < 4; ++q) {
-                    d.m[2 * q] = g.mat[q].real();
-                    d.m[2 * q + 1] = g.mat[q].imag();
-                }
-            } else if (g.kind == LoweredGate::PARITY) {
-                d.zmask = g.zmask;
-                d.m[0] = g.mat[0].real();
-                d.m[1] = g.mat[0].imag();
-                d.m[2] = g.mat[1].real();
-                d.m[3] = g.mat[1].imag();
-            } else {  // DIAG with 0 or 1 table bits
-                d.zmask = g.k == 1 ? (1ull << g.tgt_bits[0]) : 0;
-                d.m[0] = g.mat[0].real();
-                d.m[1] = g.mat[0].imag();
-                d.m[2] = g.k == 1 ? g.mat[1].real() : g.mat[0].real();
-                d.m[3] = g.k == 1 ? g.mat[1].imag() : g.mat[0].imag();
+            d = it.d;
+            if (d.kind == 1) {
+                d.tbit = (unsigned)pos[it.tgt];
+            } else if (d.kind == 2) {
+                unsigned xl = 0;
+                for (int b = 0; b < n; ++b)
+                    if (d.xg >> b & 1) xl |= 1u << pos[b];
+                d.tbit = xl;
             }
         }
         sv.stat_launches += 1;
@@ -229,6 +222,83 @@ void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std:
             launch_gens_t<float>(sv, bra, ket, out_dev, P);
         todo.swap(rest);
     }
+}
+
+}  // namespace
+
+// out_dev[2 * slots[k] ..] += <bra| gens[k] |ket> (re, im) for every k, with as few reads of the vectors as the
+// tile size allows.  Generators are LoweredGates used as operators (controls = projectors).
+void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std::vector<LoweredGate> &gens,
+                         const std::vector<int> &slots, double *out_dev) {
+    sv.use();
+    const int n = sv.n;
+    std::vector<GenItem> todo;
+    for (size_t k = 0; k < gens.size(); ++k) {
+        const LoweredGate &g = gens[k];
+        int kind;
+        if (g.kind == LoweredGate::NOP) continue;  // a projector that is zero on this shard
+        if (!(n >= GT_TB && tile_gen_kind(g, n, kind))) {
+            launch_bra_op_ket(sv, bra, ket, g, out_dev, slots[k]);
+            continue;
+        }
+        GenItem it;
+        memset(&it.d, 0, sizeof(it.d));
+        it.d.kind = kind;
+        it.d.slot = slots[k];
+        it.d.ctrl = g.ctrl_mask;
+        if (kind == 1) {
+            it.tgt = g.tgt_bits[0];
+            if (it.tgt >= GT_L) it.need = 1ull << it.tgt;
+            for (int q = 0; q < 4; ++q) {
+                it.d.m[2 * q] = g.mat[q].real();
+                it.d.m[2 * q + 1] = g.mat[q].imag();
+            }
+        } else if (g.kind == LoweredGate::PARITY) {
+            it.d.zmask = g.zmask;
+            it.d.m[0] = g.mat[0].real();
+            it.d.m[1] = g.mat[0].imag();
+            it.d.m[2] = g.mat[1].real();
+            it.d.m[3] = g.mat[1].imag();
+        } else {  // DIAG with 0 or 1 table bits
+            it.d.zmask = g.k == 1 ? (1ull << g.tgt_bits[0]) : 0;
+            it.d.m[0] = g.mat[0].real();
+            it.d.m[1] = g.mat[0].imag();
+            it.d.m[2] = g.k == 1 ? g.mat[1].real() : g.mat[0].real();
+            it.d.m[3] = g.k == 1 ? g.mat[1].imag() : g.mat[0].imag();
+        }
+        todo.push_back(it);
+    }
+    run_items(sv, bra, ket, todo, out_dev);
+}
+
+// out_dev[2 * (first_slot + t) ..] += <bra| P_t |ket> for Pauli words given by (x, z, #Y) masks: single-pass fused
+// expectation values of many words -- every word whose X/Y letters fit one tile shares one read of the vectors
+// (replaces custatevecComputeExpectationsOnPauliBasis, Managed.hpp:1117-1128)
+void launch_bra_paulis_ket(State &sv, const void *bra, const void *ket, int n_terms, const uint64_t *xmasks,
+                           const uint64_t *zmasks, const int *nys, int first_slot, double *out_dev) {
+    sv.use();
+    const int n = sv.n;
+    const uint64_t low = (1ull << GT_L) - 1ull;
+    std::vector<GenItem> todo;
+    for (int t = 0; t < n_terms; ++t) {
+        const uint64_t need = xmasks[t] & ~low;
+        if (n < GT_TB || __builtin_popcountll(need) > GT_TB - GT_L) {
+            launch_bra_pauli_ket(sv, bra, ket, xmasks[t], zmasks[t], nys[t], out_dev, first_slot + t);
+            continue;
+        }
+        GenItem it;
+        memset(&it.d, 0, sizeof(it.d));
+        it.d.kind = 2;
+        it.d.slot = first_slot + t;
+        it.d.xg = xmasks[t];
+        it.d.zmask = zmasks[t];
+        const double ph[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        it.d.m[0] = ph[nys[t] & 3][0];
+        it.d.m[1] = ph[nys[t] & 3][1];
+        it.need = need;
+        todo.push_back(it);
+    }
+    run_items(sv, bra, ket, todo, out_dev);
 }
 
 }  // namespace qsv

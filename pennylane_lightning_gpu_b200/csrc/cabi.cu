@@ -1,5 +1,6 @@
 // extern "C" surface of libqsv_b200.so (see include/qsv_b200.h for the reference call sites each
 // entry replaces).  Every entry converts C++ exceptions into a status code + thread-local message.
+#include <algorithm>
 #include <cstdio>
 
 #include "qsv_internal.h"
@@ -133,7 +134,9 @@ int qsv_create_external(int n_qubits, int dtype, int device, void *device_ptr, v
         sv->data = device_ptr;
         sv->owns = false;
     } else {
-        QSV_CUDA(cudaMalloc(&sv->data, sv->bytes()));
+        // at least 2 MiB: smaller cudaMalloc blocks are sub-allocated from a shared block, which cannot be exported
+        // one by one over CUDA IPC when the state later becomes a shard of a distributed register
+        QSV_CUDA(cudaMalloc(&sv->data, std::max<size_t>(sv->bytes(), (size_t)2 << 20)));
         sv->owns = true;
         launch_fill_basis(*sv, 0);
     }
@@ -410,6 +413,8 @@ int qsv_expval_pauli_words(qsv_state *sv, int n_terms, const char *letters, cons
     const int n = sv->n;
     double *red = sv->reduction_buffer(2 * (size_t)std::max(n_terms, 1));
     reduction_zero(*sv, red, 2 * (size_t)std::max(n_terms, 1));
+    std::vector<uint64_t> xs(n_terms), zs(n_terms);
+    std::vector<int> nys(n_terms);
     for (int t = 0; t < n_terms; ++t) {
         uint64_t x = 0, z = 0;
         int ny = 0;
@@ -425,8 +430,12 @@ int qsv_expval_pauli_words(qsv_state *sv, int n_terms, const char *letters, cons
             default: fail(std::string("invalid Pauli letter '") + letters[j] + "'");
             }
         }
-        launch_bra_pauli_ket(*sv, sv->data, sv->data, x, z, ny, red, t);
+        xs[t] = x;
+        zs[t] = z;
+        nys[t] = ny;
     }
+    // single-pass fused evaluation: words whose X/Y letters fit one tile share one read of the state
+    launch_bra_paulis_ket(*sv, sv->data, sv->data, n_terms, xs.data(), zs.data(), nys.data(), 0, red);
     std::vector<double> h(2 * (size_t)std::max(n_terms, 1));
     reduction_read(*sv, red, h.data(), h.size());
     double tot = 0;

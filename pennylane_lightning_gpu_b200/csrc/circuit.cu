@@ -243,8 +243,8 @@ double observable_expval(State &sv, const Obs &o) {
             const size_t T = xs.size();
             double *red = sv.reduction_buffer(2 * T);
             reduction_zero(sv, red, 2 * T);
-            for (size_t t = 0; t < T; ++t)
-                launch_bra_pauli_ket(sv, sv.data, sv.data, xs[t], zs[t], 0, red, (int)t);
+            std::vector<int> ny0(T, 0);  // cf already carries i^ny
+            launch_bra_paulis_ket(sv, sv.data, sv.data, (int)T, xs.data(), zs.data(), ny0.data(), 0, red);
             std::vector<double> out(2 * T);
             reduction_read(sv, red, out.data(), 2 * T);
             double tot = 0;

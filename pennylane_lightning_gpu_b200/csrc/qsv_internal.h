@@ -165,6 +165,9 @@ void launch_bra_op_ket(State &sv, const void *bra, const void *ket, const Lowere
 // (adjoint_kernels.cu)
 void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std::vector<LoweredGate> &gens,
                          const std::vector<int> &slots, double *out_dev);
+// many Pauli words at once: out_dev[2 * (first_slot + t) ..] += <bra| P_t |ket>
+void launch_bra_paulis_ket(State &sv, const void *bra, const void *ket, int n_terms, const uint64_t *xmasks,
+                           const uint64_t *zmasks, const int *nys, int first_slot, double *out_dev);
 // <bra| P |ket> for a Pauli word given by masks; result *(i^ny) applied on device
 void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t xmask, uint64_t zmask,
                           int ny, double *out_dev, int slot);

@@ -355,11 +355,11 @@ int pool_need(const LoweredGate &g) {
 
 template <typename T> void launch_sweep_t(State &sv, const TileProgram &P, void *const *table, int n_vecs, bool tma) {
     const size_t smem = ((size_t)1 << P.tb) * sizeof(typename Cx<T>::type);
-    static bool configured[2] = {false, false};
+    static bool configured[64][2] = {{false, false}};  // per device: function attributes belong to the device's context
     auto kern = tma ? k_tile_sweep<T, true> : k_tile_sweep<T, false>;
-    if (!configured[tma ? 1 : 0]) {
+    if (!configured[sv.device & 63][tma ? 1 : 0]) {
         QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured[tma ? 1 : 0] = true;
+        configured[sv.device & 63][tma ? 1 : 0] = true;
     }
     dim3 grid((unsigned)(1ull << (sv.n - P.tb)), (unsigned)n_vecs);
     kern<<<grid, TILE_NT, smem, sv.stream>>>(table ? nullptr : sv.data, table, P);
@@ -544,7 +544,6 @@ std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> 
 // Register-blocked executor (tile_regs.cu): same sweep packing, but the tile has 12 - L arbitrary high bits with
 // L as small as one warp-wide access allows, and the gates of a sweep are list-scheduled into register passes.
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
-    const bool f32 = sv.dtype == QSV_C64;
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const int max_hi = 12 - L;

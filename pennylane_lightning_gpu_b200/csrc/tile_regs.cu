@@ -365,11 +365,11 @@ namespace {
 template <typename T> void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs) {
     constexpr int MINB = sizeof(T) == 8 ? 2 : 3;
     const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
-    static bool configured = false;
+    static bool configured[64] = {false};  // per device: function attributes belong to the device's context
     auto kern = k_tile_regs<T, MINB>;
-    if (!configured) {
+    if (!configured[sv.device & 63]) {
         QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[sv.device & 63] = true;
     }
     dim3 grid((unsigned)(1ull << (sv.n - RT_TB)), (unsigned)n_vecs);
     kern<<<grid, RT_NT, smem, sv.stream>>>(table ? nullptr : sv.data, table, P);

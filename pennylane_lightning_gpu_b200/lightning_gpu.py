@@ -23,11 +23,12 @@ from typing import Sequence, Union
 
 import numpy as np
 
-_PKG = os.path.dirname(os.path.abspath(__file__))
-if _PKG not in sys.path:
-    sys.path.insert(0, _PKG)
-try:
-    import lightning_gpu_qubit_ops as _ops  # noqa: E402
+try:  # one module object per process: pybind11 types can only be registered once
+    if __package__:
+        from . import lightning_gpu_qubit_ops as _ops
+    else:  # pragma: no cover - file used outside the package
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import lightning_gpu_qubit_ops as _ops  # noqa: E402
 except ImportError as e:  # pragma: no cover - loud failure instead of a CPU fallback
     raise ImportError(
         "lightning_gpu_qubit_ops is not built: run `python -m pennylane_lightning_gpu_b200._build` "

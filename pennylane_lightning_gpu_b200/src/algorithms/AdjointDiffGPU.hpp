@@ -3,8 +3,10 @@
 // qsv_adjoint_jacobian.  The reverse sweep itself runs inside libqsv_b200.so (csrc/circuit.cu).
 #pragma once
 #include <complex>
+#include <algorithm>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "Error.hpp"
@@ -97,12 +99,47 @@ template <class T = double> class AdjointJacobianGPU {
         for (std::size_t i = 0; i < obs.size(); ++i)
             for (std::size_t p = 0; p < tp.size(); ++p) jac[i][p] = static_cast<T>(flat[i * tp.size() + p]);
     }
-    // Observable batching over several GPUs (AdjointDiffGPU.hpp:392-473) is replicas-only and outside the
-    // hot-path scope: the single-device sweep already shares U^dagger across all bras.
+    // Observable batching over all visible GPUs (AdjointDiffGPU.hpp:392-473): replicas, no communication.  The
+    // observables are split into contiguous chunks (ceil division, :416-419), one std::thread per GPU copies the
+    // state to its device (peer copy) and runs the sweep on its chunk.  On one GPU this is adjointJacobian.
     void batchAdjointJacobian(const SV &sv, std::vector<std::vector<T>> &jac, const std::vector<ObsPtr> &obs,
                               const OpsData<SV> &ops, const std::vector<std::size_t> &trainableParams,
                               bool apply_operations = false) {
-        adjointJacobian(sv, jac, obs, ops, trainableParams, apply_operations);
+        int n_dev = 0;
+        Util::check(qsv_device_count(&n_dev));
+        const std::size_t n_chunks = std::min<std::size_t>(static_cast<std::size_t>(std::max(n_dev, 1)), obs.size());
+        if (n_chunks <= 1) {
+            adjointJacobian(sv, jac, obs, ops, trainableParams, apply_operations);
+            return;
+        }
+        PL_ABORT_IF(trainableParams.empty(), "No trainable parameters provided.");
+        jac.assign(obs.size(), std::vector<T>(trainableParams.size(), 0));
+        const std::size_t per = (obs.size() + n_chunks - 1) / n_chunks;
+        std::vector<std::thread> threads;
+        std::vector<std::string> errors(n_chunks);
+        for (std::size_t c = 0; c < n_chunks; ++c) {
+            const std::size_t first = c * per, last = std::min(obs.size(), first + per);
+            if (first >= last) break;
+            threads.emplace_back([&, c, first, last]() {
+                try {
+                    const int dev = static_cast<int>(c);
+                    std::vector<ObsPtr> mine(obs.begin() + first, obs.begin() + last);
+                    std::vector<std::vector<T>> part;
+                    if (dev == sv.getDevTag().getDeviceID()) {
+                        adjointJacobian(sv, part, mine, ops, trainableParams, apply_operations);
+                    } else {
+                        SV local(sv.getNumQubits(), CUDA::DevTag<int>(dev));
+                        Util::check(qsv_d2d(local.handle(), sv.handle()));
+                        adjointJacobian(local, part, mine, ops, trainableParams, apply_operations);
+                    }
+                    for (std::size_t i = 0; i < part.size(); ++i) jac[first + i] = part[i];
+                } catch (const std::exception &e) {
+                    errors[c] = e.what();
+                }
+            });
+        }
+        for (auto &t : threads) t.join();
+        for (const auto &e : errors) PL_ABORT_IF(!e.empty(), e);
     }
 };
 

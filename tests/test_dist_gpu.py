@@ -22,4 +22,8 @@ def test_sharded_register_matches_oracle(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"dist_check_{world}gpu.log"), "w") as f:  # evidence / post-mortem
+        f.write(r.stdout[-200000:] + "\n==== stderr ====\n" + r.stderr[-20000:])
     assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -534,3 +534,76 @@ def test_config3_vqe_reduced(q):
     a = sv.expval_csr(m.indptr, m.indices, m.data)
     b = sv.expval_pauli_words(w2, ws2, c2)
     assert abs(a - b) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# register-tile executor and batched reductions: dedicated stress cases
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,low", [(12, 4), (12, 1), (14, 3), (15, 6), (13, 9)])
+def test_register_tile_kernel_stress(q, n, low, dtype, monkeypatch):
+    """csrc/tile_regs.cu: controls on register / thread / outside bits, two-level gates taken as 4x4 blocks, diagonal
+    tables with mixed bit sources, every tile-low-bit setting, against the oracle."""
+    monkeypatch.setenv("QSV_REGS_LOW", str(low))
+    rng = np.random.default_rng(1000 * n + low)
+    names = ["RX", "RY", "RZ", "CNOT", "CZ", "Hadamard", "PhaseShift", "IsingXX", "IsingYY", "IsingZZ", "CRX", "CRY", "CRZ",
+             "SWAP", "Toffoli", "SingleExcitation", "SingleExcitationPlus", "S", "T", "PauliX", "PauliY", "PauliZ", "MultiRZ",
+             "CRot", "ControlledPhaseShift", "CSWAP", "CY", "Rot", "QubitUnitary1", "QubitUnitary2", "DiagUnitary2"]
+    ops = []
+    for i in range(120):
+        name = names[rng.integers(len(names))]
+        if name.startswith("QubitUnitary"):
+            k = int(name[-1])
+            ops.append({"name": "QubitUnitary", "wires": _rand_wires(rng, n, k), "params": [], "matrix": _haar(rng, 1 << k),
+                        "adjoint": bool(rng.integers(2))})
+            continue
+        if name == "DiagUnitary2":
+            ops.append({"name": "QubitUnitary", "wires": _rand_wires(rng, n, 2), "params": [],
+                        "matrix": np.diag(np.exp(1j * rng.uniform(-3, 3, 4)))})
+            continue
+        nw, npar = orc.GATE_ARITY[name]
+        nw = nw if nw is not None else int(rng.integers(1, 5))
+        # half of the gates on neighbouring wires: ladders put controls on the register bits of the previous target
+        if nw >= 2 and i % 2 == 0:
+            w0 = int(rng.integers(0, n - nw + 1))
+            wires = list(range(w0, w0 + nw))
+            if rng.integers(2):
+                wires = wires[::-1]
+        else:
+            wires = _rand_wires(rng, n, nw)
+        ops.append({"name": name, "wires": wires, "params": [float(x) for x in rng.uniform(-3, 3, npar)],
+                    "adjoint": bool(rng.integers(2))})
+    psi = random_state(n, 5)
+    want = orc.apply_ops(psi, ops)
+    sv = gpu_state(q, psi, dtype)
+    sv.apply_ops(q.Ops(ops), fuse=True)
+    assert_close(sv.d2h(), want, dtype, scale=20, what=f"n={n} low={low}")
+    launches, _ = sv.last_apply_stats()
+    assert launches < len(ops)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [11, 13, 17])
+def test_fused_pauli_word_expvals(q, n, dtype):
+    """csrc/adjoint_kernels.cu (Pauli kind): many words per read of the state, incl. words whose X/Y letters do not fit one
+    tile (separate launch) and identity letters, per-term values and the weighted sum against the oracle."""
+    rng = np.random.default_rng(40 + n)
+    psi = random_state(n, 8)
+    sv = gpu_state(q, psi, dtype)
+    words, wires, coeffs = [], [], []
+    for t in range(70):
+        k = int(rng.integers(1, min(n, 10) + 1)) if t % 7 == 0 else int(rng.integers(1, 5))
+        words.append("".join(rng.choice(list("XYZI"), size=k)))
+        wires.append(_rand_wires(rng, n, k))
+        coeffs.append(float(rng.normal()))
+    words.append("X" * min(n, 9))
+    wires.append(list(range(n - 1, n - 1 - min(n, 9), -1)))
+    coeffs.append(0.7)
+    tot, terms = sv.expval_pauli_words(words, wires, coeffs, return_terms=True)
+    for t, (w, ws) in enumerate(zip(words, wires)):
+        want = np.vdot(psi, orc.pauli_word_matrix_free(psi, w, ws)).real
+        assert_close(terms[t], want, dtype, what=f"word {w}{ws}")
+    assert_close(tot, orc.expval_pauli_words(psi.astype(dtype), words, wires, coeffs), dtype, scale=80)
+    ham = ("Hamiltonian", coeffs, [("TensorProd", [("Named", {"X": "PauliX", "Y": "PauliY", "Z": "PauliZ", "I": "Identity"}[c], [w])
+                                                   for c, w in zip(word, ws)]) for word, ws in zip(words, wires)])
+    assert_close(sv.expval(q.Observable.from_tuple(ham)), orc.expval_pauli_words(psi, words, wires, coeffs), dtype, scale=80)

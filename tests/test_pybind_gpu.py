@@ -18,8 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def ops_mod():
-    sys.path.insert(0, os.path.join(ROOT, "pennylane_lightning_gpu_b200"))
-    import lightning_gpu_qubit_ops as m
+    from pennylane_lightning_gpu_b200 import lightning_gpu_qubit_ops as m  # one module object per process
 
     return m
 
