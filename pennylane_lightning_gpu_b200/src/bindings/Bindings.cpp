@@ -274,7 +274,15 @@ template <class PrecisionT> void register_precision(py::module_ &m) {
                  return Ops{ops_name, params, ops_wires, ops_inverses, mats};
              })
         .def("adjoint_jacobian", jacobian)
-        .def("adjoint_jacobian_batched", jacobian);
+        .def("adjoint_jacobian_batched",
+             [](Adj &adj, const SV &sv, const std::vector<ObsPtr> &observables, const Ops &operations,
+                const std::vector<std::size_t> &trainableParams) {
+                 std::vector<std::vector<PrecisionT>> jac;
+                 adj.batchAdjointJacobian(sv, jac, observables, operations, trainableParams, false);
+                 py::array_t<ParamT> out({observables.size(), trainableParams.size()});
+                 for (std::size_t i = 0; i < jac.size(); ++i) std::copy(jac[i].begin(), jac[i].end(), out.mutable_data(i, 0));
+                 return out;
+             });
 }
 
 
