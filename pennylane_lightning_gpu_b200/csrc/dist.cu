@@ -432,28 +432,50 @@ void dist_expval_pauli(State &sv, int n_terms, const uint64_t *x_log, const uint
     const int n_local = sv.n;
     const uint64_t hi_mask = ~((1ull << n_local) - 1ull);
     std::vector<double> vals(2 * (size_t)std::max(n_terms, 1), 0.0);
-    double *red = sv.reduction_buffer(2);
-    for (int t = 0; t < n_terms; ++t) {
-        // X/Y letters on global qubits need the partner amplitudes: make those qubits local first
+    // groups of words whose X/Y letters are all on local qubits under one layout: one batched, fused launch sequence per
+    // group (launch_bra_paulis_ket); X/Y letters on global qubits make those qubits local first
+    std::vector<char> left(n_terms, 1);
+    int n_left = n_terms;
+    while (n_left > 0) {
+        int first = 0;
+        while (!left[first]) ++first;
         for (int lb = 0; lb < d.n_total; ++lb) {
-            if (!(x_log[t] >> lb & 1) || d.phys_of[lb] < n_local) continue;
+            if (!(x_log[first] >> lb & 1) || d.phys_of[lb] < n_local) continue;
             int best = -1;
             for (int l = n_local - 1; l >= 0; --l)
-                if (!(x_log[t] >> d.log_of[l] & 1)) {
+                if (!(x_log[first] >> d.log_of[l] & 1)) {
                     best = l;
                     break;
                 }
             QSV_CHECK(best >= 0, "Pauli word flips more qubits than a shard holds");
             swap_logical_in(sv, d.phys_of[lb], best, chunk_bytes);
         }
-        const uint64_t x = remap_mask(x_log[t], d.phys_of), z = remap_mask(z_log[t], d.phys_of);
-        reduction_zero(sv, red, 2);
-        launch_bra_pauli_ket(sv, sv.data, sv.data, x, z & ~hi_mask, ny[t], red, 0);
-        double h[2];
-        reduction_read(sv, red, h, 2);
-        const double sgn = (__builtin_popcountll(sv.index_hi & z & hi_mask) & 1) ? -1.0 : 1.0;
-        vals[2 * t] = sgn * h[0];
-        vals[2 * t + 1] = sgn * h[1];
+        std::vector<int> group;
+        std::vector<uint64_t> gx, gz;
+        std::vector<int> gy;
+        std::vector<double> sgn;
+        for (int t = first; t < n_terms; ++t) {
+            if (!left[t]) continue;
+            const uint64_t x = remap_mask(x_log[t], d.phys_of);
+            if (x & hi_mask) continue;
+            const uint64_t z = remap_mask(z_log[t], d.phys_of);
+            group.push_back(t);
+            gx.push_back(x);
+            gz.push_back(z & ~hi_mask);
+            gy.push_back(ny[t]);
+            sgn.push_back((__builtin_popcountll(sv.index_hi & z & hi_mask) & 1) ? -1.0 : 1.0);
+            left[t] = 0;
+            --n_left;
+        }
+        double *red = sv.reduction_buffer(2 * group.size());
+        reduction_zero(sv, red, 2 * group.size());
+        launch_bra_paulis_ket(sv, sv.data, sv.data, (int)group.size(), gx.data(), gz.data(), gy.data(), 0, red);
+        std::vector<double> h(2 * group.size());
+        reduction_read(sv, red, h.data(), h.size());
+        for (size_t q = 0; q < group.size(); ++q) {
+            vals[2 * group[q]] = sgn[q] * h[2 * q];
+            vals[2 * group[q] + 1] = sgn[q] * h[2 * q + 1];
+        }
     }
     for (int off = 0; off < 2 * n_terms; off += 4096)
         dist_allreduce(sv, vals.data() + off, std::min(4096, 2 * n_terms - off));
