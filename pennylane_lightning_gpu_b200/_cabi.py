@@ -14,7 +14,8 @@ from typing import Sequence
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libqsv_b200.so")
+# QSV_LIB_PATH: another build of the same library (kernel A/B experiments, tools/regs_variants.py)
+LIB_PATH = os.environ.get("QSV_LIB_PATH") or os.path.join(_PKG, "lib", "libqsv_b200.so")
 
 QSV_C64, QSV_C128 = 0, 1
 

@@ -27,9 +27,7 @@ namespace qsv {
 namespace {
 
 constexpr int RT_TB = 12;   // tile bits
-constexpr int RT_RB = 4;    // register bits
-constexpr int RT_NT = 256;  // threads per CTA = 2^(TB - RB)
-constexpr int RT_NS = 16;   // amplitudes per thread
+constexpr int RT_RB = 4;    // register bits, at most (QSV_REGS_RB=3: 8 amplitudes per thread, 512 threads per CTA)
 constexpr int RT_MAX_GATES = 48;
 constexpr int RT_MAX_PASSES = 48;
 constexpr int RT_POOL = 1280;  // doubles
@@ -51,7 +49,7 @@ struct RegGate {
 
 struct RegPass {
     unsigned char rbits[RT_RB];          // tile-local position of register bit 0..3
-    unsigned char tbits[RT_TB - RT_RB];  // tile-local position of thread bit 0..7
+    unsigned char tbits[RT_TB];          // tile-local position of thread bit 0..(TB - RB - 1)
     unsigned short gate_begin, gate_end;
 };
 
@@ -86,13 +84,13 @@ template <int SW> __device__ __forceinline__ uint32_t swz(uint32_t e) {
 // Controls among the register bits are a per-slot predicate.  (A variant with separate unpredicated code paths
 // plus a scheduling constraint that keeps controls out of the register bits was measured slower on B200:
 // 196 ms vs 166 ms for the config-2 circuit -- more code, 128 registers with spills.)
-template <typename T, int B, typename A>
-__device__ __forceinline__ void reg_d1(A (&x)[RT_NS], int kind, const T *mp, uint32_t creg) {
+template <typename T, int B, int NS, typename A>
+__device__ __forceinline__ void reg_d1(A (&x)[NS], int kind, const T *mp, uint32_t creg) {
     const A q0 = reinterpret_cast<const A *>(mp)[0], q1 = reinterpret_cast<const A *>(mp)[1];
     const A q2 = reinterpret_cast<const A *>(mp)[2], q3 = reinterpret_cast<const A *>(mp)[3];
     if (kind == RG_D1_SWAP) {
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if ((j >> B) & 1) continue;
             if ((j & creg) == creg) {
                 const A t = x[j];
@@ -102,7 +100,7 @@ __device__ __forceinline__ void reg_d1(A (&x)[RT_NS], int kind, const T *mp, uin
         }
     } else if (kind == RG_D1_REAL) {
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if ((j >> B) & 1) continue;
             if ((j & creg) == creg) {
                 const A a = x[j], b = x[j | (1 << B)];
@@ -115,7 +113,7 @@ __device__ __forceinline__ void reg_d1(A (&x)[RT_NS], int kind, const T *mp, uin
     } else if (kind == RG_D1_RX) {
         // real diagonal, imaginary off-diagonal (RX and products of RX)
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if ((j >> B) & 1) continue;
             if ((j & creg) == creg) {
                 const A a = x[j], b = x[j | (1 << B)];
@@ -127,7 +125,7 @@ __device__ __forceinline__ void reg_d1(A (&x)[RT_NS], int kind, const T *mp, uin
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if ((j >> B) & 1) continue;
             if ((j & creg) == creg) {
                 const A a = x[j], b = x[j | (1 << B)];
@@ -141,10 +139,10 @@ __device__ __forceinline__ void reg_d1(A (&x)[RT_NS], int kind, const T *mp, uin
 }
 
 // 4x4 block on register bits BA > BB; matrix index = 2 * bit(BA) + bit(BB)
-template <typename T, int BA, int BB, typename A>
-__device__ __forceinline__ void reg_d2(A (&x)[RT_NS], const T *mp, uint32_t creg) {
+template <typename T, int BA, int BB, int NS, typename A>
+__device__ __forceinline__ void reg_d2(A (&x)[NS], const T *mp, uint32_t creg) {
 #pragma unroll
-    for (int j = 0; j < RT_NS; ++j) {
+    for (int j = 0; j < NS; ++j) {
         if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
         if ((j & creg) == creg) {
             const int i0 = j, i1 = j | (1 << BB), i2 = j | (1 << BA), i3 = j | (1 << BA) | (1 << BB);
@@ -166,14 +164,14 @@ __device__ __forceinline__ void reg_d2(A (&x)[RT_NS], const T *mp, uint32_t creg
 }
 
 // diagonal / parity gates: phase table of NB bits; table bit b of slot j = tb[b] ^ parity(j & q[b])
-template <typename T, int NB, typename A>
-__device__ __forceinline__ void reg_diag(A (&x)[RT_NS], const T *mp, bool thr_on, uint32_t creg, int tb0, int tb1,
+template <typename T, int NB, int NS, typename A>
+__device__ __forceinline__ void reg_diag(A (&x)[NS], const T *mp, bool thr_on, uint32_t creg, int tb0, int tb1,
                                          uint32_t q0, uint32_t q1) {
     const A *tab = reinterpret_cast<const A *>(mp);
     if (NB == 0) {
         const A e = tab[0];
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if (thr_on && (j & creg) == creg) {
                 const A a = x[j];
                 x[j].x = e.x * a.x - e.y * a.y;
@@ -185,7 +183,7 @@ __device__ __forceinline__ void reg_diag(A (&x)[RT_NS], const T *mp, bool thr_on
         const A e0 = tab[0], e1 = tab[1];
         const A pa = tb1 ? e1 : e0, pb = tb1 ? e0 : e1;
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if (thr_on && (j & creg) == creg) {
                 const bool odd = __popc(j & q1) & 1;
                 const T pr = odd ? pb.x : pa.x, pi = odd ? pb.y : pa.y;
@@ -197,7 +195,7 @@ __device__ __forceinline__ void reg_diag(A (&x)[RT_NS], const T *mp, bool thr_on
     } else {
         const A e0 = tab[0], e1 = tab[1], e2 = tab[2], e3 = tab[3];
 #pragma unroll
-        for (int j = 0; j < RT_NS; ++j) {
+        for (int j = 0; j < NS; ++j) {
             if (thr_on && (j & creg) == creg) {
                 const int c0 = tb0 ^ (__popc(j & q0) & 1), c1 = tb1 ^ (__popc(j & q1) & 1);
                 const T pr = c0 ? (c1 ? e3.x : e2.x) : (c1 ? e1.x : e0.x);
@@ -210,11 +208,14 @@ __device__ __forceinline__ void reg_diag(A (&x)[RT_NS], const T *mp, bool thr_on
     }
 }
 
-template <typename T, int MINB>
-__global__ void __launch_bounds__(RT_NT, MINB)
+template <typename T, int RB, int MINB>
+__global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     k_tile_regs(void *single, void *const *table, const __grid_constant__ RegProgram P) {
     using A = typename Cx<T>::type;
     constexpr int SW = Cx<T>::SW;
+    constexpr int NS = 1 << RB;            // amplitudes per thread
+    constexpr int NT = 1 << (RT_TB - RB);  // threads per CTA
+    constexpr int NTB = RT_TB - RB;        // thread bits
     extern __shared__ __align__(16) unsigned char smem_raw[];
     A *s = reinterpret_cast<A *>(smem_raw);
     A *gbase = reinterpret_cast<A *>(table ? table[blockIdx.y] : single);
@@ -225,37 +226,52 @@ __global__ void __launch_bounds__(RT_NT, MINB)
     // broadcast LDS: indexed constant-bank loads (LDC) inside the thread-divergent gate code run on the ADU pipe,
     // which ncu showed to be the busiest unit of the first version of this kernel (52 % vs 33 % FP64).
     T *spool = reinterpret_cast<T *>(smem_raw + (sizeof(A) << RT_TB));
-    for (int i = tid; i < P.pool_used; i += RT_NT) spool[i] = (T)P.pool[i];
+    for (int i = tid; i < P.pool_used; i += NT) spool[i] = (T)P.pool[i];
     __syncthreads();
 
-    A x[RT_NS];
+    A x[NS];
     for (int p = 0; p < P.n_passes; ++p) {
         const RegPass &ps = P.passes[p];
         uint32_t lt = 0;  // thread part of the tile-local index
 #pragma unroll
-        for (int i = 0; i < RT_TB - RT_RB; ++i) lt |= ((tid >> i) & 1u) << ps.tbits[i];
-        const uint32_t r0 = 1u << ps.rbits[0], r1 = 1u << ps.rbits[1], r2 = 1u << ps.rbits[2], r3 = 1u << ps.rbits[3];
+        for (int i = 0; i < NTB; ++i) lt |= ((tid >> i) & 1u) << ps.tbits[i];
+        uint32_t sr[RB];   // swizzled shared-memory offset of register bit b
+        uint64_t gr[RB];   // global offset of register bit b
         const uint32_t st = swz<SW>(lt);
-        const uint32_t s0 = swz<SW>(r0), s1 = swz<SW>(r1), s2 = swz<SW>(r2), s3 = swz<SW>(r3);
         const bool first = p == 0, last = p == P.n_passes - 1;
-        uint64_t gt = 0, g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        uint64_t gt = 0;
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            sr[b] = swz<SW>(1u << ps.rbits[b]);
+            gr[b] = 0;
+        }
         if (first || last) {
 #pragma unroll
-            for (int i = 0; i < RT_TB - RT_RB; ++i) gt |= (uint64_t)((tid >> i) & 1u) << P.gpos[ps.tbits[i]];
+            for (int i = 0; i < NTB; ++i) gt |= (uint64_t)((tid >> i) & 1u) << P.gpos[ps.tbits[i]];
             gt |= base;
-            g0 = 1ull << P.gpos[ps.rbits[0]];
-            g1 = 1ull << P.gpos[ps.rbits[1]];
-            g2 = 1ull << P.gpos[ps.rbits[2]];
-            g3 = 1ull << P.gpos[ps.rbits[3]];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) gr[b] = 1ull << P.gpos[ps.rbits[b]];
         }
+        auto goff = [&](int j) {
+            uint64_t o = gt;
+#pragma unroll
+            for (int b = 0; b < RB; ++b)
+                if ((j >> b) & 1) o += gr[b];
+            return o;
+        };
+        auto soff = [&](int j) {
+            uint32_t o = st;
+#pragma unroll
+            for (int b = 0; b < RB; ++b)
+                if ((j >> b) & 1) o ^= sr[b];
+            return o;
+        };
         if (first) {
 #pragma unroll
-            for (int j = 0; j < RT_NS; ++j)
-                x[j] = gbase[gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)];
+            for (int j = 0; j < NS; ++j) x[j] = gbase[goff(j)];
         } else {
 #pragma unroll
-            for (int j = 0; j < RT_NS; ++j)
-                x[j] = s[st ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)];
+            for (int j = 0; j < NS; ++j) x[j] = s[soff(j)];
         }
 
         for (int gi = ps.gate_begin; gi < ps.gate_end; ++gi) {
@@ -270,29 +286,39 @@ __global__ void __launch_bounds__(RT_NT, MINB)
                 const int tb1 = (__popc(tid & g.thr_mask[1]) ^ __popcll(outside & g.out_mask[1])) & 1;
                 const uint32_t q0 = g.reg_mask[0], q1 = g.reg_mask[1];
                 if (nb == 0)
-                    reg_diag<T, 0>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+                    reg_diag<T, 0, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
                 else if (nb == 1)
-                    reg_diag<T, 1>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+                    reg_diag<T, 1, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
                 else
-                    reg_diag<T, 2>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+                    reg_diag<T, 2, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
             } else if (g.kind == RG_D2) {
                 if (thr_on) {
-                    switch (g.ra * 4 + g.rb) {
-                    case 1 * 4 + 0: reg_d2<T, 1, 0>(x, mp, creg); break;
-                    case 2 * 4 + 0: reg_d2<T, 2, 0>(x, mp, creg); break;
-                    case 2 * 4 + 1: reg_d2<T, 2, 1>(x, mp, creg); break;
-                    case 3 * 4 + 0: reg_d2<T, 3, 0>(x, mp, creg); break;
-                    case 3 * 4 + 1: reg_d2<T, 3, 1>(x, mp, creg); break;
-                    default: reg_d2<T, 3, 2>(x, mp, creg); break;
+                    const int pair = g.ra * 4 + g.rb;
+                    if (pair == 1 * 4 + 0) {
+                        reg_d2<T, 1, 0, NS>(x, mp, creg);
+                    } else if (pair == 2 * 4 + 0) {
+                        reg_d2<T, 2, 0, NS>(x, mp, creg);
+                    } else if (pair == 2 * 4 + 1) {
+                        reg_d2<T, 2, 1, NS>(x, mp, creg);
+                    } else if constexpr (RB > 3) {
+                        if (pair == 3 * 4 + 0)
+                            reg_d2<T, 3, 0, NS>(x, mp, creg);
+                        else if (pair == 3 * 4 + 1)
+                            reg_d2<T, 3, 1, NS>(x, mp, creg);
+                        else
+                            reg_d2<T, 3, 2, NS>(x, mp, creg);
                     }
                 }
             } else {
                 if (thr_on) {
-                    switch (g.ra) {
-                    case 0: reg_d1<T, 0>(x, g.kind, mp, creg); break;
-                    case 1: reg_d1<T, 1>(x, g.kind, mp, creg); break;
-                    case 2: reg_d1<T, 2>(x, g.kind, mp, creg); break;
-                    default: reg_d1<T, 3>(x, g.kind, mp, creg); break;
+                    if (g.ra == 0) {
+                        reg_d1<T, 0, NS>(x, g.kind, mp, creg);
+                    } else if (g.ra == 1) {
+                        reg_d1<T, 1, NS>(x, g.kind, mp, creg);
+                    } else if (g.ra == 2) {
+                        reg_d1<T, 2, NS>(x, g.kind, mp, creg);
+                    } else if constexpr (RB > 3) {
+                        reg_d1<T, 3, NS>(x, g.kind, mp, creg);
                     }
                 }
             }
@@ -300,13 +326,11 @@ __global__ void __launch_bounds__(RT_NT, MINB)
 
         if (last) {
 #pragma unroll
-            for (int j = 0; j < RT_NS; ++j)
-                gbase[gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)] = x[j];
+            for (int j = 0; j < NS; ++j) gbase[goff(j)] = x[j];
         } else {
             if (!first) __syncthreads();  // every thread has finished reading the previous layout
 #pragma unroll
-            for (int j = 0; j < RT_NS; ++j)
-                s[st ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)] = x[j];
+            for (int j = 0; j < NS; ++j) s[soff(j)] = x[j];
             __syncthreads();
         }
     }
@@ -362,18 +386,26 @@ uint64_t regs_need_bits(const LoweredGate &g) { return g.kind == LoweredGate::DE
 
 namespace {
 
-template <typename T> void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs) {
-    constexpr int MINB = sizeof(T) == 8 ? 2 : 3;
+template <typename T, int RB> void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs) {
+    // register budget: 16 amplitudes per thread need 2 CTAs of 256 threads (128 registers); 8 amplitudes per thread run as
+    // 2 CTAs of 512 threads (64 registers)
+    constexpr int MINB = RB == 4 ? (sizeof(T) == 8 ? 2 : 3) : 2;
     const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
     static bool configured[64] = {false};  // per device: function attributes belong to the device's context
-    auto kern = k_tile_regs<T, MINB>;
+    auto kern = k_tile_regs<T, RB, MINB>;
     if (!configured[sv.device & 63]) {
         QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[sv.device & 63] = true;
     }
     dim3 grid((unsigned)(1ull << (sv.n - RT_TB)), (unsigned)n_vecs);
-    kern<<<grid, RT_NT, smem, sv.stream>>>(table ? nullptr : sv.data, table, P);
+    kern<<<grid, 1 << (RT_TB - RB), smem, sv.stream>>>(table ? nullptr : sv.data, table, P);
     QSV_CUDA(cudaGetLastError());
+}
+
+int regs_rb() {
+    const char *v = std::getenv("QSV_REGS_RB");
+    const int rb = v ? std::atoi(v) : 4;
+    return rb == 3 ? 3 : 4;
 }
 
 }  // namespace
@@ -383,6 +415,7 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
                     int n_vecs) {
     const int n = sv.n;
     const int tb = RT_TB;
+    const int rb = regs_rb();
     QSV_CHECK(n >= tb, "internal: register tile kernel needs at least 12 local qubits");
     QSV_CHECK((int)gates.size() <= RT_MAX_GATES, "internal: too many gates in a sweep");
     RegProgram P;
@@ -542,7 +575,7 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
                 for (int i : preds[j]) ready = ready && dn[i];
                 if (!ready) continue;
                 const uint32_t u = R | ng[j].dense;
-                if (__builtin_popcount(u) > RT_RB || (u & (F | ng[j].forbid))) continue;
+                if (__builtin_popcount(u) > rb || (u & (F | ng[j].forbid))) continue;
                 const int nw = __builtin_popcount(u) - __builtin_popcount(R);
                 if (nw < best_new) {
                     best_new = nw;
@@ -577,9 +610,9 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         RegPass &ps = P.passes[P.n_passes++];
         // register bits: the dense bits of the pass, filled up with the highest other positions
         uint32_t R = best_R;
-        for (int p = tb - 1; p >= 0 && __builtin_popcount(R) < RT_RB; --p)
+        for (int p = tb - 1; p >= 0 && __builtin_popcount(R) < rb; --p)
             if (!((R | best_F) >> p & 1)) R |= 1u << p;
-        QSV_CHECK(__builtin_popcount(R) == RT_RB, "internal: no free register bits for a pass");
+        QSV_CHECK(__builtin_popcount(R) == rb, "internal: no free register bits for a pass");
         int regbit_of[16];
         for (int p = 0, k = 0; p < tb; ++p) {
             regbit_of[p] = -1;
@@ -607,7 +640,7 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         for (size_t q = 5; q < rest.size(); ++q) ordered.push_back(rest[q]);
         int thrbit_of[16];
         for (int p = 0; p < tb; ++p) thrbit_of[p] = -1;
-        for (int k = 0; k < tb - RT_RB; ++k) {
+        for (int k = 0; k < tb - rb; ++k) {
             ps.tbits[k] = (unsigned char)ordered[k];
             thrbit_of[ordered[k]] = k;
         }
@@ -656,10 +689,17 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     P.pool_used = n_pool;
     sv.stat_launches += 1;
     sv.stat_sweeps += 1;
-    if (sv.dtype == QSV_C128)
-        launch_regs_t<double>(sv, P, table, n_vecs);
-    else
-        launch_regs_t<float>(sv, P, table, n_vecs);
+    if (sv.dtype == QSV_C128) {
+        if (rb == 4)
+            launch_regs_t<double, 4>(sv, P, table, n_vecs);
+        else
+            launch_regs_t<double, 3>(sv, P, table, n_vecs);
+    } else {
+        if (rb == 4)
+            launch_regs_t<float, 4>(sv, P, table, n_vecs);
+        else
+            launch_regs_t<float, 3>(sv, P, table, n_vecs);
+    }
 }
 
 }  // namespace qsv

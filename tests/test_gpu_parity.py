@@ -540,11 +540,12 @@ def test_config3_vqe_reduced(q):
 # register-tile executor and batched reductions: dedicated stress cases
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("n,low", [(12, 4), (12, 1), (14, 3), (15, 6), (13, 9)])
-def test_register_tile_kernel_stress(q, n, low, dtype, monkeypatch):
+@pytest.mark.parametrize("n,low,rb", [(12, 4, 4), (12, 1, 4), (14, 3, 4), (15, 6, 4), (13, 9, 4), (13, 4, 3), (15, 2, 3)])
+def test_register_tile_kernel_stress(q, n, low, rb, dtype, monkeypatch):
     """csrc/tile_regs.cu: controls on register / thread / outside bits, two-level gates taken as 4x4 blocks, diagonal
     tables with mixed bit sources, every tile-low-bit setting, against the oracle."""
     monkeypatch.setenv("QSV_REGS_LOW", str(low))
+    monkeypatch.setenv("QSV_REGS_RB", str(rb))  # 16 or 8 amplitudes per thread
     rng = np.random.default_rng(1000 * n + low)
     names = ["RX", "RY", "RZ", "CNOT", "CZ", "Hadamard", "PhaseShift", "IsingXX", "IsingYY", "IsingZZ", "CRX", "CRY", "CRZ",
              "SWAP", "Toffoli", "SingleExcitation", "SingleExcitationPlus", "S", "T", "PauliX", "PauliY", "PauliZ", "MultiRZ",
