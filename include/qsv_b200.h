@@ -101,6 +101,12 @@ int qsv_ops_size(const qsv_ops *ops);
  * shared-memory tile kernels (one HBM sweep per fused block); fuse = 0 applies gate by gate.
  * This is the batched form of apply_cq (lightning_gpu.py:519-555). */
 int qsv_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse);
+/* host-only view of what qsv_apply_ops(fuse = 1) would do for an n_qubits register (no device needed): gates are
+ * merged, then packed into HBM sweeps over the dependency DAG of the circuit (dag = 1) or in program order
+ * (dag = 0); low_bits = contiguous low tile bits (0 = default).  order_valid = 1 when every gate is executed
+ * exactly once and every pair of gates that does not commute structurally keeps its program order. */
+int qsv_ops_plan_sweeps(const qsv_ops *ops, int n_qubits, int dag, int low_bits, int64_t *n_gates_merged,
+                        int64_t *n_sweeps, int64_t *max_gates_per_sweep, int *order_valid);
 /* statistics of the last qsv_apply_ops on this state: kernel launches and HBM sweeps */
 int qsv_last_apply_stats(const qsv_state *sv, int64_t *launches, int64_t *sweeps);
 

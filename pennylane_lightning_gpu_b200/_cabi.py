@@ -64,6 +64,7 @@ SIGNATURES = {
     "qsv_ops_append": (_I, [_P, C.c_char_p, _IP, _I, _DP, _I, _I, _DP, C.c_size_t]),
     "qsv_ops_size": (_I, [_P]),
     "qsv_apply_ops": (_I, [_P, _P, _I]),
+    "qsv_ops_plan_sweeps": (_I, [_P, _I, _I, _I, _I64P, _I64P, _I64P, _IP]),
     "qsv_last_apply_stats": (_I, [_P, _I64P, _I64P]),
     "qsv_expval_named": (_I, [_P, C.c_char_p, _IP, _I, _DP, _I, _DP]),
     "qsv_expval_matrix": (_I, [_P, _DP, _IP, _I, _DP]),
@@ -191,6 +192,14 @@ class Ops:
 
     def __len__(self):
         return lib().qsv_ops_size(self._h)
+
+    def plan_sweeps(self, n_qubits: int, dag: bool = True, low_bits: int = 0) -> dict:
+        """Host-only: how apply_ops(fuse=True) would pack this circuit into HBM sweeps (no device needed)."""
+        m, s, g, ok = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        _check(lib().qsv_ops_plan_sweeps(self._h, n_qubits, int(bool(dag)), low_bits, C.byref(m), C.byref(s),
+                                         C.byref(g), C.byref(ok)))
+        return {"gates_after_merge": m.value, "sweeps": s.value, "max_gates_per_sweep": g.value,
+                "order_valid": bool(ok.value)}
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

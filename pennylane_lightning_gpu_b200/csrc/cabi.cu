@@ -335,6 +335,23 @@ int qsv_ops_append(qsv_ops *ops, const char *name, const int *wires, int n_wires
 
 int qsv_ops_size(const qsv_ops *ops) { return ops ? (int)ops->ops.size() : -1; }
 
+static std::vector<LoweredGate> lower_all(int n_qubits, const qsv_ops *ops) {
+    std::vector<LoweredGate> gates;
+    gates.reserve(ops->ops.size());
+    for (const auto &op : ops->ops) {
+        if (op.name == "Identity") continue;
+        if (find_gate(op.name) != nullptr) {
+            gates.push_back(lower_named(n_qubits, op.name, op.wires, op.params, op.inverse));
+        } else {
+            QSV_CHECK(!op.matrix.empty(), "Currently unsupported gate: " + op.name);
+            const size_t dim = 1ull << op.wires.size();
+            QSV_CHECK(op.matrix.size() == dim * dim, "matrix of gate " + op.name + " does not match its wires");
+            gates.push_back(lower_matrix(n_qubits, op.matrix.data(), {}, op.wires, op.inverse));
+        }
+    }
+    return gates;
+}
+
 int qsv_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse) {
     QSV_API_BEGIN
     need(sv, "state");
@@ -344,21 +361,45 @@ int qsv_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse) {
     if (!fuse) {
         for (const auto &op : ops->ops) apply_op(*sv, op, false);
     } else {
-        std::vector<LoweredGate> gates;
-        gates.reserve(ops->ops.size());
-        for (const auto &op : ops->ops) {
-            if (op.name == "Identity") continue;
-            if (find_gate(op.name) != nullptr) {
-                gates.push_back(lower_named(sv->n, op.name, op.wires, op.params, op.inverse));
-            } else {
-                QSV_CHECK(!op.matrix.empty(), "Currently unsupported gate: " + op.name);
-                const size_t dim = 1ull << op.wires.size();
-                QSV_CHECK(op.matrix.size() == dim * dim, "matrix of gate " + op.name + " does not match its wires");
-                gates.push_back(lower_matrix(sv->n, op.matrix.data(), {}, op.wires, op.inverse));
-            }
-        }
-        apply_ops_fused(*sv, gates);
+        apply_ops_fused(*sv, lower_all(sv->n, ops));
     }
+    QSV_API_END
+}
+
+int qsv_ops_plan_sweeps(const qsv_ops *ops, int n_qubits, int dag, int low_bits, int64_t *n_gates_merged,
+                        int64_t *n_sweeps, int64_t *max_gates_per_sweep, int *order_valid) {
+    QSV_API_BEGIN
+    need(ops, "ops");
+    QSV_CHECK(n_qubits >= 12 && n_qubits <= 62, "sweep planning needs 12..62 qubits");
+    const int L = std::max(1, std::min(low_bits > 0 ? low_bits : 4, 11));
+    const std::vector<LoweredGate> merged = prepare_gates_regs(lower_all(n_qubits, ops));
+    const std::vector<SweepPlan> plan = plan_sweeps_regs(n_qubits, merged, L, dag != 0, 48, 512);
+    // self-check: every gate exactly once, and every pair that does not commute structurally keeps its order
+    std::vector<int64_t> pos(merged.size(), -1);
+    int64_t at = 0, biggest = 0, total = 0;
+    bool ok = true;
+    for (const SweepPlan &sw : plan) {
+        biggest = std::max<int64_t>(biggest, (int64_t)sw.gates.size());
+        for (int i : sw.gates) {
+            ok = ok && i >= 0 && i < (int)merged.size() && pos[i] < 0;
+            if (!ok) break;
+            pos[i] = at++;
+        }
+        if (sw.fused) ok = ok && __builtin_popcountll(sw.need) <= 12 - L;
+    }
+    for (size_t i = 0; ok && i < merged.size(); ++i) {
+        if (merged[i].kind == LoweredGate::NOP) continue;
+        ++total;
+        ok = ok && pos[i] >= 0;
+        for (size_t j = i + 1; ok && j < merged.size(); ++j)
+            if (merged[j].kind != LoweredGate::NOP && !gates_commute_structurally(merged[i], merged[j]))
+                ok = pos[j] >= 0 && pos[i] < pos[j];
+    }
+    ok = ok && at == total;
+    if (n_gates_merged) *n_gates_merged = total;
+    if (n_sweeps) *n_sweeps = (int64_t)plan.size();
+    if (max_gates_per_sweep) *max_gates_per_sweep = biggest;
+    if (order_valid) *order_valid = ok ? 1 : 0;
     QSV_API_END
 }
 

@@ -198,7 +198,16 @@ void apply_op(State &sv, const Op &op, bool extra_adjoint);
 void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
 // same, on several vectors at once (dev_table = device array of n_vecs pointers, or null for sv.data)
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs);
-// register-blocked tile kernel (tile_regs.cu)
+// register-blocked tile kernel (tile_regs.cu) and its sweep planner (tile_kernels.cu)
+struct SweepPlan {
+    std::vector<int> gates;  // indices into the (merged) gate list, in execution order
+    uint64_t need = 0;       // dense-target bits >= L the tile must contain
+    bool fused = false;      // false: a lone gate for the one-sweep-per-gate kernels
+};
+std::vector<LoweredGate> prepare_gates_regs(const std::vector<LoweredGate> &gates_in);
+std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag,
+                                        int max_gates, int window);
+bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);
 bool regs_fusable(const LoweredGate &g, int n_local);
 uint64_t regs_need_bits(const LoweredGate &g);
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,

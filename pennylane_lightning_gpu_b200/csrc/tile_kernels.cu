@@ -541,52 +541,144 @@ std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> 
 
 }  // namespace
 
-// Register-blocked executor (tile_regs.cu): same sweep packing, but the tile has 12 - L arbitrary high bits with
-// L as small as one warp-wide access allows, and the gates of a sweep are list-scheduled into register passes.
+// Register-blocked executor (tile_regs.cu).  The tile has 12 - L arbitrary high bits with L as small as one
+// warp-wide access allows, and the gates of a sweep are list-scheduled into register passes.
+//
+// Sweep packing works on the dependency DAG of the circuit instead of its program order: two gates commute when
+// they share no index bit, or share only bits on which both act diagonally (controls, phase tables, parity masks),
+// so a sweep may take any gate whose predecessors are already inside it (or done) as long as the union of the
+// high dense-target bits still fits the tile.  On the config-2 circuit (200 random gates, 30 qubits) this packs
+// 8 sweeps instead of the 12 of in-order packing.  QSV_REGS_DAG=0 restores program order.
+std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag,
+                                        int max_gates, int window) {
+    const int max_hi = 12 - L;
+    const uint64_t low = (1ull << L) - 1ull;
+    std::vector<SweepPlan> plan;
+    auto pool_of = [](const LoweredGate &g) {
+        return (g.kind == LoweredGate::DENSE && !(g.k == 1 && g.tgt_bits.size() == 1)) ? 32 : 8;
+    };
+    // one maximal run of fusable gates (indices into `gates`), packed over its dependency DAG
+    auto pack_segment = [&](const std::vector<int> &seg) {
+        const int m = (int)seg.size();
+        std::vector<uint64_t> need(m);
+        std::vector<std::vector<int>> succ(m);
+        std::vector<int> unsat(m, 0);
+        {
+            // exact dependencies through per-bit tracking: the last gate that touched the bit non-diagonally and the
+            // diagonal touches since then
+            int last_dense[64];
+            std::vector<int> diag_since[64];
+            for (int b = 0; b < 64; ++b) last_dense[b] = -1;
+            auto edge = [&](int i, int j) {
+                if (i < 0 || (!succ[i].empty() && succ[i].back() == j)) return;
+                succ[i].push_back(j);
+                ++unsat[j];
+            };
+            for (int j = 0; j < m; ++j) {
+                const LoweredGate &g = gates[seg[j]];
+                const uint64_t dense = regs_need_bits(g);
+                need[j] = dense & ~low;
+                const uint64_t bits = all_bits(g) | dense;
+                for (int b = 0; b < 64; ++b) {
+                    if (!(bits >> b & 1)) continue;
+                    edge(last_dense[b], j);
+                    if (dense >> b & 1) {
+                        for (int i : diag_since[b]) edge(i, j);
+                        diag_since[b].clear();
+                        last_dense[b] = j;
+                    } else {
+                        diag_since[b].push_back(j);
+                    }
+                }
+            }
+        }
+        std::vector<char> done(m, 0);
+        int first = 0, n_done = 0;
+        while (n_done < m) {
+            while (done[first]) ++first;
+            SweepPlan sw;
+            int cur_pool = 0;
+            auto try_take = [&](int j) {
+                const int pn = pool_of(gates[seg[j]]);
+                if (__builtin_popcountll(sw.need | need[j]) > max_hi || (int)sw.gates.size() >= max_gates ||
+                    cur_pool + pn > 1280)
+                    return false;
+                sw.gates.push_back(seg[j]);
+                sw.need |= need[j];
+                cur_pool += pn;
+                done[j] = 1;
+                ++n_done;
+                for (int k : succ[j]) --unsat[k];
+                return true;
+            };
+            if (!dag) {
+                // program order: the first gate that does not fit ends the sweep
+                for (int j = first; j < m && try_take(j); ++j) {
+                }
+            } else {
+                // first fit over the ready gates of a look-ahead window, repeated until nothing more fits
+                const int stop = std::min(m, first + window);
+                for (bool progress = true; progress;) {
+                    progress = false;
+                    for (int j = first; j < stop; ++j)
+                        if (!done[j] && unsat[j] == 0 && try_take(j)) progress = true;
+                }
+            }
+            QSV_CHECK(!sw.gates.empty(), "internal: sweep packing made no progress");
+            sw.fused = sw.gates.size() > 1;  // a lone gate: the one-sweep kernel touches only what the gate changes
+            plan.push_back(std::move(sw));
+        }
+    };
+    std::vector<int> seg;
+    for (int i = 0; i < (int)gates.size(); ++i) {
+        const LoweredGate &g = gates[i];
+        if (g.kind == LoweredGate::NOP) continue;
+        if (!regs_fusable(g, n_local)) {
+            pack_segment(seg);
+            seg.clear();
+            SweepPlan sw;
+            sw.gates.push_back(i);
+            plan.push_back(std::move(sw));
+            continue;
+        }
+        seg.push_back(i);
+    }
+    pack_segment(seg);
+    return plan;
+}
+
+std::vector<LoweredGate> prepare_gates_regs(const std::vector<LoweredGate> &gates_in) {
+    return env_int("QSV_MERGE_1Q", 1) != 0 ? merge_single_qubit_runs(gates_in) : gates_in;
+}
+
+// commutation rule the packer relies on, pairwise (used by the plan self-check of the C ABI and by the tests)
+bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b) {
+    const uint64_t da = a.kind == LoweredGate::DENSE ? touched_mask(a) : 0, db = b.kind == LoweredGate::DENSE ? touched_mask(b) : 0;
+    const uint64_t ba = all_bits(a) | da, bb = all_bits(b) | db;
+    return ((da & bb) | (ba & db)) == 0;
+}
+
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
-    const int max_hi = 12 - L;
-    const bool merge = env_int("QSV_MERGE_1Q", 1) != 0;
-    const int max_gates = std::min(48, env_int("QSV_REGS_MAX_GATES", 48));
-    const std::vector<LoweredGate> merged = merge ? merge_single_qubit_runs(gates_in) : gates_in;
+    const std::vector<LoweredGate> merged = prepare_gates_regs(gates_in);
+    const std::vector<SweepPlan> plan =
+        plan_sweeps_regs(sv.n, merged, L, env_int("QSV_REGS_DAG", 1) != 0, std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
+                         std::max(1, env_int("QSV_REGS_WINDOW", 512)));
     std::vector<const LoweredGate *> cur;
-    uint64_t cur_need = 0;
-    int cur_pool = 0;
-    auto single = [&](const LoweredGate &g) {
-        if (dev_table)
-            launch_gate_multi(sv, g, dev_table, n_vecs);
-        else
-            launch_gate(sv, g);
-    };
-    auto flush = [&]() {
-        if (cur.empty()) return;
-        if (cur.size() == 1)
-            single(*cur[0]);  // a lone gate: the one-sweep kernel touches only what the gate changes
-        else
-            run_sweep_regs(sv, cur, cur_need, L, dev_table, n_vecs);
-        cur.clear();
-        cur_need = 0;
-        cur_pool = 0;
-    };
-    const uint64_t low = (1ull << L) - 1ull;
-    for (const LoweredGate &g : merged) {
-        if (g.kind == LoweredGate::NOP) continue;
-        if (!regs_fusable(g, sv.n)) {
-            flush();
-            single(g);
+    for (const SweepPlan &sw : plan) {
+        if (!sw.fused) {
+            const LoweredGate &g = merged[sw.gates[0]];
+            if (dev_table)
+                launch_gate_multi(sv, g, dev_table, n_vecs);
+            else
+                launch_gate(sv, g);
             continue;
         }
-        const uint64_t need = regs_need_bits(g) & ~low;
-        const int pn = (g.kind == LoweredGate::DENSE && !(g.k == 1 && g.tgt_bits.size() == 1)) ? 32 : 8;
-        const bool fits = __builtin_popcountll(cur_need | need) <= max_hi && (int)cur.size() < max_gates &&
-                          cur_pool + pn <= 1280;
-        if (!fits) flush();
-        cur.push_back(&g);
-        cur_need |= need;
-        cur_pool += pn;
+        cur.clear();
+        for (int i : sw.gates) cur.push_back(&merged[i]);
+        run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs);
     }
-    flush();
 }
 
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {

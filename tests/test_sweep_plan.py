@@ -1,0 +1,60 @@
+"""CPU-only checks of the host-side sweep planner of the fused executor (csrc/tile_kernels.cu: plan_sweeps_regs):
+packing over the dependency DAG must execute every gate exactly once, keep the order of every pair of gates that
+does not commute structurally, and need fewer HBM sweeps than program-order packing."""
+import numpy as np
+import pytest
+
+from pennylane_lightning_gpu_b200 import _build, workloads
+
+
+@pytest.fixture(scope="module")
+def q():
+    _build.build_lib()
+    import pennylane_lightning_gpu_b200 as q
+
+    return q
+
+
+def test_config2_circuit_dag_packing(q):
+    ops = workloads.random_gate_circuit(30, 200, 2024)
+    rec = q.Ops(ops)
+    in_order = rec.plan_sweeps(30, dag=False)
+    dag = rec.plan_sweeps(30, dag=True)
+    assert in_order["order_valid"] and dag["order_valid"]
+    assert in_order["gates_after_merge"] == dag["gates_after_merge"]
+    assert dag["sweeps"] < in_order["sweeps"]
+    assert dag["sweeps"] <= 9  # 8 with the default tile geometry (4 low bits + 8 arbitrary high bits)
+
+
+@pytest.mark.parametrize("n,seed", [(12, 0), (14, 1), (20, 2), (33, 3)])
+def test_random_circuits_keep_dependencies(q, n, seed):
+    rng = np.random.default_rng(seed)
+    names1 = ["RX", "RY", "RZ", "Hadamard", "PauliX", "S", "T", "PhaseShift"]
+    names2 = ["CNOT", "CZ", "SWAP", "CRX", "CRZ", "IsingXX", "IsingZZ", "ControlledPhaseShift", "SingleExcitation"]
+    ops = []
+    for _ in range(400):
+        r = rng.random()
+        if r < 0.5:
+            nm = names1[rng.integers(len(names1))]
+            w = [int(rng.integers(n))]
+        elif r < 0.9:
+            nm = names2[rng.integers(len(names2))]
+            w = [int(x) for x in rng.choice(n, 2, replace=False)]
+        elif r < 0.95:
+            nm, w = "Toffoli", [int(x) for x in rng.choice(n, 3, replace=False)]
+        else:
+            nm, w = "MultiRZ", [int(x) for x in rng.choice(n, 3, replace=False)]
+        par = [float(rng.uniform(-3, 3))] if nm[0] in "RCIMS" and nm not in ("CNOT", "CZ", "SWAP", "S") or nm == "PhaseShift" else []
+        ops.append({"name": nm, "wires": w, "params": par})
+    rec = q.Ops(ops)
+    for low in (0, 3, 6):
+        for dag in (False, True):
+            plan = rec.plan_sweeps(n, dag=dag, low_bits=low)
+            assert plan["order_valid"], (n, seed, low, dag, plan)
+            assert plan["max_gates_per_sweep"] <= 48
+
+
+def test_plan_rejects_unknown_gate(q):
+    rec = q.Ops([{"name": "NoSuchGate", "wires": [0], "params": []}])
+    with pytest.raises(q.QsvError):
+        rec.plan_sweeps(20)
