@@ -19,200 +19,26 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "device_utils.cuh"
+#include <vector>
+
 #include "qsv_internal.h"
+#include "tile_regs_core.cuh"
 
 namespace qsv {
 
+using namespace rt;
+
 namespace {
 
-constexpr int RT_TB = 12;   // tile bits
-constexpr int RT_RB = 4;    // register bits, at most (QSV_REGS_RB=3: 8 amplitudes per thread, 512 threads per CTA)
-constexpr int RT_MAX_GATES = 48;
-constexpr int RT_MAX_PASSES = 48;
-constexpr int RT_POOL = 1280;  // doubles
-
-enum : unsigned char { RG_D1 = 1, RG_D1_REAL = 2, RG_D1_RX = 3, RG_D1_SWAP = 4, RG_D2 = 5, RG_DIAG = 6 };
-
-struct RegGate {
-    unsigned char kind;
-    unsigned char ra, rb;        // register-bit numbers (D1: ra; D2: ra = matrix MSB > rb)
-    unsigned char ctrl_reg;      // controls among the register bits (mask over the slot number)
-    unsigned char reg_mask[2];   // DIAG: table bit b = parity(slot & reg_mask[b]) ^ parity(tid & thr_mask[b]) ^ ...
-    unsigned short ctrl_thr;     // controls among the thread bits (mask over threadIdx.x)
-    unsigned short thr_mask[2];
-    unsigned short mat_off;      // first double of this gate in the pool
-    unsigned short pad0;
-    uint64_t out_ctrl;           // controls outside the tile (global bit positions)
-    uint64_t out_mask[2];        // ... ^ parity(outside & out_mask[b]); table index = 2 * bit[0] + bit[1]
-};
-
-struct RegPass {
-    unsigned char rbits[RT_RB];          // tile-local position of register bit 0..3
-    unsigned char tbits[RT_TB];          // tile-local position of thread bit 0..(TB - RB - 1)
-    unsigned short gate_begin, gate_end;
-};
-
-struct RegProgram {
-    int n_passes;
-    int n_gates;
-    int pool_used;
-    int pad0;
-    uint64_t index_hi;                // value of the index bits above the local shard
-    unsigned char gpos[16];           // global bit of tile-local position p
-    Holes tile_holes;                 // all tile bits, ascending (expands blockIdx.x to the tile base)
-    RegPass passes[RT_MAX_PASSES];
-    RegGate gates[RT_MAX_GATES];
-    double pool[RT_POOL];
-};
-
-template <typename T> struct Cx;
-template <> struct Cx<double> { using type = double2; static constexpr int SW = 3; };
-template <> struct Cx<float> { using type = float2; static constexpr int SW = 4; };
-
-// XOR swizzle of the shared-memory tile: the low SW bits (one 128-byte line) are XORed with every higher
-// SW-bit field, so that lanes differing in any bits with distinct positions mod SW hit distinct banks.
-template <int SW> __device__ __forceinline__ uint32_t swz(uint32_t e) {
-    constexpr uint32_t M = (1u << SW) - 1u;
-    uint32_t r = e;
-#pragma unroll
-    for (int s = SW; s < RT_TB; s += SW) r ^= (e >> s) & M;
-    return r;
-}
-
-// ---- gates on register-resident amplitudes --------------------------------------------------------------
-// Controls among the register bits are a per-slot predicate.  (A variant with separate unpredicated code paths
-// plus a scheduling constraint that keeps controls out of the register bits was measured slower on B200:
-// 196 ms vs 166 ms for the config-2 circuit -- more code, 128 registers with spills.)
-template <typename T, int B, int NS, typename A>
-__device__ __forceinline__ void reg_d1(A (&x)[NS], int kind, const T *mp, uint32_t creg) {
-    const A q0 = reinterpret_cast<const A *>(mp)[0], q1 = reinterpret_cast<const A *>(mp)[1];
-    const A q2 = reinterpret_cast<const A *>(mp)[2], q3 = reinterpret_cast<const A *>(mp)[3];
-    if (kind == RG_D1_SWAP) {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if ((j >> B) & 1) continue;
-            if ((j & creg) == creg) {
-                const A t = x[j];
-                x[j] = x[j | (1 << B)];
-                x[j | (1 << B)] = t;
-            }
-        }
-    } else if (kind == RG_D1_REAL) {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if ((j >> B) & 1) continue;
-            if ((j & creg) == creg) {
-                const A a = x[j], b = x[j | (1 << B)];
-                x[j].x = q0.x * a.x + q1.x * b.x;
-                x[j].y = q0.x * a.y + q1.x * b.y;
-                x[j | (1 << B)].x = q2.x * a.x + q3.x * b.x;
-                x[j | (1 << B)].y = q2.x * a.y + q3.x * b.y;
-            }
-        }
-    } else if (kind == RG_D1_RX) {
-        // real diagonal, imaginary off-diagonal (RX and products of RX)
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if ((j >> B) & 1) continue;
-            if ((j & creg) == creg) {
-                const A a = x[j], b = x[j | (1 << B)];
-                x[j].x = q0.x * a.x - q1.y * b.y;
-                x[j].y = q0.x * a.y + q1.y * b.x;
-                x[j | (1 << B)].x = q3.x * b.x - q2.y * a.y;
-                x[j | (1 << B)].y = q3.x * b.y + q2.y * a.x;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if ((j >> B) & 1) continue;
-            if ((j & creg) == creg) {
-                const A a = x[j], b = x[j | (1 << B)];
-                x[j].x = q0.x * a.x - q0.y * a.y + q1.x * b.x - q1.y * b.y;
-                x[j].y = q0.x * a.y + q0.y * a.x + q1.x * b.y + q1.y * b.x;
-                x[j | (1 << B)].x = q2.x * a.x - q2.y * a.y + q3.x * b.x - q3.y * b.y;
-                x[j | (1 << B)].y = q2.x * a.y + q2.y * a.x + q3.x * b.y + q3.y * b.x;
-            }
-        }
-    }
-}
-
-// 4x4 block on register bits BA > BB; matrix index = 2 * bit(BA) + bit(BB)
-template <typename T, int BA, int BB, int NS, typename A>
-__device__ __forceinline__ void reg_d2(A (&x)[NS], const T *mp, uint32_t creg) {
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-        if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
-        if ((j & creg) == creg) {
-            const int i0 = j, i1 = j | (1 << BB), i2 = j | (1 << BA), i3 = j | (1 << BA) | (1 << BB);
-            const A v0 = x[i0], v1 = x[i1], v2 = x[i2], v3 = x[i3];
-            A y[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const A *row = reinterpret_cast<const A *>(mp) + 4 * r;
-                const A c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
-                y[r].x = c0.x * v0.x - c0.y * v0.y + c1.x * v1.x - c1.y * v1.y + c2.x * v2.x - c2.y * v2.y + c3.x * v3.x - c3.y * v3.y;
-                y[r].y = c0.x * v0.y + c0.y * v0.x + c1.x * v1.y + c1.y * v1.x + c2.x * v2.y + c2.y * v2.x + c3.x * v3.y + c3.y * v3.x;
-            }
-            x[i0] = y[0];
-            x[i1] = y[1];
-            x[i2] = y[2];
-            x[i3] = y[3];
-        }
-    }
-}
-
-// diagonal / parity gates: phase table of NB bits; table bit b of slot j = tb[b] ^ parity(j & q[b])
-template <typename T, int NB, int NS, typename A>
-__device__ __forceinline__ void reg_diag(A (&x)[NS], const T *mp, bool thr_on, uint32_t creg, int tb0, int tb1,
-                                         uint32_t q0, uint32_t q1) {
-    const A *tab = reinterpret_cast<const A *>(mp);
-    if (NB == 0) {
-        const A e = tab[0];
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if (thr_on && (j & creg) == creg) {
-                const A a = x[j];
-                x[j].x = e.x * a.x - e.y * a.y;
-                x[j].y = e.x * a.y + e.y * a.x;
-            }
-        }
-    } else if (NB == 1) {
-        // one table bit (RZ, CRZ, IsingZZ, MultiRZ ...): a per-thread pair of phases, slots pick by parity
-        const A e0 = tab[0], e1 = tab[1];
-        const A pa = tb1 ? e1 : e0, pb = tb1 ? e0 : e1;
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if (thr_on && (j & creg) == creg) {
-                const bool odd = __popc(j & q1) & 1;
-                const T pr = odd ? pb.x : pa.x, pi = odd ? pb.y : pa.y;
-                const A a = x[j];
-                x[j].x = pr * a.x - pi * a.y;
-                x[j].y = pr * a.y + pi * a.x;
-            }
-        }
-    } else {
-        const A e0 = tab[0], e1 = tab[1], e2 = tab[2], e3 = tab[3];
-#pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if (thr_on && (j & creg) == creg) {
-                const int c0 = tb0 ^ (__popc(j & q0) & 1), c1 = tb1 ^ (__popc(j & q1) & 1);
-                const T pr = c0 ? (c1 ? e3.x : e2.x) : (c1 ? e1.x : e0.x);
-                const T pi = c0 ? (c1 ? e3.y : e2.y) : (c1 ? e1.y : e0.y);
-                const A a = x[j];
-                x[j].x = pr * a.x - pi * a.y;
-                x[j].y = pr * a.y + pi * a.x;
-            }
-        }
-    }
-}
+constexpr int RT_TB = TB;
+constexpr int RT_MAX_GATES = MAX_GATES;
+constexpr int RT_MAX_PASSES = MAX_PASSES;
+constexpr int RT_POOL = POOL;
 
 template <typename T, int RB, int MINB>
 __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     k_tile_regs(void *single, void *const *table, const __grid_constant__ RegProgram P) {
     using A = typename Cx<T>::type;
-    constexpr int SW = Cx<T>::SW;
     constexpr int NS = 1 << RB;            // amplitudes per thread
     constexpr int NT = 1 << (RT_TB - RB);  // threads per CTA
     constexpr int NTB = RT_TB - RB;        // thread bits
@@ -222,6 +48,22 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     const uint64_t base = expand_index((uint64_t)blockIdx.x, P.tile_holes);
     const uint64_t outside = base | P.index_hi;
     const uint32_t tid = threadIdx.x;
+    // The tile that the CTA scheduled `prefetch` CTAs after this one will load is requested into L2 now, so that its
+    // HBM latency is hidden behind the arithmetic of the tiles in flight.
+    if (P.prefetch > 0 && blockIdx.x + (unsigned)P.prefetch < gridDim.x) {
+        const uint64_t pbase = expand_index((uint64_t)blockIdx.x + (uint64_t)P.prefetch, P.tile_holes);
+        const uint64_t gt = pbase ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
+        uint64_t gr[RB_MAX];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) gr[b] = P.gl_load.reg[b];
+        if ((tid & (sizeof(A) == 16 ? 7u : 15u)) == 0u) {  // one request per 128-byte line of the warp's row
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const A *p = gbase + slot_offset<RB>(gt, gr, j);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+    }
     // Gate constants go to shared memory once per CTA (in the kernel's precision) and are then read with uniform,
     // broadcast LDS: indexed constant-bank loads (LDC) inside the thread-divergent gate code run on the ADU pipe,
     // which ncu showed to be the busiest unit of the first version of this kernel (52 % vs 33 % FP64).
@@ -232,105 +74,40 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     A x[NS];
     for (int p = 0; p < P.n_passes; ++p) {
         const RegPass &ps = P.passes[p];
-        uint32_t lt = 0;  // thread part of the tile-local index
-#pragma unroll
-        for (int i = 0; i < NTB; ++i) lt |= ((tid >> i) & 1u) << ps.tbits[i];
-        uint32_t sr[RB];   // swizzled shared-memory offset of register bit b
-        uint64_t gr[RB];   // global offset of register bit b
-        const uint32_t st = swz<SW>(lt);
         const bool first = p == 0, last = p == P.n_passes - 1;
-        uint64_t gt = 0;
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            sr[b] = swz<SW>(1u << ps.rbits[b]);
-            gr[b] = 0;
-        }
-        if (first || last) {
-#pragma unroll
-            for (int i = 0; i < NTB; ++i) gt |= (uint64_t)((tid >> i) & 1u) << P.gpos[ps.tbits[i]];
-            gt |= base;
-#pragma unroll
-            for (int b = 0; b < RB; ++b) gr[b] = 1ull << P.gpos[ps.rbits[b]];
-        }
-        auto goff = [&](int j) {
-            uint64_t o = gt;
-#pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if ((j >> b) & 1) o += gr[b];
-            return o;
-        };
-        auto soff = [&](int j) {
-            uint32_t o = st;
-#pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if ((j >> b) & 1) o ^= sr[b];
-            return o;
-        };
         if (first) {
+            const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
+            uint64_t gr[RB_MAX];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) x[j] = gbase[goff(j)];
+            for (int b = 0; b < RB; ++b) gr[b] = P.gl_load.reg[b];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
         } else {
+            const uint32_t st = thread_offset<NTB>(ps.ld_thr, ps.ld_c, tid);
+            uint32_t sr[RB_MAX];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) x[j] = s[soff(j)];
+            for (int b = 0; b < RB; ++b) sr[b] = ps.ld_reg[b];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) x[j] = s[slot_offset<RB>(st, sr, j)];
         }
 
-        for (int gi = ps.gate_begin; gi < ps.gate_end; ++gi) {
-            const RegGate &g = P.gates[gi];
-            if ((outside & g.out_ctrl) != g.out_ctrl) continue;  // CTA-uniform
-            const bool thr_on = (tid & g.ctrl_thr) == g.ctrl_thr;
-            const T *mp = spool + g.mat_off;
-            const uint32_t creg = g.ctrl_reg;
-            if (g.kind == RG_DIAG) {
-                const int nb = g.rb;  // table bits in use
-                const int tb0 = (__popc(tid & g.thr_mask[0]) ^ __popcll(outside & g.out_mask[0])) & 1;
-                const int tb1 = (__popc(tid & g.thr_mask[1]) ^ __popcll(outside & g.out_mask[1])) & 1;
-                const uint32_t q0 = g.reg_mask[0], q1 = g.reg_mask[1];
-                if (nb == 0)
-                    reg_diag<T, 0, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
-                else if (nb == 1)
-                    reg_diag<T, 1, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
-                else
-                    reg_diag<T, 2, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
-            } else if (g.kind == RG_D2) {
-                if (thr_on) {
-                    const int pair = g.ra * 4 + g.rb;
-                    if (pair == 1 * 4 + 0) {
-                        reg_d2<T, 1, 0, NS>(x, mp, creg);
-                    } else if (pair == 2 * 4 + 0) {
-                        reg_d2<T, 2, 0, NS>(x, mp, creg);
-                    } else if (pair == 2 * 4 + 1) {
-                        reg_d2<T, 2, 1, NS>(x, mp, creg);
-                    } else if constexpr (RB > 3) {
-                        if (pair == 3 * 4 + 0)
-                            reg_d2<T, 3, 0, NS>(x, mp, creg);
-                        else if (pair == 3 * 4 + 1)
-                            reg_d2<T, 3, 1, NS>(x, mp, creg);
-                        else
-                            reg_d2<T, 3, 2, NS>(x, mp, creg);
-                    }
-                }
-            } else {
-                if (thr_on) {
-                    if (g.ra == 0) {
-                        reg_d1<T, 0, NS>(x, g.kind, mp, creg);
-                    } else if (g.ra == 1) {
-                        reg_d1<T, 1, NS>(x, g.kind, mp, creg);
-                    } else if (g.ra == 2) {
-                        reg_d1<T, 2, NS>(x, g.kind, mp, creg);
-                    } else if constexpr (RB > 3) {
-                        reg_d1<T, 3, NS>(x, g.kind, mp, creg);
-                    }
-                }
-            }
-        }
+        pass_compute<T, RB>(x, P, ps, tid, outside, spool);
 
         if (last) {
+            const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
+            uint64_t gr[RB_MAX];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) gbase[goff(j)] = x[j];
+            for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
         } else {
             if (!first) __syncthreads();  // every thread has finished reading the previous layout
+            const uint32_t st = thread_offset<NTB>(ps.st_thr, ps.st_c, tid);
+            uint32_t sr[RB_MAX];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) s[soff(j)] = x[j];
+            for (int b = 0; b < RB; ++b) sr[b] = ps.st_reg[b];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s[slot_offset<RB>(st, sr, j)] = x[j];
             __syncthreads();
         }
     }
@@ -350,7 +127,31 @@ struct NormGate {
     uint32_t mask_loc[2] = {0, 0};  // DIAG table-bit masks
     uint64_t mask_out[2] = {0, 0};
     int n_table_bits = 0;
+    int perm = 0;                 // index permutation folded into a pass boundary: 1 = X / CNOT on da, 2 = SWAP(da, db)
     std::vector<double> pool;     // what goes into the constant pool
+};
+
+// GF(2)-affine map on tile-local indices: e -> XOR_p e_p * col[p] ^ c
+struct AffineMap {
+    uint32_t col[RT_TB];
+    uint32_t c = 0;
+    AffineMap() {
+        for (int p = 0; p < RT_TB; ++p) col[p] = 1u << p;
+    }
+    // compose with an index permutation applied AFTER this map
+    void then(const NormGate &g) {
+        auto f = [&](uint32_t v, bool is_const) {
+            if (g.perm == 2) {
+                const uint32_t a = (v >> g.da) & 1u, b = (v >> g.db) & 1u;
+                return (v & ~((1u << g.da) | (1u << g.db))) | (b << g.da) | (a << g.db);
+            }
+            if (g.ctrl_loc == 0) return is_const ? v ^ (1u << g.da) : v;  // PauliX: a translation
+            const uint32_t on = (v & g.ctrl_loc) == g.ctrl_loc ? 1u : 0u;   // single control: linear
+            return v ^ (on << g.da);
+        };
+        for (int p = 0; p < RT_TB; ++p) col[p] = f(col[p], false);
+        c = f(c, true);
+    }
 };
 
 uint64_t touched_of(const LoweredGate &g) {
@@ -402,6 +203,16 @@ template <typename T, int RB> void launch_regs_t(State &sv, const RegProgram &P,
     QSV_CUDA(cudaGetLastError());
 }
 
+int env_int_regs(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+bool env_flag(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v ? std::atoi(v) : dflt) != 0;
+}
+
 int regs_rb() {
     const char *v = std::getenv("QSV_REGS_RB");
     const int rb = v ? std::atoi(v) : 4;
@@ -410,17 +221,18 @@ int regs_rb() {
 
 }  // namespace
 
-// One sweep of the register kernel over `gates` (all regs_fusable, dense-touched bits >= L listed in `need`).
-void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,
-                    int n_vecs) {
-    const int n = sv.n;
+// Program of one sweep of the register kernel over `gates` (all regs_fusable, dense-touched bits >= L listed in `need`).
+void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<const LoweredGate *> &gates, uint64_t need,
+                       int L, int rb, RegProgram &P) {
     const int tb = RT_TB;
-    const int rb = regs_rb();
     QSV_CHECK(n >= tb, "internal: register tile kernel needs at least 12 local qubits");
     QSV_CHECK((int)gates.size() <= RT_MAX_GATES, "internal: too many gates in a sweep");
-    RegProgram P;
+    QSV_CHECK(rb == 3 || rb == 4, "internal: 3 or 4 register bits");
     memset(&P, 0, sizeof(P));
-    P.index_hi = sv.index_hi;
+    P.index_hi = index_hi;
+    const bool fold = env_flag("QSV_REGS_FOLD", 1);
+    const bool merge_diag = env_flag("QSV_REGS_UDIAG", 1);
+    const bool diag_as_d1 = env_flag("QSV_REGS_DIAG1", 1);
 
     // tile bits: the low L bits, the needed high bits, then the lowest free bits
     std::vector<int> hi;
@@ -431,13 +243,14 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     std::sort(hi.begin(), hi.end());
     QSV_CHECK((int)hi.size() == tb - L, "internal: tile bit selection");
     int pos[64];
+    int gpos[RT_TB];  // global bit of tile-local position p
     for (int b = 0; b < 64; ++b) pos[b] = -1;
     std::vector<int> tile_bits;
     for (int b = 0; b < L; ++b) tile_bits.push_back(b);
     for (int b : hi) tile_bits.push_back(b);
     for (int p = 0; p < tb; ++p) {
         pos[tile_bits[p]] = p;
-        P.gpos[p] = (unsigned char)tile_bits[p];
+        gpos[p] = tile_bits[p];
     }
     P.tile_holes = make_holes(tile_bits.data(), tb, 0);
     auto map_mask = [&](uint64_t m, uint64_t &outside) {
@@ -548,6 +361,22 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         }
     }
 
+    // index permutations that can be folded into a pass boundary: PauliX / CNOT with the control inside the tile, SWAP
+    if (fold) {
+        for (size_t i = 0; i < m; ++i) {
+            NormGate &o = ng[i];
+            if (o.ctrl_out != 0) continue;
+            if (o.kind == RG_D1_SWAP && __builtin_popcount(o.ctrl_loc) <= 1) {
+                o.perm = 1;
+            } else if (o.kind == RG_D2 && o.ctrl_loc == 0) {
+                static const double swap_m[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+                bool is_swap = true;
+                for (int q = 0; q < 16; ++q) is_swap = is_swap && o.pool[2 * q] == swap_m[q] && o.pool[2 * q + 1] == 0.0;
+                if (is_swap) o.perm = 2;
+            }
+        }
+    }
+
     // ---- list-schedule into passes -----------------------------------------------------------------
     // gate j depends on an earlier gate i when they share a tile bit that one of them touches non-diagonally
     std::vector<std::vector<int>> preds(m);
@@ -556,6 +385,28 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
             if ((ng[i].dense & ng[j].bits) | (ng[i].bits & ng[j].dense)) preds[j].push_back((int)i);
     std::vector<char> done(m, 0);
     size_t n_done = 0;
+    auto ready_in = [&](size_t j, const std::vector<char> &dn) {
+        for (int i : preds[j])
+            if (!dn[i]) return false;
+        return true;
+    };
+    // folded permutations run at pass boundaries: slot s = before pass s (slot 0: the load from HBM, slot n_passes: the
+    // store to HBM)
+    std::vector<std::vector<int>> slot_perms;
+    auto take_perms = [&]() {
+        std::vector<int> v;
+        for (bool progress = true; progress;) {
+            progress = false;
+            for (size_t j = 0; j < m; ++j)
+                if (!done[j] && ng[j].perm && ready_in(j, done)) {
+                    v.push_back((int)j);
+                    done[j] = 1;
+                    ++n_done;
+                    progress = true;
+                }
+        }
+        return v;
+    };
     auto grow = [&](int seed, std::vector<char> &dn, uint32_t &R, uint32_t &F, std::vector<int> &order) {
         // greedy: keep adding the ready gate that needs the fewest new register bits
         R = 0;
@@ -570,10 +421,7 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
             next = -1;
             int best_new = 99;
             for (size_t j = 0; j < m; ++j) {
-                if (dn[j]) continue;
-                bool ready = true;
-                for (int i : preds[j]) ready = ready && dn[i];
-                if (!ready) continue;
+                if (dn[j] || ng[j].perm || !ready_in(j, dn)) continue;
                 const uint32_t u = R | ng[j].dense;
                 if (__builtin_popcount(u) > rb || (u & (F | ng[j].forbid))) continue;
                 const int nw = __builtin_popcount(u) - __builtin_popcount(R);
@@ -585,16 +433,16 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         }
     };
     int n_pool = 0;
-    const int SW = sv.dtype == QSV_C128 ? 3 : 4;
-    while (n_done < m) {
+    const int SW = dtype == QSV_C128 ? 3 : 4;
+    const int ntb = tb - rb;
+    int lay_r[RT_MAX_PASSES][RB_MAX], lay_t[RT_MAX_PASSES][NTB_MAX];
+    slot_perms.push_back(take_perms());
+    while (n_done < m || P.n_passes == 0) {
         // try every ready gate as the seed of the next pass, keep the pass that retires the most gates
         std::vector<int> best_order;
         uint32_t best_R = 0, best_F = 0;
         for (size_t sd = 0; sd < m; ++sd) {
-            if (done[sd]) continue;
-            bool ready = true;
-            for (int i : preds[sd]) ready = ready && done[i];
-            if (!ready) continue;
+            if (done[sd] || ng[sd].perm || !ready_in(sd, done)) continue;
             std::vector<char> dn = done;
             std::vector<int> order;
             uint32_t R, F;
@@ -605,20 +453,26 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
                 best_F = F;
             }
         }
-        QSV_CHECK(!best_order.empty(), "internal: pass scheduling made no progress");
+        QSV_CHECK(!best_order.empty() || n_done == m, "internal: pass scheduling made no progress");
         QSV_CHECK(P.n_passes < RT_MAX_PASSES, "internal: too many passes in a sweep");
-        RegPass &ps = P.passes[P.n_passes++];
-        // register bits: the dense bits of the pass, filled up with the highest other positions
+        const int pi = P.n_passes++;
+        RegPass &ps = P.passes[pi];
+        // register bits: the dense bits of the pass, filled up with the highest other positions -- preferably ones that no
+        // diagonal gate of the pass looks at, so that those gates stay thread-uniform
+        uint32_t avoid = 0;
+        for (int gi : best_order)
+            if (ng[gi].kind == RG_DIAG) avoid |= ng[gi].bits;
         uint32_t R = best_R;
-        for (int p = tb - 1; p >= 0 && __builtin_popcount(R) < rb; --p)
-            if (!((R | best_F) >> p & 1)) R |= 1u << p;
+        for (int round = 0; round < 2; ++round)
+            for (int p = tb - 1; p >= 0 && __builtin_popcount(R) < rb; --p)
+                if (!((R | best_F) >> p & 1) && (round == 1 || !(avoid >> p & 1))) R |= 1u << p;
         QSV_CHECK(__builtin_popcount(R) == rb, "internal: no free register bits for a pass");
         int regbit_of[16];
         for (int p = 0, k = 0; p < tb; ++p) {
             regbit_of[p] = -1;
             if (R >> p & 1) {
                 regbit_of[p] = k;
-                ps.rbits[k++] = (unsigned char)p;
+                lay_r[pi][k++] = p;
             }
         }
         // thread bits: lanes take the lowest positions (coalescing); among them, the first SW lane bits get
@@ -640,8 +494,8 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         for (size_t q = 5; q < rest.size(); ++q) ordered.push_back(rest[q]);
         int thrbit_of[16];
         for (int p = 0; p < tb; ++p) thrbit_of[p] = -1;
-        for (int k = 0; k < tb - rb; ++k) {
-            ps.tbits[k] = (unsigned char)ordered[k];
+        for (int k = 0; k < ntb; ++k) {
+            lay_t[pi][k] = ordered[k];
             thrbit_of[ordered[k]] = k;
         }
         auto split = [&](uint32_t loc, unsigned &reg, unsigned &thr) {
@@ -655,38 +509,98 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
                         thr |= 1u << thrbit_of[p];
                 }
         };
-        ps.gate_begin = (unsigned short)P.n_gates;
-        for (int gi : best_order) {
-            const NormGate &o = ng[gi];
-            RegGate &t = P.gates[P.n_gates++];
-            t.kind = (unsigned char)o.kind;
+        auto thread_uniform = [&](const NormGate &o) {
+            if (!merge_diag || o.kind != RG_DIAG) return false;
             unsigned reg, thr;
-            split(o.ctrl_loc, reg, thr);
-            t.ctrl_reg = (unsigned char)reg;
-            t.ctrl_thr = (unsigned short)thr;
-            t.out_ctrl = o.ctrl_out;
-            if (o.kind == RG_DIAG) {
-                t.rb = (unsigned char)o.n_table_bits;
-                for (int b = 0; b < 2; ++b) {
-                    split(o.mask_loc[b], reg, thr);
-                    t.reg_mask[b] = (unsigned char)reg;
-                    t.thr_mask[b] = (unsigned short)thr;
-                    t.out_mask[b] = o.mask_out[b];
+            split(o.ctrl_loc | o.mask_loc[0] | o.mask_loc[1], reg, thr);
+            return reg == 0;
+        };
+        ps.gate_begin = (unsigned short)P.n_gates;
+        for (int phase = 0; phase < 2; ++phase) {
+            // phase 0: the thread-uniform diagonal gates (they commute with every other gate of the pass), phase 1: the rest
+            for (int gi : best_order) {
+                const NormGate &o = ng[gi];
+                if (thread_uniform(o) != (phase == 0)) continue;
+                RegGate &t = P.gates[P.n_gates++];
+                t.kind = (unsigned char)o.kind;
+                unsigned reg, thr;
+                split(o.ctrl_loc, reg, thr);
+                t.ctrl_reg = (unsigned char)reg;
+                t.ctrl_thr = (unsigned short)thr;
+                t.out_ctrl = o.ctrl_out;
+                if (o.kind == RG_DIAG) {
+                    t.rb = (unsigned char)o.n_table_bits;
+                    for (int b = 0; b < 2; ++b) {
+                        split(o.mask_loc[b], reg, thr);
+                        t.reg_mask[b] = (unsigned char)reg;
+                        t.thr_mask[b] = (unsigned short)thr;
+                        t.out_mask[b] = o.mask_out[b];
+                    }
+                    // a one-bit phase table with exactly one register bit runs as a diagonal 2x2 on that bit
+                    if (diag_as_d1 && o.n_table_bits == 1 && __builtin_popcount(t.reg_mask[1]) == 1) {
+                        t.kind = RG_D1_DIAG;
+                        t.ra = (unsigned char)__builtin_ctz(t.reg_mask[1]);
+                    }
+                } else {
+                    t.ra = (unsigned char)regbit_of[o.da];
+                    if (o.kind == RG_D2) t.rb = (unsigned char)regbit_of[o.db];
                 }
-            } else {
-                t.ra = (unsigned char)regbit_of[o.da];
-                if (o.kind == RG_D2) t.rb = (unsigned char)regbit_of[o.db];
+                QSV_CHECK(n_pool + (int)o.pool.size() <= RT_POOL, "internal: constant pool overflow");
+                t.mat_off = (unsigned short)n_pool;
+                for (double v : o.pool) P.pool[n_pool++] = v;
+                done[gi] = 1;
+                ++n_done;
             }
-            QSV_CHECK(n_pool + (int)o.pool.size() <= RT_POOL, "internal: constant pool overflow");
-            t.mat_off = (unsigned short)n_pool;
-            for (double v : o.pool) P.pool[n_pool++] = v;
-            done[gi] = 1;
-            ++n_done;
+            if (phase == 0) ps.udiag_end = (unsigned short)P.n_gates;
         }
         ps.gate_end = (unsigned short)P.n_gates;
+        slot_perms.push_back(take_perms());
     }
+    QSV_CHECK((int)slot_perms.size() == P.n_passes + 1, "internal: permutation slots");
 
+    // ---- address maps --------------------------------------------------------------------------------
+    auto to_global = [&](uint32_t v) {
+        uint64_t o = 0;
+        for (int p = 0; p < tb; ++p)
+            if (v >> p & 1) o |= 1ull << gpos[p];
+        return o;
+    };
+    auto smem_cols = [&](const AffineMap &mp, int pi, unsigned short *thr, unsigned short *reg, unsigned short &c) {
+        for (int k = 0; k < ntb; ++k) thr[k] = (unsigned short)swz(mp.col[lay_t[pi][k]], SW);
+        for (int k = 0; k < rb; ++k) reg[k] = (unsigned short)swz(mp.col[lay_r[pi][k]], SW);
+        c = (unsigned short)swz(mp.c, SW);
+    };
+    auto global_cols = [&](const AffineMap &mp, int pi, GlobalMap &g) {
+        for (int k = 0; k < ntb; ++k) g.thr[k] = to_global(mp.col[lay_t[pi][k]]);
+        for (int k = 0; k < rb; ++k) g.reg[k] = to_global(mp.col[lay_r[pi][k]]);
+        g.c = to_global(mp.c);
+    };
+    for (int pi = 0; pi < P.n_passes; ++pi) {
+        RegPass &ps = P.passes[pi];
+        smem_cols(AffineMap(), pi, ps.ld_thr, ps.ld_reg, ps.ld_c);
+        AffineMap after;  // permutations between this pass and the next: the value held for index e is stored at pi(e)
+        for (int gi : slot_perms[pi + 1]) after.then(ng[gi]);
+        if (pi + 1 < P.n_passes)
+            smem_cols(after, pi, ps.st_thr, ps.st_reg, ps.st_c);
+        else
+            global_cols(after, pi, P.gl_store);
+    }
+    {
+        // slot 0: the first pass wants S'[e] = S[pi^-1(e)]; every folded permutation is an involution, so the inverse is the
+        // same gates composed in reverse order
+        AffineMap inv;
+        for (auto it = slot_perms[0].rbegin(); it != slot_perms[0].rend(); ++it) inv.then(ng[*it]);
+        global_cols(inv, 0, P.gl_load);
+    }
     P.pool_used = n_pool;
+    P.prefetch = std::max(0, env_int_regs("QSV_REGS_PREFETCH", 0));
+}
+
+void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,
+                    int n_vecs) {
+    const int rb = regs_rb();
+    RegProgram P;
+    build_reg_program(sv.n, sv.dtype, sv.index_hi, gates, need, L, rb, P);
     sv.stat_launches += 1;
     sv.stat_sweeps += 1;
     if (sv.dtype == QSV_C128) {

@@ -1,0 +1,350 @@
+// Program format and per-thread arithmetic of the register-blocked fused tile kernel (tile_regs.cu).
+//
+// Everything here is __host__ __device__: the kernel and the test-only CPU emulator of the kernel
+// (tests/native/regs_emu.cu, never part of the product library) run the very same per-thread code on the very
+// same RegProgram, so the host-side planner / program builder can be checked against the oracle without a GPU.
+#pragma once
+
+#include <vector>
+
+#include "device_utils.cuh"
+
+namespace qsv {
+namespace rt {
+
+constexpr int TB = 12;       // tile bits: a CTA owns 2^12 amplitudes
+constexpr int RB_MAX = 4;    // register bits (QSV_REGS_RB=3: 8 amplitudes per thread, 512 threads per CTA)
+constexpr int NTB_MAX = 9;   // thread bits, at most
+constexpr int MAX_GATES = 48;
+constexpr int MAX_PASSES = 48;
+constexpr int POOL = 1280;   // doubles
+
+enum : unsigned char { RG_D1 = 1, RG_D1_REAL = 2, RG_D1_RX = 3, RG_D1_SWAP = 4, RG_D2 = 5, RG_DIAG = 6, RG_D1_DIAG = 7 };
+
+struct RegGate {
+    unsigned char kind;
+    unsigned char ra, rb;        // register-bit numbers (D1: ra; D2: ra = matrix MSB > rb; DIAG: rb = #table bits)
+    unsigned char ctrl_reg;      // controls among the register bits (mask over the slot number)
+    unsigned char reg_mask[2];   // DIAG: table bit b = parity(slot & reg_mask[b]) ^ parity(tid & thr_mask[b]) ^ ...
+    unsigned short ctrl_thr;     // controls among the thread bits (mask over threadIdx.x)
+    unsigned short thr_mask[2];
+    unsigned short mat_off;      // first double of this gate in the pool
+    unsigned short pad0;
+    uint64_t out_ctrl;           // controls outside the tile (global bit positions)
+    uint64_t out_mask[2];        // ... ^ parity(outside & out_mask[b]); table index = 2 * bit[0] + bit[1]
+};
+
+// Addresses are GF(2)-affine in (thread bits, register bits): offset = c ^ XOR_i tid_i * thr[i] ^ XOR_b slot_b * reg[b].
+// Shared-memory offsets are in elements and already XOR-swizzled (the swizzle is linear); index permutations
+// (PauliX, CNOT, SWAP between passes) are folded into the columns on the host, so they cost nothing here.
+struct RegPass {
+    unsigned short ld_thr[NTB_MAX], ld_reg[RB_MAX], ld_c;  // load at the start of the pass (passes > 0)
+    unsigned short st_thr[NTB_MAX], st_reg[RB_MAX], st_c;  // store at its end (all but the last pass)
+    unsigned short gate_begin;  // [gate_begin, udiag_end): thread-uniform diagonal gates, merged into one phase
+    unsigned short udiag_end;   // [udiag_end, gate_end): everything else, in order
+    unsigned short gate_end;
+    unsigned short pad0;
+};
+
+struct GlobalMap {  // element offsets inside the shard (tile bits only)
+    uint64_t thr[NTB_MAX], reg[RB_MAX], c;
+};
+
+struct RegProgram {
+    int n_passes;
+    int n_gates;
+    int pool_used;
+    int prefetch;                     // > 0: CTA b prefetches the tile of CTA b + prefetch into L2
+    uint64_t index_hi;                // value of the index bits above the local shard
+    Holes tile_holes;                 // all tile bits, ascending (expands blockIdx.x to the tile base)
+    GlobalMap gl_load, gl_store;      // first pass load / last pass store
+    RegPass passes[MAX_PASSES];
+    RegGate gates[MAX_GATES];
+    double pool[POOL];
+};
+
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; static constexpr int SW = 3; };
+template <> struct Cx<float> { using type = float2; static constexpr int SW = 4; };
+
+// XOR swizzle of the shared-memory tile: the low SW bits (one 128-byte line) are XORed with every higher
+// SW-bit field, so that lanes differing in any bits with distinct positions mod SW hit distinct banks.
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t e, int sw) {
+    const uint32_t m = (1u << sw) - 1u;
+    uint32_t r = e;
+    for (int s = sw; s < TB; s += sw) r ^= (e >> s) & m;
+    return r;
+}
+
+__host__ __device__ __forceinline__ int popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+__host__ __device__ __forceinline__ int popc64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+template <int NTB> __host__ __device__ __forceinline__ uint32_t thread_offset(const unsigned short *cols, unsigned short c, uint32_t tid) {
+    uint32_t r = c;
+#pragma unroll
+    for (int i = 0; i < NTB; ++i) r ^= (0u - ((tid >> i) & 1u)) & (uint32_t)cols[i];
+    return r;
+}
+template <int NTB> __host__ __device__ __forceinline__ uint64_t thread_offset64(const uint64_t *cols, uint64_t c, uint32_t tid) {
+    uint64_t r = c;
+#pragma unroll
+    for (int i = 0; i < NTB; ++i) r ^= (0ull - (uint64_t)((tid >> i) & 1u)) & cols[i];
+    return r;
+}
+// offset of slot j: XOR of the register-bit columns selected by the (compile-time) bits of j
+template <int RB, typename U> __host__ __device__ __forceinline__ U slot_offset(U base, const U (&col)[RB_MAX], int j) {
+    U o = base;
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+        if ((j >> b) & 1) o ^= col[b];
+    return o;
+}
+
+// ---- gates on register-resident amplitudes --------------------------------------------------------------
+// Controls among the register bits are a per-slot predicate.  (A variant with separate unpredicated code paths
+// plus a scheduling constraint that keeps controls out of the register bits was measured slower on B200:
+// 196 ms vs 166 ms for the config-2 circuit -- more code, 128 registers with spills.)
+template <typename T, int B, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d1(A (&x)[NS], int kind, const T *mp, uint32_t creg, int tb1) {
+    const A q0 = reinterpret_cast<const A *>(mp)[0], q1 = reinterpret_cast<const A *>(mp)[1];
+    const A q2 = reinterpret_cast<const A *>(mp)[2], q3 = reinterpret_cast<const A *>(mp)[3];
+    if (kind == RG_D1_DIAG) {
+        // one-bit phase table whose only register bit is B (RZ, PhaseShift, CRZ, IsingZZ / MultiRZ with the other qubits on
+        // thread bits): the slot's phase is known at compile time, the thread part of the parity swaps the two phases
+        const A p0 = tb1 ? q1 : q0, p1 = tb1 ? q0 : q1;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            if ((j & creg) == creg) {
+                const A a = x[j], b = x[j | (1 << B)];
+                x[j].x = p0.x * a.x - p0.y * a.y;
+                x[j].y = p0.x * a.y + p0.y * a.x;
+                x[j | (1 << B)].x = p1.x * b.x - p1.y * b.y;
+                x[j | (1 << B)].y = p1.x * b.y + p1.y * b.x;
+            }
+        }
+    } else if (kind == RG_D1_SWAP) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            if ((j & creg) == creg) {
+                const A t = x[j];
+                x[j] = x[j | (1 << B)];
+                x[j | (1 << B)] = t;
+            }
+        }
+    } else if (kind == RG_D1_REAL) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            if ((j & creg) == creg) {
+                const A a = x[j], b = x[j | (1 << B)];
+                x[j].x = q0.x * a.x + q1.x * b.x;
+                x[j].y = q0.x * a.y + q1.x * b.y;
+                x[j | (1 << B)].x = q2.x * a.x + q3.x * b.x;
+                x[j | (1 << B)].y = q2.x * a.y + q3.x * b.y;
+            }
+        }
+    } else if (kind == RG_D1_RX) {
+        // real diagonal, imaginary off-diagonal (RX and products of RX)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            if ((j & creg) == creg) {
+                const A a = x[j], b = x[j | (1 << B)];
+                x[j].x = q0.x * a.x - q1.y * b.y;
+                x[j].y = q0.x * a.y + q1.y * b.x;
+                x[j | (1 << B)].x = q3.x * b.x - q2.y * a.y;
+                x[j | (1 << B)].y = q3.x * b.y + q2.y * a.x;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            if ((j & creg) == creg) {
+                const A a = x[j], b = x[j | (1 << B)];
+                x[j].x = q0.x * a.x - q0.y * a.y + q1.x * b.x - q1.y * b.y;
+                x[j].y = q0.x * a.y + q0.y * a.x + q1.x * b.y + q1.y * b.x;
+                x[j | (1 << B)].x = q2.x * a.x - q2.y * a.y + q3.x * b.x - q3.y * b.y;
+                x[j | (1 << B)].y = q2.x * a.y + q2.y * a.x + q3.x * b.y + q3.y * b.x;
+            }
+        }
+    }
+}
+
+// 4x4 block on register bits BA > BB; matrix index = 2 * bit(BA) + bit(BB)
+template <typename T, int BA, int BB, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d2(A (&x)[NS], const T *mp, uint32_t creg) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
+        if ((j & creg) == creg) {
+            const int i0 = j, i1 = j | (1 << BB), i2 = j | (1 << BA), i3 = j | (1 << BA) | (1 << BB);
+            const A v0 = x[i0], v1 = x[i1], v2 = x[i2], v3 = x[i3];
+            A y[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const A *row = reinterpret_cast<const A *>(mp) + 4 * r;
+                const A c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[3];
+                y[r].x = c0.x * v0.x - c0.y * v0.y + c1.x * v1.x - c1.y * v1.y + c2.x * v2.x - c2.y * v2.y + c3.x * v3.x - c3.y * v3.y;
+                y[r].y = c0.x * v0.y + c0.y * v0.x + c1.x * v1.y + c1.y * v1.x + c2.x * v2.y + c2.y * v2.x + c3.x * v3.y + c3.y * v3.x;
+            }
+            x[i0] = y[0];
+            x[i1] = y[1];
+            x[i2] = y[2];
+            x[i3] = y[3];
+        }
+    }
+}
+
+// diagonal / parity gates: phase table of NB bits; table bit b of slot j = tb[b] ^ parity(j & q[b])
+template <typename T, int NB, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_diag(A (&x)[NS], const T *mp, bool thr_on, uint32_t creg, int tb0, int tb1,
+                                                  uint32_t q0, uint32_t q1) {
+    const A *tab = reinterpret_cast<const A *>(mp);
+    if (NB == 0) {
+        const A e = tab[0];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (thr_on && (j & creg) == creg) {
+                const A a = x[j];
+                x[j].x = e.x * a.x - e.y * a.y;
+                x[j].y = e.x * a.y + e.y * a.x;
+            }
+        }
+    } else if (NB == 1) {
+        // one table bit (RZ, CRZ, IsingZZ, MultiRZ ...): a per-thread pair of phases, slots pick by parity
+        const A e0 = tab[0], e1 = tab[1];
+        const A pa = tb1 ? e1 : e0, pb = tb1 ? e0 : e1;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (thr_on && (j & creg) == creg) {
+                const bool odd = popc32(j & q1) & 1;
+                const T pr = odd ? pb.x : pa.x, pi = odd ? pb.y : pa.y;
+                const A a = x[j];
+                x[j].x = pr * a.x - pi * a.y;
+                x[j].y = pr * a.y + pi * a.x;
+            }
+        }
+    } else {
+        const A e0 = tab[0], e1 = tab[1], e2 = tab[2], e3 = tab[3];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (thr_on && (j & creg) == creg) {
+                const int c0 = tb0 ^ (popc32(j & q0) & 1), c1 = tb1 ^ (popc32(j & q1) & 1);
+                const T pr = c0 ? (c1 ? e3.x : e2.x) : (c1 ? e1.x : e0.x);
+                const T pi = c0 ? (c1 ? e3.y : e2.y) : (c1 ? e1.y : e0.y);
+                const A a = x[j];
+                x[j].x = pr * a.x - pi * a.y;
+                x[j].y = pr * a.y + pi * a.x;
+            }
+        }
+    }
+}
+
+// All the arithmetic of one pass for one thread: x = the thread's 2^RB amplitudes, `outside` = index bits beyond the
+// tile, spool = gate constants in the kernel's precision.
+template <typename T, int RB, typename A>
+__host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const RegProgram &P, const RegPass &ps, uint32_t tid,
+                                                      uint64_t outside, const T *spool) {
+    constexpr int NS = 1 << RB;
+    // Thread-uniform diagonal gates (no target or control on a register bit) commute with every other gate of the pass:
+    // their phases are multiplied per thread and applied to the 2^RB amplitudes once.
+    if (ps.udiag_end > ps.gate_begin) {
+        T pr = (T)1, pi = (T)0;
+        bool any = false;
+        for (int gi = ps.gate_begin; gi < ps.udiag_end; ++gi) {
+            const RegGate &g = P.gates[gi];
+            if ((outside & g.out_ctrl) != g.out_ctrl) continue;
+            if ((tid & g.ctrl_thr) != g.ctrl_thr) continue;
+            const int tb0 = (popc32(tid & g.thr_mask[0]) ^ popc64(outside & g.out_mask[0])) & 1;
+            const int tb1 = (popc32(tid & g.thr_mask[1]) ^ popc64(outside & g.out_mask[1])) & 1;
+            const A e = reinterpret_cast<const A *>(spool + g.mat_off)[2 * tb0 + tb1];
+            const T nr = pr * e.x - pi * e.y;
+            pi = pr * e.y + pi * e.x;
+            pr = nr;
+            any = true;
+        }
+        if (any) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const A a = x[j];
+                x[j].x = pr * a.x - pi * a.y;
+                x[j].y = pr * a.y + pi * a.x;
+            }
+        }
+    }
+    for (int gi = ps.udiag_end; gi < ps.gate_end; ++gi) {
+        const RegGate &g = P.gates[gi];
+        if ((outside & g.out_ctrl) != g.out_ctrl) continue;  // CTA-uniform
+        const bool thr_on = (tid & g.ctrl_thr) == g.ctrl_thr;
+        const T *mp = spool + g.mat_off;
+        const uint32_t creg = g.ctrl_reg;
+        if (g.kind == RG_DIAG) {
+            const int nb = g.rb;  // table bits in use
+            const int tb0 = (popc32(tid & g.thr_mask[0]) ^ popc64(outside & g.out_mask[0])) & 1;
+            const int tb1 = (popc32(tid & g.thr_mask[1]) ^ popc64(outside & g.out_mask[1])) & 1;
+            const uint32_t q0 = g.reg_mask[0], q1 = g.reg_mask[1];
+            if (nb == 0)
+                reg_diag<T, 0, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+            else if (nb == 1)
+                reg_diag<T, 1, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+            else
+                reg_diag<T, 2, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
+        } else if (g.kind == RG_D2) {
+            if (thr_on) {
+                const int pair = g.ra * 4 + g.rb;
+                if (pair == 1 * 4 + 0) {
+                    reg_d2<T, 1, 0, NS>(x, mp, creg);
+                } else if (pair == 2 * 4 + 0) {
+                    reg_d2<T, 2, 0, NS>(x, mp, creg);
+                } else if (pair == 2 * 4 + 1) {
+                    reg_d2<T, 2, 1, NS>(x, mp, creg);
+                } else if constexpr (RB > 3) {
+                    if (pair == 3 * 4 + 0)
+                        reg_d2<T, 3, 0, NS>(x, mp, creg);
+                    else if (pair == 3 * 4 + 1)
+                        reg_d2<T, 3, 1, NS>(x, mp, creg);
+                    else
+                        reg_d2<T, 3, 2, NS>(x, mp, creg);
+                }
+            }
+        } else {
+            if (thr_on) {
+                int tb1 = 0;
+                if (g.kind == RG_D1_DIAG) tb1 = (popc32(tid & g.thr_mask[1]) ^ popc64(outside & g.out_mask[1])) & 1;
+                if (g.ra == 0) {
+                    reg_d1<T, 0, NS>(x, g.kind, mp, creg, tb1);
+                } else if (g.ra == 1) {
+                    reg_d1<T, 1, NS>(x, g.kind, mp, creg, tb1);
+                } else if (g.ra == 2) {
+                    reg_d1<T, 2, NS>(x, g.kind, mp, creg, tb1);
+                } else if constexpr (RB > 3) {
+                    reg_d1<T, 3, NS>(x, g.kind, mp, creg, tb1);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace rt
+
+// Host-side program construction (tile_regs.cu); exported for the test-only emulator.
+struct LoweredGate;
+void build_reg_program(int n_local, int dtype, uint64_t index_hi, const std::vector<const LoweredGate *> &gates,
+                       uint64_t need, int L, int rb, rt::RegProgram &P);
+
+}  // namespace qsv

@@ -1,0 +1,167 @@
+// TEST-ONLY CPU emulator of the register-blocked fused tile kernel (csrc/tile_regs.cu).
+//
+// It is built into tests/native/_build/libregs_emu.so by tests/native/build_emu.py, is never linked into or loaded by
+// the product (pennylane_lightning_gpu_b200/), and exists so that the HOST side of the fused executor -- gate merging,
+// DAG sweep packing, pass scheduling, folded index permutations, address maps, program encoding -- can be checked
+// against the NumPy oracle on a machine without a GPU.  The per-thread arithmetic is the kernel's own
+// (__host__ __device__ code of csrc/tile_regs_core.cuh); only the thread/CTA loops and the memories are emulated.
+#include <cstdio>
+#include <vector>
+
+#include "../../pennylane_lightning_gpu_b200/csrc/qsv_internal.h"
+#include "../../pennylane_lightning_gpu_b200/csrc/tile_regs_core.cuh"
+
+using namespace qsv;
+using namespace qsv::rt;
+
+namespace {
+
+// plain reference application of one lowered gate (lone gates go to the one-sweep kernels on the GPU)
+template <typename A> void apply_lowered_host(std::vector<A> &psi, int n, const LoweredGate &g) {
+    using T = decltype(A().x);
+    const uint64_t N = 1ull << n;
+    auto cmul = [](cplx a, A b) { return cplx(a.real() * b.x - a.imag() * b.y, a.real() * b.y + a.imag() * b.x); };
+    if (g.kind == LoweredGate::DIAG || g.kind == LoweredGate::PARITY) {
+        for (uint64_t i = 0; i < N; ++i) {
+            if ((i & g.ctrl_mask) != g.ctrl_mask) continue;
+            int t = 0;
+            if (g.kind == LoweredGate::PARITY) {
+                t = __builtin_popcountll(i & g.zmask) & 1;
+            } else {
+                for (int b = 0; b < g.k; ++b) t = (t << 1) | (int)((i >> g.tgt_bits[b]) & 1);
+            }
+            const cplx r = cmul(g.mat[t], psi[i]);
+            psi[i].x = (T)r.real();
+            psi[i].y = (T)r.imag();
+        }
+    } else if (g.kind == LoweredGate::DENSE) {
+        Holes h = make_holes(g.holes.data(), (int)g.holes.size(), 0);
+        const uint64_t groups = N >> g.holes.size();
+        const int d = 1 << g.k;
+        std::vector<cplx> in(d), out(d);
+        for (uint64_t o = 0; o < groups; ++o) {
+            const uint64_t base = expand_index(o, h) | g.ctrl_mask;
+            for (int a = 0; a < d; ++a) in[a] = cplx(psi[base + g.offs[a]].x, psi[base + g.offs[a]].y);
+            for (int r = 0; r < d; ++r) {
+                cplx s = 0;
+                for (int c = 0; c < d; ++c) s += g.mat[r * d + c] * in[c];
+                psi[base + g.offs[r]].x = (T)s.real();
+                psi[base + g.offs[r]].y = (T)s.imag();
+            }
+        }
+    }
+}
+
+template <typename T, int RB> void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegProgram &P) {
+    using A = typename Cx<T>::type;
+    constexpr int NS = 1 << RB, NT = 1 << (TB - RB), NTB = TB - RB;
+    std::vector<A> smem(1 << TB);
+    std::vector<T> spool(POOL);
+    for (int i = 0; i < P.pool_used; ++i) spool[i] = (T)P.pool[i];
+    std::vector<A> xs((size_t)NT * NS);
+    const uint64_t tiles = 1ull << (n - TB);
+    for (uint64_t blk = 0; blk < tiles; ++blk) {
+        const uint64_t base = expand_index(blk, P.tile_holes);
+        const uint64_t outside = base | P.index_hi;
+        for (int p = 0; p < P.n_passes; ++p) {
+            const RegPass &ps = P.passes[p];
+            const bool first = p == 0, last = p == P.n_passes - 1;
+            for (uint32_t tid = 0; tid < (uint32_t)NT; ++tid) {
+                A *x = &xs[(size_t)tid * NS];
+                if (first) {
+                    const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
+                    for (int j = 0; j < NS; ++j) x[j] = psi[slot_offset<RB>(gt, P.gl_load.reg, j)];
+                } else {
+                    const uint32_t st = thread_offset<NTB>(ps.ld_thr, ps.ld_c, tid);
+                    uint32_t sr[RB_MAX] = {0, 0, 0, 0};
+                    for (int b = 0; b < RB; ++b) sr[b] = ps.ld_reg[b];
+                    for (int j = 0; j < NS; ++j) x[j] = smem[slot_offset<RB>(st, sr, j)];
+                }
+            }
+            for (uint32_t tid = 0; tid < (uint32_t)NT; ++tid) {
+                A(&x)[NS] = *reinterpret_cast<A(*)[NS]>(&xs[(size_t)tid * NS]);
+                pass_compute<T, RB>(x, P, ps, tid, outside, spool.data());
+                if (last) {
+                    const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
+                    for (int j = 0; j < NS; ++j) psi[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
+                } else {
+                    const uint32_t st = thread_offset<NTB>(ps.st_thr, ps.st_c, tid);
+                    uint32_t sr[RB_MAX] = {0, 0, 0, 0};
+                    for (int b = 0; b < RB; ++b) sr[b] = ps.st_reg[b];
+                    for (int j = 0; j < NS; ++j) smem[slot_offset<RB>(st, sr, j)] = x[j];
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+void run_all(std::vector<typename Cx<T>::type> &psi, int n, int dtype, int rb, int L, bool dag, const std::vector<LoweredGate> &merged,
+             int64_t *stats) {
+    const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, L, dag, 48, 512);
+    std::vector<const LoweredGate *> cur;
+    static RegProgram P;
+    for (const SweepPlan &sw : plan) {
+        stats[0] += 1;
+        if (!sw.fused) {
+            apply_lowered_host(psi, n, merged[sw.gates[0]]);
+            stats[4] += 1;
+            continue;
+        }
+        cur.clear();
+        for (int i : sw.gates) cur.push_back(&merged[i]);
+        build_reg_program(n, dtype, 0, cur, sw.need, L, rb, P);
+        stats[1] += P.n_passes;
+        stats[2] += (int64_t)cur.size() - P.n_gates;  // gates folded into pass boundaries
+        for (int p = 0; p < P.n_passes; ++p) stats[3] += P.passes[p].udiag_end - P.passes[p].gate_begin;
+        if (rb == 4)
+            emulate_program<T, 4>(psi, n, P);
+        else
+            emulate_program<T, 3>(psi, n, P);
+    }
+}
+
+}  // namespace
+
+// ops = a qsv_ops handle of libqsv_b200.so; state = 2^n interleaved (re, im) doubles, updated in place (complex64 runs
+// the float kernel code on a float copy).  stats[5] = {sweeps, passes, folded permutation gates, merged diagonal gates,
+// lone gates}.  Returns 0 on success.
+extern "C" int regs_emu_apply_ops(const void *ops_handle, int n, int dtype, int rb, int low_bits, int dag, double *state,
+                                  int64_t *stats) {
+    try {
+        const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
+        std::vector<LoweredGate> gates;
+        for (const auto &op : ops->ops) {
+            if (op.name == "Identity") continue;
+            if (find_gate(op.name) != nullptr)
+                gates.push_back(lower_named(n, op.name, op.wires, op.params, op.inverse));
+            else
+                gates.push_back(lower_matrix(n, op.matrix.data(), {}, op.wires, op.inverse));
+        }
+        const std::vector<LoweredGate> merged = prepare_gates_regs(gates);
+        for (int i = 0; i < 5; ++i) stats[i] = 0;
+        const uint64_t N = 1ull << n;
+        const int L = low_bits > 0 ? low_bits : 4;
+        if (dtype == QSV_C128) {
+            std::vector<double2> psi(N);
+            for (uint64_t i = 0; i < N; ++i) psi[i] = make_double2(state[2 * i], state[2 * i + 1]);
+            run_all<double>(psi, n, dtype, rb, L, dag != 0, merged, stats);
+            for (uint64_t i = 0; i < N; ++i) {
+                state[2 * i] = psi[i].x;
+                state[2 * i + 1] = psi[i].y;
+            }
+        } else {
+            std::vector<float2> psi(N);
+            for (uint64_t i = 0; i < N; ++i) psi[i] = make_float2((float)state[2 * i], (float)state[2 * i + 1]);
+            run_all<float>(psi, n, dtype, rb, L, dag != 0, merged, stats);
+            for (uint64_t i = 0; i < N; ++i) {
+                state[2 * i] = psi[i].x;
+                state[2 * i + 1] = psi[i].y;
+            }
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "regs_emu: %s\n", e.what());
+        return 1;
+    }
+}

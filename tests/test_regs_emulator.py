@@ -1,0 +1,147 @@
+"""CPU-only check of the HOST side of the fused executor against the oracle: gate merging, DAG sweep packing, pass
+scheduling, folded index permutations (PauliX / CNOT / SWAP at pass boundaries), merged thread-uniform diagonal
+gates, affine address maps and program encoding.  tests/native/regs_emu.cu emulates the thread / CTA structure of
+k_tile_regs and runs the kernel's own per-thread code (csrc/tile_regs_core.cuh) on the very program the GPU would get.
+The GPU execution of the same programs is covered by the -m gpu parity tests."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as orc
+from pennylane_lightning_gpu_b200 import workloads
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(HERE, "native", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    lib.regs_emu_apply_ops.restype = C.c_int
+    lib.regs_emu_apply_ops.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    return lib
+
+
+def run_emulated(emu, ops, psi0, dtype=np.complex128, rb=4, low=0, dag=True):
+    import pennylane_lightning_gpu_b200 as q
+
+    n = int(np.log2(psi0.size))
+    rec = q.Ops(ops)
+    buf = np.ascontiguousarray(psi0.astype(np.complex128)).view(np.float64).copy()
+    stats = (C.c_int64 * 5)()
+    rc = emu.regs_emu_apply_ops(rec._h, n, 1 if dtype == np.complex128 else 0, rb, low, int(dag),
+                                buf.ctypes.data_as(C.POINTER(C.c_double)), stats)
+    assert rc == 0
+    names = ("sweeps", "passes", "folded", "merged_diag", "lone")
+    return buf.view(np.complex128), dict(zip(names, list(stats)))
+
+
+def rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return v / np.linalg.norm(v)
+
+
+def dtype_code_ok():
+    import pennylane_lightning_gpu_b200._cabi as cabi
+
+    return cabi
+
+
+def random_mixed_circuit(n, n_gates, seed):
+    rng = np.random.default_rng(seed)
+    one = ["RX", "RY", "RZ", "Hadamard", "PauliX", "PauliY", "PauliZ", "S", "T", "PhaseShift", "Rot"]
+    two = ["CNOT", "CZ", "SWAP", "CY", "CRX", "CRY", "CRZ", "IsingXX", "IsingYY", "IsingZZ", "ControlledPhaseShift",
+           "SingleExcitation", "SingleExcitationPlus", "CRot"]
+    npar = {"RX": 1, "RY": 1, "RZ": 1, "PhaseShift": 1, "Rot": 3, "CRX": 1, "CRY": 1, "CRZ": 1, "IsingXX": 1, "IsingYY": 1,
+            "IsingZZ": 1, "ControlledPhaseShift": 1, "SingleExcitation": 1, "SingleExcitationPlus": 1, "CRot": 3,
+            "MultiRZ": 1, "DoubleExcitation": 1}
+    ops = []
+    for _ in range(n_gates):
+        r = rng.random()
+        if r < 0.40:
+            nm, k = one[rng.integers(len(one))], 1
+        elif r < 0.80:
+            nm, k = two[rng.integers(len(two))], 2
+        elif r < 0.86:
+            nm, k = ["Toffoli", "CSWAP", "MultiRZ"][rng.integers(3)], 3
+        elif r < 0.93:
+            w = [int(x) for x in rng.choice(n, 1 + int(rng.integers(2)), replace=False)]
+            ops.append({"name": "QubitUnitary", "wires": w, "params": [],
+                        "matrix": workloads.haar_unitary(rng, 1 << len(w))})
+            continue
+        else:
+            nm, k = "DoubleExcitation", 4
+        w = [int(x) for x in rng.choice(n, k, replace=False)]
+        ops.append({"name": nm, "wires": w, "params": [float(x) for x in rng.uniform(-3, 3, npar.get(nm, 0))],
+                    "adjoint": bool(rng.random() < 0.2)})
+    return ops
+
+
+def code_of(dtype):
+    return dtype
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (13, 2), (14, 3)])
+@pytest.mark.parametrize("rb", [4, 3])
+def test_mixed_circuits_match_oracle(emu, n, seed, rb):
+    ops = random_mixed_circuit(n, 150, seed)
+    psi0 = rand_state(n, 100 + seed)
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0, rb=rb)
+    assert np.max(np.abs(got - want)) < 1e-12, st
+    assert st["sweeps"] >= 1 and st["passes"] >= st["sweeps"] - st["lone"]
+
+
+@pytest.mark.parametrize("env", [{}, {"QSV_REGS_FOLD": "0"}, {"QSV_REGS_UDIAG": "0"}, {"QSV_REGS_DAG": "0"},
+                                 {"QSV_REGS_FOLD": "0", "QSV_REGS_UDIAG": "0"}, {"QSV_MERGE_1Q": "0"}])
+def test_feature_switches(emu, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 13
+    ops = random_mixed_circuit(n, 120, 7)
+    psi0 = rand_state(n, 8)
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0, dag=env.get("QSV_REGS_DAG", "1") == "1")
+    assert np.max(np.abs(got - want)) < 1e-12, (env, st)
+    if env.get("QSV_REGS_FOLD") == "0":
+        assert st["folded"] == 0
+    if env.get("QSV_REGS_UDIAG") == "0":
+        assert st["merged_diag"] == 0
+
+
+def test_permutation_only_and_ladders(emu):
+    n = 12
+    psi0 = rand_state(n, 3)
+    # CNOT ladder + X + SWAP chain: everything folds into the load / store address maps, no arithmetic at all
+    ops = [{"name": "CNOT", "wires": [i, i + 1], "params": []} for i in range(n - 1)]
+    ops += [{"name": "PauliX", "wires": [3], "params": []}, {"name": "SWAP", "wires": [0, 11], "params": []},
+            {"name": "SWAP", "wires": [5, 6], "params": []}, {"name": "CNOT", "wires": [11, 0], "params": []}]
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0)
+    assert np.max(np.abs(got - want)) == 0.0
+    assert st["folded"] == len(ops) and st["sweeps"] == 1 and st["passes"] == 1
+    # hardware-efficient ansatz: rotations + ladder per layer
+    ops, _ = workloads.hardware_efficient_ansatz(n, layers=3, seed=11)
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert st["folded"] > 0
+
+
+@pytest.mark.parametrize("low", [3, 4, 6])
+def test_config2_style_circuit(emu, low):
+    n = 14
+    ops = workloads.random_gate_circuit(n, 200, 2024)
+    psi0 = rand_state(n, 5)
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0, low=low)
+    assert np.max(np.abs(got - want)) < 1e-12, st
+    got32, _ = run_emulated(emu, ops, psi0, dtype=np.complex64, low=low)
+    assert np.max(np.abs(got32 - want)) < 2e-5
