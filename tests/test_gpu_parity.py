@@ -584,6 +584,32 @@ def test_register_tile_kernel_stress(q, n, low, rb, dtype, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("env", [{}, {"QSV_REGS_FOLD": "0"}, {"QSV_REGS_UDIAG": "0", "QSV_REGS_DIAG1": "0"},
+                                 {"QSV_REGS_DAG": "0"}, {"QSV_REGS_PREFETCH": "3"}, {"QSV_REGS_RB": "3"}])
+def test_register_tile_feature_switches(q, env, dtype, monkeypatch):
+    """csrc/tile_regs.cu: index permutations folded into pass boundaries (PauliX / CNOT / SWAP), merged thread-uniform
+    diagonal gates, diagonal-as-2x2, DAG sweep packing and the L2 prefetch, each switched off in turn; CNOT ladders and
+    permutation-only stretches included (the host side of the same programs is checked on the CPU by
+    tests/test_regs_emulator.py)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 15
+    ops = [{"name": "CNOT", "wires": [i, i + 1], "params": []} for i in range(n - 1)]
+    ops += [{"name": "PauliX", "wires": [3], "params": []}, {"name": "SWAP", "wires": [0, n - 1], "params": []},
+            {"name": "CNOT", "wires": [n - 1, 0], "params": []}]
+    ops += workloads.random_gate_circuit(n, 150, 77)
+    ladder, _ = workloads.hardware_efficient_ansatz(n, layers=2, seed=3)
+    ops += ladder
+    ops += [{"name": "SWAP", "wires": [2, 9], "params": []}, {"name": "CNOT", "wires": [9, 2], "params": []},
+            {"name": "PauliX", "wires": [n - 1], "params": []}]
+    psi = random_state(n, 21)
+    want = orc.apply_ops(psi, ops)
+    sv = gpu_state(q, psi, dtype)
+    sv.apply_ops(q.Ops(ops), fuse=True)
+    assert_close(sv.d2h(), want, dtype, scale=20, what=f"env={env}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [11, 13, 17])
 def test_fused_pauli_word_expvals(q, n, dtype):
     """csrc/adjoint_kernels.cu (Pauli kind): many words per read of the state, incl. words whose X/Y letters do not fit one
