@@ -72,44 +72,54 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     __syncthreads();
 
     A x[NS];
-    for (int p = 0; p < P.n_passes; ++p) {
+    {
+        const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
+        uint64_t gr[RB_MAX];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) gr[b] = P.gl_load.reg[b];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
+    }
+    const int last = P.n_passes - 1;
+    for (int p = 0;; ++p) {
         const RegPass &ps = P.passes[p];
-        const bool first = p == 0, last = p == P.n_passes - 1;
-        if (first) {
-            const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
-            uint64_t gr[RB_MAX];
-#pragma unroll
-            for (int b = 0; b < RB; ++b) gr[b] = P.gl_load.reg[b];
-#pragma unroll
-            for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
-        } else {
-            const uint32_t st = thread_offset<NTB>(ps.ld_thr, ps.ld_c, tid);
-            uint32_t sr[RB_MAX];
-#pragma unroll
-            for (int b = 0; b < RB; ++b) sr[b] = ps.ld_reg[b];
-#pragma unroll
-            for (int j = 0; j < NS; ++j) x[j] = s[slot_offset<RB>(st, sr, j)];
-        }
-
         pass_compute<T, RB>(x, P, ps, tid, outside, spool);
-
-        if (last) {
-            const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
-            uint64_t gr[RB_MAX];
-#pragma unroll
-            for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
-#pragma unroll
-            for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
-        } else {
-            if (!first) __syncthreads();  // every thread has finished reading the previous layout
+        if (p == last) break;
+        // transpose through shared memory: store in this pass's layout (folded permutations included), load in the next one's
+        if (p > 0) __syncthreads();  // every thread has finished reading the previous layout
+        {
             const uint32_t st = thread_offset<NTB>(ps.st_thr, ps.st_c, tid);
             uint32_t sr[RB_MAX];
 #pragma unroll
             for (int b = 0; b < RB; ++b) sr[b] = ps.st_reg[b];
 #pragma unroll
             for (int j = 0; j < NS; ++j) s[slot_offset<RB>(st, sr, j)] = x[j];
-            __syncthreads();
         }
+        __syncthreads();
+        {
+            const RegPass &pn = P.passes[p + 1];
+            const uint32_t st = thread_offset<NTB>(pn.ld_thr, pn.ld_c, tid);
+            uint32_t sr[RB_MAX];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) sr[b] = pn.ld_reg[b];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) x[j] = s[slot_offset<RB>(st, sr, j)];
+        }
+    }
+    // A single-pass sweep has no barrier between its loads and its stores, and with a folded permutation a thread does
+    // not write where it read.
+    if (last == 0) __syncthreads();
+    {
+        // opaque copy of the thread index: otherwise the per-bit masks of the load addresses are kept (spilled) for the
+        // whole kernel just to be reused here
+        uint32_t tid_s = tid;
+        asm volatile("" : "+r"(tid_s));
+        const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
+        uint64_t gr[RB_MAX];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
     }
 }
 
