@@ -88,6 +88,29 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_lib_variant(name: str, extra_flags: list[str]) -> str:
+    """A/B build of the same library with extra nvcc flags (e.g. -DQSV_PLAIN_SMEM) into lib/variants/libqsv_<name>.so;
+    select it at run time with QSV_LIB_PATH.  The default library is left untouched."""
+    out_dir = os.path.join(LIBDIR, "variants")
+    obj_dir = os.path.join(OBJDIR, "variant_" + name)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libqsv_{name}.so")
+    nccl_inc, nccl_lib = _nccl_dirs()
+    sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    jobs, objs = [], []
+    for s in sources:
+        obj = os.path.join(obj_dir, s[:-3] + ".o")
+        objs.append(obj)
+        jobs.append([NVCC] + NVCC_FLAGS + list(extra_flags) + (["-I", nccl_inc] if nccl_inc else []) +
+                    ["-c", os.path.join(CSRC, s), "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        list(ex.map(_run, jobs))
+    link = ["-L", nccl_lib, "-l:libnccl.so.2", "-Xlinker", "-rpath=" + nccl_lib] if nccl_lib else ["-lnccl"]
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + link)
+    return out
+
+
 def pybind_module_path() -> str:
     return os.path.join(PKG, "lightning_gpu_qubit_ops" + sysconfig.get_config_var("EXT_SUFFIX"))
 

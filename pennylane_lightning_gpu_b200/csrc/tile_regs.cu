@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
     }
     const int last = P.n_passes - 1;
-    for (int p = 0;; ++p) {
+    for (int pv = 0;; ++pv) {
+        // the pass counter may be spilled under the 128-register cap; a broadcast from lane 0 tells the compiler that it is
+        // warp-uniform again, so that pass / gate descriptors and gate constants are fetched with uniform loads (LDCU) into
+        // uniform registers instead of per-thread LDC + vector registers
+        const int p = __shfl_sync(0xffffffffu, pv, 0);
         const RegPass &ps = P.passes[p];
         pass_compute<T, RB>(x, P, ps, tid, outside, spool);
         if (p == last) break;
@@ -603,6 +607,8 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         global_cols(inv, 0, P.gl_load);
     }
     P.pool_used = n_pool;
+    for (int i = 0; i < n_pool; ++i) P.poolf[i] = (float)P.pool[i];
+    P.uniform_consts = env_flag("QSV_REGS_UCONST", 1) ? 1 : 0;
     P.prefetch = std::max(0, env_int_regs("QSV_REGS_PREFETCH", 0));
 }
 

@@ -60,8 +60,27 @@ struct RegProgram {
     GlobalMap gl_load, gl_store;      // first pass load / last pass store
     RegPass passes[MAX_PASSES];
     RegGate gates[MAX_GATES];
-    double pool[POOL];
+    double pool[POOL];                // gate constants (complex128 kernels read them from here or from shared memory)
+    float poolf[POOL];                // the same in single precision for the complex64 kernels
+    int uniform_consts;               // != 0: uncontrolled dense gates read their matrix straight from this struct
+    int pad1;
 };
+
+template <typename T> __host__ __device__ __forceinline__ const T *const_pool(const RegProgram &P);
+// where the unpredicated dense paths read their matrix from: the kernel-parameter constant bank (default) or the
+// shared-memory copy (-DQSV_PLAIN_SMEM, an A/B build)
+template <typename T> __host__ __device__ __forceinline__ const T *plain_consts(const RegProgram &P, const T *spool);
+template <> __host__ __device__ __forceinline__ const double *const_pool<double>(const RegProgram &P) { return P.pool; }
+template <> __host__ __device__ __forceinline__ const float *const_pool<float>(const RegProgram &P) { return P.poolf; }
+template <typename T> __host__ __device__ __forceinline__ const T *plain_consts(const RegProgram &P, const T *spool) {
+#ifdef QSV_PLAIN_SMEM
+    (void)P;
+    return spool;
+#else
+    (void)spool;
+    return const_pool<T>(P);
+#endif
+}
 
 template <typename T> struct Cx;
 template <> struct Cx<double> { using type = double2; static constexpr int SW = 3; };
@@ -185,6 +204,66 @@ __host__ __device__ __forceinline__ void reg_d1(A (&x)[NS], int kind, const T *m
     }
 }
 
+// Uncontrolled dense gates: no predicates, and the matrix is read from the kernel-parameter constant bank with a
+// CTA-uniform index -- in convergent code the compiler keeps it in UNIFORM registers (LDCU) and feeds DFMA / FFMA from
+// there, so the constants cost neither vector registers nor shared-memory round trips.
+template <typename T, int B, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d1_plain(A (&x)[NS], int kind, const T *cp) {
+    const T q0x = cp[0], q0y = cp[1], q1x = cp[2], q1y = cp[3], q2x = cp[4], q2y = cp[5], q3x = cp[6], q3y = cp[7];
+    if (kind == RG_D1_REAL) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const A a = x[j], b = x[j | (1 << B)];
+            x[j].x = q0x * a.x + q1x * b.x;
+            x[j].y = q0x * a.y + q1x * b.y;
+            x[j | (1 << B)].x = q2x * a.x + q3x * b.x;
+            x[j | (1 << B)].y = q2x * a.y + q3x * b.y;
+        }
+    } else if (kind == RG_D1_RX) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const A a = x[j], b = x[j | (1 << B)];
+            x[j].x = q0x * a.x - q1y * b.y;
+            x[j].y = q0x * a.y + q1y * b.x;
+            x[j | (1 << B)].x = q3x * b.x - q2y * a.y;
+            x[j | (1 << B)].y = q3x * b.y + q2y * a.x;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const A a = x[j], b = x[j | (1 << B)];
+            x[j].x = q0x * a.x - q0y * a.y + q1x * b.x - q1y * b.y;
+            x[j].y = q0x * a.y + q0y * a.x + q1x * b.y + q1y * b.x;
+            x[j | (1 << B)].x = q2x * a.x - q2y * a.y + q3x * b.x - q3y * b.y;
+            x[j | (1 << B)].y = q2x * a.y + q2y * a.x + q3x * b.y + q3y * b.x;
+        }
+    }
+}
+
+template <typename T, int BA, int BB, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d2_plain(A (&x)[NS], const T *cp) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
+        const int i0 = j, i1 = j | (1 << BB), i2 = j | (1 << BA), i3 = j | (1 << BA) | (1 << BB);
+        const A v0 = x[i0], v1 = x[i1], v2 = x[i2], v3 = x[i3];
+        A y[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const T *row = cp + 8 * r;
+            y[r].x = row[0] * v0.x - row[1] * v0.y + row[2] * v1.x - row[3] * v1.y + row[4] * v2.x - row[5] * v2.y + row[6] * v3.x - row[7] * v3.y;
+            y[r].y = row[0] * v0.y + row[1] * v0.x + row[2] * v1.y + row[3] * v1.x + row[4] * v2.y + row[5] * v2.x + row[6] * v3.y + row[7] * v3.x;
+        }
+        x[i0] = y[0];
+        x[i1] = y[1];
+        x[i2] = y[2];
+        x[i3] = y[3];
+    }
+}
+
 // 4x4 block on register bits BA > BB; matrix index = 2 * bit(BA) + bit(BB)
 template <typename T, int BA, int BB, int NS, typename A>
 __host__ __device__ __forceinline__ void reg_d2(A (&x)[NS], const T *mp, uint32_t creg) {
@@ -293,6 +372,7 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
         const bool thr_on = (tid & g.ctrl_thr) == g.ctrl_thr;
         const T *mp = spool + g.mat_off;
         const uint32_t creg = g.ctrl_reg;
+        const bool plain = P.uniform_consts != 0 && g.ctrl_thr == 0 && creg == 0;  // CTA-uniform
         if (g.kind == RG_DIAG) {
             const int nb = g.rb;  // table bits in use
             const int tb0 = (popc32(tid & g.thr_mask[0]) ^ popc64(outside & g.out_mask[0])) & 1;
@@ -305,7 +385,24 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
             else
                 reg_diag<T, 2, NS>(x, mp, thr_on, creg, tb0, tb1, q0, q1);
         } else if (g.kind == RG_D2) {
-            if (thr_on) {
+            if (plain) {
+                const T *cp = plain_consts<T>(P, spool) + g.mat_off;
+                const int pair = g.ra * 4 + g.rb;
+                if (pair == 1 * 4 + 0) {
+                    reg_d2_plain<T, 1, 0, NS>(x, cp);
+                } else if (pair == 2 * 4 + 0) {
+                    reg_d2_plain<T, 2, 0, NS>(x, cp);
+                } else if (pair == 2 * 4 + 1) {
+                    reg_d2_plain<T, 2, 1, NS>(x, cp);
+                } else if constexpr (RB > 3) {
+                    if (pair == 3 * 4 + 0)
+                        reg_d2_plain<T, 3, 0, NS>(x, cp);
+                    else if (pair == 3 * 4 + 1)
+                        reg_d2_plain<T, 3, 1, NS>(x, cp);
+                    else
+                        reg_d2_plain<T, 3, 2, NS>(x, cp);
+                }
+            } else if (thr_on) {
                 const int pair = g.ra * 4 + g.rb;
                 if (pair == 1 * 4 + 0) {
                     reg_d2<T, 1, 0, NS>(x, mp, creg);
@@ -321,6 +418,17 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
                     else
                         reg_d2<T, 3, 2, NS>(x, mp, creg);
                 }
+            }
+        } else if (plain && g.kind != RG_D1_DIAG && g.kind != RG_D1_SWAP) {
+            const T *cp = plain_consts<T>(P, spool) + g.mat_off;
+            if (g.ra == 0) {
+                reg_d1_plain<T, 0, NS>(x, g.kind, cp);
+            } else if (g.ra == 1) {
+                reg_d1_plain<T, 1, NS>(x, g.kind, cp);
+            } else if (g.ra == 2) {
+                reg_d1_plain<T, 2, NS>(x, g.kind, cp);
+            } else if constexpr (RB > 3) {
+                reg_d1_plain<T, 3, NS>(x, g.kind, cp);
             }
         } else {
             if (thr_on) {
