@@ -591,6 +591,8 @@ def test_register_tile_feature_switches(q, env, dtype, monkeypatch):
     diagonal gates, diagonal-as-2x2, DAG sweep packing and the L2 prefetch, each switched off in turn; CNOT ladders and
     permutation-only stretches included (the host side of the same programs is checked on the CPU by
     tests/test_regs_emulator.py)."""
+    from pennylane_lightning_gpu_b200 import workloads
+
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     n = 15
