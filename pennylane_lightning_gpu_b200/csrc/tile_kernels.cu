@@ -492,23 +492,61 @@ bool as_plain_1q(const LoweredGate &g, int &bit, cplx m[4], bool &diag) {
     return false;
 }
 
+// an uncontrolled dense 4x4 on two bits (tgt_bits[0] = matrix MSB)
+bool as_plain_2q(const LoweredGate &g) {
+    return g.kind == LoweredGate::DENSE && g.k == 2 && g.ctrl_mask == 0 && g.tgt_bits.size() == 2 && g.holes.size() == 2;
+}
+
+// Host-side gate fusion ahead of the sweep packer (north_star item c, "dense k-qubit blocks" with k <= 2):
+//  * runs of uncontrolled single-qubit gates on the same qubit become one 2x2 (diagonal if all of them are);
+//  * an uncontrolled dense two-qubit gate absorbs the pending single-qubit blocks of its two qubits, every later
+//    single-qubit gate on them, and later dense two-qubit gates on the same pair, until another gate touches one of
+//    the two qubits.  A 4x4 block costs the same 16 FP64 operations per amplitude however many gates it absorbed.
+// QSV_MERGE_2Q=0 keeps two-qubit gates as they are.
 std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> &in) {
     struct Pending {
-        cplx m[4];
-        bool diag;
+        int k = 1;            // qubits
+        int hi = -1, lo = -1; // k = 1: bit = lo;  k = 2: matrix index = 2 * bit(hi) + bit(lo)
+        cplx m[16];
+        bool diag = false;
+        bool live = true;
     };
-    std::map<int, Pending> pending;
+    const bool merge2 = env_int("QSV_MERGE_2Q", 1) != 0;
+    std::vector<Pending> pool;
+    std::map<int, int> pending;  // bit -> index into pool
     std::vector<LoweredGate> out;
     auto flush = [&](int bit) {
         auto it = pending.find(bit);
         if (it == pending.end()) return;
-        const Pending &p = it->second;
-        if (p.diag)
-            out.push_back(make_diag_gate({bit}, 0, {p.m[0], p.m[3]}));
-        else
-            out.push_back(make_dense_gate({bit}, 0, {p.m[0], p.m[1], p.m[2], p.m[3]}));
-        pending.erase(it);
+        Pending &p = pool[it->second];
+        if (p.k == 1) {
+            if (p.diag)
+                out.push_back(make_diag_gate({p.lo}, 0, {p.m[0], p.m[3]}));
+            else
+                out.push_back(make_dense_gate({p.lo}, 0, {p.m[0], p.m[1], p.m[2], p.m[3]}));
+            pending.erase(it);
+        } else {
+            out.push_back(make_dense_gate({p.hi, p.lo}, 0, std::vector<cplx>(p.m, p.m + 16)));
+            const int hi = p.hi, lo = p.lo;
+            pending.erase(hi);
+            pending.erase(lo);
+        }
+        p.live = false;
     };
+    // 4x4 = a (x) b in the (hi, lo) basis
+    auto kron = [](const cplx a[4], const cplx b[4], cplx r[16]) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) r[i * 4 + j] = a[(i >> 1) * 2 + (j >> 1)] * b[(i & 1) * 2 + (j & 1)];
+    };
+    auto matmul4 = [](const cplx a[16], const cplx b[16], cplx r[16]) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                cplx s = 0.0;
+                for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+                r[i * 4 + j] = s;
+            }
+    };
+    const cplx id2[4] = {1.0, 0.0, 0.0, 1.0};
     for (const LoweredGate &g : in) {
         if (g.kind == LoweredGate::NOP) continue;
         int bit;
@@ -518,16 +556,72 @@ std::vector<LoweredGate> merge_single_qubit_runs(const std::vector<LoweredGate> 
             auto it = pending.find(bit);
             if (it == pending.end()) {
                 Pending p;
+                p.k = 1;
+                p.lo = bit;
                 for (int i = 0; i < 4; ++i) p.m[i] = m[i];
                 p.diag = diag;
-                pending[bit] = p;
+                pool.push_back(p);
+                pending[bit] = (int)pool.size() - 1;
             } else {
-                Pending &p = it->second;  // new = m * old
-                cplx r[4] = {m[0] * p.m[0] + m[1] * p.m[2], m[0] * p.m[1] + m[1] * p.m[3],
-                             m[2] * p.m[0] + m[3] * p.m[2], m[2] * p.m[1] + m[3] * p.m[3]};
-                for (int i = 0; i < 4; ++i) p.m[i] = r[i];
-                p.diag = p.diag && diag;
+                Pending &p = pool[it->second];
+                if (p.k == 1) {  // new = m * old
+                    cplx r[4] = {m[0] * p.m[0] + m[1] * p.m[2], m[0] * p.m[1] + m[1] * p.m[3],
+                                 m[2] * p.m[0] + m[3] * p.m[2], m[2] * p.m[1] + m[3] * p.m[3]};
+                    for (int i = 0; i < 4; ++i) p.m[i] = r[i];
+                    p.diag = p.diag && diag;
+                } else {  // new = (m on this bit) * old
+                    cplx full[16], r[16];
+                    if (bit == p.hi)
+                        kron(m, id2, full);
+                    else
+                        kron(id2, m, full);
+                    matmul4(full, p.m, r);
+                    for (int i = 0; i < 16; ++i) p.m[i] = r[i];
+                }
             }
+            continue;
+        }
+        if (merge2 && as_plain_2q(g)) {
+            const int hi = g.tgt_bits[0], lo = g.tgt_bits[1];
+            auto ih = pending.find(hi), il = pending.find(lo);
+            if (ih != pending.end() && il != pending.end() && ih->second == il->second && pool[ih->second].k == 2) {
+                // same pair: new = G * old, G expressed in the pending block's bit order
+                Pending &p = pool[ih->second];
+                cplx gm[16], r[16];
+                const bool same_order = p.hi == hi;
+                for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j < 4; ++j) {
+                        const int si = same_order ? i : ((i & 1) << 1) | (i >> 1), sj = same_order ? j : ((j & 1) << 1) | (j >> 1);
+                        gm[i * 4 + j] = g.mat[si * 4 + sj];
+                    }
+                matmul4(gm, p.m, r);
+                for (int i = 0; i < 16; ++i) p.m[i] = r[i];
+                continue;
+            }
+            // blocks on a different pair end here; single-qubit blocks are absorbed: new = G * (P_hi (x) P_lo)
+            for (int b : {hi, lo}) {
+                auto it = pending.find(b);
+                if (it != pending.end() && pool[it->second].k == 2) flush(b);
+            }
+            cplx ph[4] = {1.0, 0.0, 0.0, 1.0}, pl[4] = {1.0, 0.0, 0.0, 1.0};
+            for (int w = 0; w < 2; ++w) {
+                auto it = pending.find(w == 0 ? hi : lo);
+                if (it == pending.end()) continue;
+                Pending &q1 = pool[it->second];
+                for (int i = 0; i < 4; ++i) (w == 0 ? ph : pl)[i] = q1.m[i];
+                q1.live = false;
+                pending.erase(it);
+            }
+            Pending p;
+            p.k = 2;
+            p.hi = hi;
+            p.lo = lo;
+            cplx pre[16], gm[16];
+            kron(ph, pl, pre);
+            for (int i = 0; i < 16; ++i) gm[i] = g.mat[i];
+            matmul4(gm, pre, p.m);
+            pool.push_back(p);
+            pending[hi] = pending[lo] = (int)pool.size() - 1;
             continue;
         }
         const uint64_t bits = all_bits(g);

@@ -145,3 +145,41 @@ def test_config2_style_circuit(emu, low):
     assert np.max(np.abs(got - want)) < 1e-12, st
     got32, _ = run_emulated(emu, ops, psi0, dtype=np.complex64, low=low)
     assert np.max(np.abs(got32 - want)) < 2e-5
+
+
+@pytest.mark.parametrize("merge2q", ["1", "0"])
+def test_two_qubit_blocks_absorb_neighbours(emu, merge2q, monkeypatch):
+    """merge_single_qubit_runs: a dense two-qubit gate absorbs the pending single-qubit blocks of its qubits, later
+    single-qubit gates on them and later two-qubit gates on the same pair in either wire order."""
+    import pennylane_lightning_gpu_b200 as q
+
+    monkeypatch.setenv("QSV_MERGE_2Q", merge2q)
+    n = 12
+    rng = np.random.default_rng(17)
+    ops = []
+    for rep in range(40):
+        a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+        for _ in range(int(rng.integers(0, 3))):
+            ops.append({"name": ["RX", "RY", "RZ", "Hadamard", "T"][rng.integers(5)], "wires": [[a, b][rng.integers(2)]],
+                        "params": [float(rng.uniform(-3, 3))]})
+            if ops[-1]["name"] in ("Hadamard", "T"):
+                ops[-1]["params"] = []
+        ops.append({"name": "QubitUnitary", "wires": [a, b], "params": [], "matrix": workloads.haar_unitary(rng, 4)})
+        if rep % 3 == 0:
+            ops.append({"name": "QubitUnitary", "wires": [b, a], "params": [], "matrix": workloads.haar_unitary(rng, 4),
+                        "adjoint": True})
+        if rep % 4 == 0:
+            ops.append({"name": "IsingXX", "wires": [a, b], "params": [0.4]})
+        for _ in range(int(rng.integers(0, 3))):
+            ops.append({"name": "RY", "wires": [[a, b][rng.integers(2)]], "params": [float(rng.uniform(-3, 3))]})
+        if rep % 5 == 0:
+            ops.append({"name": "CNOT", "wires": [a, b], "params": []})
+    psi0 = rand_state(n, 4)
+    want = orc.apply_ops(psi0.copy(), ops)
+    got, st = run_emulated(emu, ops, psi0)
+    assert np.max(np.abs(got - want)) < 1e-12, st
+    plan = q.Ops(ops).plan_sweeps(n)
+    assert plan["order_valid"]
+    if merge2q == "1":
+        monkeypatch.setenv("QSV_MERGE_2Q", "0")
+        assert plan["gates_after_merge"] < q.Ops(ops).plan_sweeps(n)["gates_after_merge"]
