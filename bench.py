@@ -268,13 +268,14 @@ def run_ours(args):
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     sweep_bytes = 2 * amp_bytes * (1 << n_local)
     regs_kernel = os.environ.get("QSV_TILE_KERNEL", "1") == "1" and n_local >= 12
-    fused_kernel = ("k_tile_regs (register-blocked fused tile kernel: 16 amplitudes per thread, list-scheduled passes, "
-                    "swizzled shared-memory transposes)") if regs_kernel else \
+    fused_kernel = ("k_tile_regs (register-blocked fused tile kernel: 16 amplitudes per thread, DAG-packed sweeps, "
+                    "list-scheduled passes, swizzled shared-memory transposes with PauliX/CNOT/SWAP folded into the "
+                    "address maps)") if regs_kernel else \
         "k_tile_sweep (first-generation fused shared-memory tile kernel, TMA-staged)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": sweep_bytes if fused else None,
                 "traffic_source": ("ncu dram__bytes_read+write per fused sweep launch = 34.3 GB = 2*B*N at 30q c128 "
-                                   "(profiles/r1_ncu_summary.txt)") if fused else
+                                   "(profiles/r1_ncu_regs_summary.txt)") if fused else
                                   "ncu: 34.4 GB per full-state gate launch (profiles/r1_ncu_summary.txt); controlled gates move less",
                 "kernel": fused_kernel if fused else "k_apply_dense / k_apply_diag (one sweep per gate)",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
@@ -282,9 +283,10 @@ def run_ours(args):
     if fused:
         roofline["hbm_actual_gbs"] = sweep_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
-        roofline["note"] = ("a fused sweep applies ~14-17 gates per read+write of the state, so it is bound by FP64 issue "
-                            "(64 DFMA/clk/SM) and instruction overhead rather than by HBM: see DESIGN.md 4.2; "
-                            "detail.unfused_gate_by_gate and detail.single_gate_sweeps are the HBM-bound one-sweep-per-gate kernels") \
+        roofline["note"] = (f"a fused sweep applies ~{len(ops) * args.steps / max(launches, 1):.0f} gates per read+write of the "
+                            "state, so it is bound by FP64 issue (64 DFMA/clk/SM) and instruction overhead rather than by HBM: "
+                            "see DESIGN.md 4.2; detail.unfused_gate_by_gate and detail.single_gate_sweeps are the HBM-bound "
+                            "one-sweep-per-gate kernels") \
             if regs_kernel else \
             ("fused sweeps are shared-memory-bandwidth-bound (1024 clk per gate per 64 KiB tile), not "
              "HBM-bound: see DESIGN.md 4.2; --fuse 0 gives the HBM-bound one-sweep-per-gate kernels")

@@ -360,9 +360,10 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
         if (any) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                const A a = x[j];
-                x[j].x = pr * a.x - pi * a.y;
-                x[j].y = pr * a.y + pi * a.x;
+                // two temporaries, results written over their own inputs (no register moves at the merge point)
+                const T t = pi * x[j].y, u = pi * x[j].x;
+                x[j].x = pr * x[j].x - t;
+                x[j].y = pr * x[j].y + u;
             }
         }
     }
