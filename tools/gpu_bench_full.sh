@@ -34,6 +34,6 @@ echo "== ncu launch list" >> $OUT
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r1_launches_fused.csv $B --steps 2 > /dev/null 2>&1
 tail -2 gpurun_out/r1_launches_fused.csv | cut -c1-300 >> $OUT
 echo "== ncu regs full" >> $OUT
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_regs -s 20 -c 2 -o gpurun_out/r1_regs -f $B --steps 1 > gpurun_out/ncu_regs.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_regs -s 12 -c 2 -o gpurun_out/r1_regs -f $B --steps 1 > gpurun_out/ncu_regs.log 2>&1
 tail -2 gpurun_out/ncu_regs.log | cut -c1-200 >> $OUT
 cat $OUT
