@@ -88,6 +88,7 @@ int qsv_device_reset(void) {
     QSV_CUDA(cudaGetDeviceCount(&count));
     for (int d = 0; d < count; ++d) {
         QSV_CUDA(cudaSetDevice(d));
+        ws_trim(d);  // cached workspace blocks die with the context
         QSV_CUDA(cudaDeviceReset());
     }
     QSV_API_END

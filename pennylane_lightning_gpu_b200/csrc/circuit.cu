@@ -69,12 +69,27 @@ namespace {
 
 struct DevBuf {
     void *p = nullptr;
-    explicit DevBuf(size_t bytes) { QSV_CUDA(cudaMalloc(&p, bytes)); }
+    size_t bytes = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // small, short-lived buffers (pointer tables, CSR arrays): plain cudaMalloc
+    explicit DevBuf(size_t n) : bytes(n) { QSV_CUDA(cudaMalloc(&p, n)); }
+    // state-sized workspace: from the per-device cache
+    DevBuf(const State &sv, size_t n) : bytes(n), device(sv.device), stream(sv.stream), cached(true) {
+        p = ws_acquire(device, n, stream);
+    }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (!p) return;
+        if (cached)
+            ws_release(device, p, bytes, stream);
+        else
+            cudaFree(p);
     }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
+
+  private:
+    bool cached = false;
 };
 
 LoweredGate lower_op(const State &sv, const Op &op, bool extra_adjoint) {
@@ -103,7 +118,7 @@ void check_sparse_shape(const State &sv, const Obs &o) {
 
 // replace the contents of sv by those of tmp (same size)
 void adopt(State &sv, DevBuf &tmp) {
-    if (sv.owns) {
+    if (sv.owns || sv.swap_ok) {
         std::swap(sv.data, tmp.p);  // the old buffer is released by tmp's destructor
     } else {
         QSV_CUDA(cudaMemcpyAsync(sv.data, tmp.p, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
@@ -113,7 +128,7 @@ void adopt(State &sv, DevBuf &tmp) {
 
 double obs_expval_generic(State &sv, const Obs &o) {
     // tmp = O sv ; <sv|tmp>
-    DevBuf tmp(sv.bytes());
+    DevBuf tmp(sv, sv.bytes());
     State t;
     t.n = sv.n;
     t.dtype = sv.dtype;
@@ -164,13 +179,13 @@ void apply_observable(State &sv, const Obs &o) {
         std::vector<uint64_t> xs, zs;
         std::vector<cplx> cf;
         if (hamiltonian_of_pauli_words(o, sv.n, xs, zs, cf)) {
-            DevBuf tmp(sv.bytes());
+            DevBuf tmp(sv, sv.bytes());
             launch_pauli_sum_apply(sv, sv.data, tmp.p, (int)xs.size(), xs.data(), zs.data(), cf.data());
             adopt(sv, tmp);
             return;
         }
         // generic terms: acc = sum_t c_t O_t psi
-        DevBuf acc(sv.bytes()), tmp(sv.bytes());
+        DevBuf acc(sv, sv.bytes()), tmp(sv, sv.bytes());
         QSV_CUDA(cudaMemsetAsync(acc.p, 0, sv.bytes(), sv.stream));
         State t;
         t.n = sv.n;
@@ -191,7 +206,7 @@ void apply_observable(State &sv, const Obs &o) {
     case Obs::SPARSE: {
         check_sparse_shape(sv, o);
         CsrDev csr(sv, o);
-        DevBuf y(sv.bytes());
+        DevBuf y(sv, sv.bytes());
         launch_csr(sv, sv.data, y.p, csr.indptr.p, csr.indices.p, csr.values.p, (int64_t)sv.length(),
                    (int64_t)o.values.size(), 8, nullptr, 0);
         QSV_CUDA(cudaStreamSynchronize(sv.stream));
@@ -289,14 +304,17 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
     // lambda and the bras H_lambda[i] = O_i lambda
     const size_t bytes = sv.bytes();
     std::vector<std::unique_ptr<State>> vecs;  // [0] = lambda, [1..] = bras
+    std::vector<std::unique_ptr<DevBuf>> vec_mem;  // their memory: cached workspace, released when the call ends
     for (size_t i = 0; i < 1 + n_obs; ++i) {
+        vec_mem.push_back(std::make_unique<DevBuf>(sv, bytes));
         auto s = std::make_unique<State>();
         s->n = sv.n;
         s->dtype = sv.dtype;
         s->device = sv.device;
         s->stream = sv.stream;
-        QSV_CUDA(cudaMalloc(&s->data, bytes));
-        s->owns = true;
+        s->data = vec_mem.back()->p;
+        s->owns = false;
+        s->swap_ok = true;  // an observable may exchange the buffer for another cached block of the same size
         vecs.push_back(std::move(s));
     }
     State &lambda = *vecs[0];
@@ -306,6 +324,7 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
     for (size_t i = 0; i < n_obs; ++i) {
         QSV_CUDA(cudaMemcpyAsync(vecs[1 + i]->data, lambda.data, bytes, cudaMemcpyDeviceToDevice, sv.stream));
         apply_observable(*vecs[1 + i], *obs[i]);
+        vec_mem[1 + i]->p = vecs[1 + i]->data;  // follow a buffer exchange made by the observable
     }
     // device table of vector pointers for the batched U^dagger launch
     std::vector<void *> h_table(1 + n_obs);

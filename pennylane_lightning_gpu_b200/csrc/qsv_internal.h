@@ -100,6 +100,7 @@ struct State {
     cudaStream_t stream = nullptr;
     void *data = nullptr;
     bool owns = false;
+    bool swap_ok = false;  // borrowed from the workspace cache: may be exchanged for another block of the same size
     // reduction scratch (device) + pinned host mirror, lazily allocated
     double *red_dev = nullptr;
     double *red_host = nullptr;
@@ -145,6 +146,11 @@ struct Obs {
     std::vector<int64_t> indptr, indices;
     std::vector<cplx> values;
 };
+
+// Per-device cache of released workspace blocks (state.cu): state-sized temporaries without cudaMalloc / cudaFree per call.
+void *ws_acquire(int device, size_t bytes, cudaStream_t stream);
+void ws_release(int device, void *p, size_t bytes, cudaStream_t stream);
+void ws_trim(int device);
 
 // ------------------------------------------------------------------------------------------------
 // Kernel launchers (apply_kernels.cu / measure_kernels.cu / tile_kernels.cu).

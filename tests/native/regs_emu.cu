@@ -5,6 +5,7 @@
 // DAG sweep packing, pass scheduling, folded index permutations, address maps, program encoding -- can be checked
 // against the NumPy oracle on a machine without a GPU.  The per-thread arithmetic is the kernel's own
 // (__host__ __device__ code of csrc/tile_regs_core.cuh); only the thread/CTA loops and the memories are emulated.
+#include <chrono>
 #include <cstdio>
 #include <vector>
 
@@ -122,6 +123,33 @@ void run_all(std::vector<typename Cx<T>::type> &psi, int n, int dtype, int rb, i
 }
 
 }  // namespace
+
+// host-side cost of one fused application (lowering, merging, sweep planning, program construction), in seconds
+extern "C" double regs_emu_time_host_side(const void *ops_handle, int n, int dtype, int reps) {
+    const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
+    static RegProgram P;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) {
+        std::vector<LoweredGate> gates;
+        for (const auto &op : ops->ops) {
+            if (op.name == "Identity") continue;
+            if (find_gate(op.name) != nullptr)
+                gates.push_back(lower_named(n, op.name, op.wires, op.params, op.inverse));
+            else
+                gates.push_back(lower_matrix(n, op.matrix.data(), {}, op.wires, op.inverse));
+        }
+        const std::vector<LoweredGate> merged = prepare_gates_regs(gates);
+        const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, 4, true, 48, 512);
+        std::vector<const LoweredGate *> cur;
+        for (const SweepPlan &sw : plan) {
+            if (!sw.fused) continue;
+            cur.clear();
+            for (int i : sw.gates) cur.push_back(&merged[i]);
+            build_reg_program(n, dtype, 0, cur, sw.need, 4, 4, P);
+        }
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
 
 // ops = a qsv_ops handle of libqsv_b200.so; state = 2^n interleaved (re, im) doubles, updated in place (complex64 runs
 // the float kernel code on a float copy).  stats[5] = {sweeps, passes, folded permutation gates, merged diagonal gates,
