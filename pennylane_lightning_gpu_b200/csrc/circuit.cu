@@ -109,8 +109,21 @@ struct CsrDev {
         QSV_CUDA(cudaMemcpyAsync(indptr.p, o.indptr.data(), o.indptr.size() * 8, cudaMemcpyHostToDevice, sv.stream));
         QSV_CUDA(cudaMemcpyAsync(indices.p, o.indices.data(), o.indices.size() * 8, cudaMemcpyHostToDevice, sv.stream));
         QSV_CUDA(cudaMemcpyAsync(values.p, o.values.data(), o.values.size() * 16, cudaMemcpyHostToDevice, sv.stream));
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));  // the arrays may be used from other streams later
     }
 };
+
+// Device copy of a sparse observable, uploaded once per (observable, device) and kept for the observable's lifetime: a
+// SparseHamiltonian is immutable once built, and its CSR arrays (3.1 GB at BASELINE config 4) dwarf the product itself.
+// The reference uploads them on every call (simulator/StateVectorCudaManaged.hpp:829-832).
+const CsrDev &csr_on_device(State &sv, const Obs &o) {
+    if (!o.dev_cache || o.dev_cache_device != sv.device) {
+        o.dev_cache.reset();
+        o.dev_cache = std::shared_ptr<void>(new CsrDev(sv, o), [](void *p) { delete static_cast<CsrDev *>(p); });
+        o.dev_cache_device = sv.device;
+    }
+    return *static_cast<const CsrDev *>(o.dev_cache.get());
+}
 
 void check_sparse_shape(const State &sv, const Obs &o) {
     QSV_CHECK(o.indptr.size() == sv.length() + 1, "sparse Hamiltonian dimension does not match the state vector");
@@ -205,7 +218,7 @@ void apply_observable(State &sv, const Obs &o) {
     }
     case Obs::SPARSE: {
         check_sparse_shape(sv, o);
-        CsrDev csr(sv, o);
+        const CsrDev &csr = csr_on_device(sv, o);
         DevBuf y(sv, sv.bytes());
         launch_csr(sv, sv.data, y.p, csr.indptr.p, csr.indices.p, csr.values.p, (int64_t)sv.length(),
                    (int64_t)o.values.size(), 8, nullptr, 0);
@@ -272,7 +285,7 @@ double observable_expval(State &sv, const Obs &o) {
     }
     case Obs::SPARSE: {
         check_sparse_shape(sv, o);
-        CsrDev csr(sv, o);
+        const CsrDev &csr = csr_on_device(sv, o);
         double *red = sv.reduction_buffer(2);
         reduction_zero(sv, red, 2);
         launch_csr(sv, sv.data, nullptr, csr.indptr.p, csr.indices.p, csr.values.p, (int64_t)sv.length(),

@@ -145,6 +145,9 @@ struct Obs {
     // SPARSE
     std::vector<int64_t> indptr, indices;
     std::vector<cplx> values;
+    // device copy of the CSR arrays, made on first use and kept (circuit.cu: csr_on_device)
+    mutable std::shared_ptr<void> dev_cache;
+    mutable int dev_cache_device = -1;
 };
 
 // Per-device cache of released workspace blocks (state.cu): state-sized temporaries without cudaMalloc / cudaFree per call.
