@@ -142,6 +142,7 @@ struct NormGate {
     uint64_t mask_out[2] = {0, 0};
     int n_table_bits = 0;
     int perm = 0;                 // index permutation folded into a pass boundary: 1 = X / CNOT on da, 2 = SWAP(da, db)
+    bool mma_ok = false;          // uncontrolled 4x4 block that may run on two lane bits through FP64 tensor-core MMA
     std::vector<double> pool;     // what goes into the constant pool
 };
 
@@ -391,6 +392,11 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         }
     }
 
+    // complex128: uncontrolled 4x4 blocks may run on two lane bits through DMMA (one such gate per pass, applied first)
+    const bool use_mma = dtype == QSV_C128 && rb == 4 && env_flag("QSV_REGS_MMA", 1);
+    for (size_t i = 0; i < m; ++i)
+        ng[i].mma_ok = use_mma && ng[i].kind == RG_D2 && ng[i].ctrl_loc == 0 && ng[i].ctrl_out == 0 && ng[i].perm == 0;
+
     // ---- list-schedule into passes -----------------------------------------------------------------
     // gate j depends on an earlier gate i when they share a tile bit that one of them touches non-diagonally
     std::vector<std::vector<int>> preds(m);
@@ -421,29 +427,55 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         }
         return v;
     };
-    auto grow = [&](int seed, std::vector<char> &dn, uint32_t &R, uint32_t &F, std::vector<int> &order) {
-        // greedy: keep adding the ready gate that needs the fewest new register bits
-        R = 0;
-        F = 0;
-        order.clear();
-        int next = seed;
-        while (next >= 0) {
-            order.push_back(next);
-            dn[next] = 1;
-            R |= ng[next].dense;
-            F |= ng[next].forbid;
-            next = -1;
-            int best_new = 99;
+    struct PassPick {
+        uint32_t R = 0, F = 0, Pm = 0;  // register bits, forbidden positions, the two positions of the MMA gate
+        int mma = -1;                   // gate applied through DMMA (first in the pass), or -1
+        std::vector<int> order;
+    };
+    auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk) {
+        // greedy: keep adding the ready gate that needs the fewest new register bits.  An uncontrolled 4x4 block whose bits
+        // nothing in the pass has touched yet becomes the pass's tensor-core gate (no register bits at all); it runs first,
+        // and every later gate of the pass that looks at its bits follows it in dependency order anyway.
+        pk = PassPick();
+        uint32_t touched = 0;
+        auto mma_fits = [&](int j) {
+            return ng[j].mma_ok && pk.mma < 0 && !(ng[j].dense & (pk.R | touched | pk.F));
+        };
+        auto add = [&](int j, bool as_mma) {
+            pk.order.push_back(j);
+            dn[j] = 1;
+            touched |= ng[j].bits;
+            if (as_mma) {
+                pk.mma = j;
+                pk.Pm = ng[j].dense;
+            } else {
+                pk.R |= ng[j].dense;
+                pk.F |= ng[j].forbid;
+            }
+        };
+        add(seed, mma_fits(seed));
+        for (;;) {
+            int next = -1, best_new = 99;
+            bool next_mma = false;
             for (size_t j = 0; j < m; ++j) {
                 if (dn[j] || ng[j].perm || !ready_in(j, dn)) continue;
-                const uint32_t u = R | ng[j].dense;
-                if (__builtin_popcount(u) > rb || (u & (F | ng[j].forbid))) continue;
-                const int nw = __builtin_popcount(u) - __builtin_popcount(R);
+                if (mma_fits((int)j)) {
+                    next = (int)j;
+                    next_mma = true;
+                    best_new = -1;
+                    break;
+                }
+                const uint32_t u = pk.R | ng[j].dense;
+                if (__builtin_popcount(u) > rb || (u & (pk.F | ng[j].forbid)) || (ng[j].dense & pk.Pm)) continue;
+                const int nw = __builtin_popcount(u) - __builtin_popcount(pk.R);
                 if (nw < best_new) {
                     best_new = nw;
                     next = (int)j;
+                    next_mma = false;
                 }
             }
+            if (next < 0) break;
+            add(next, next_mma);
         }
     };
     int n_pool = 0;
@@ -453,20 +485,16 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     slot_perms.push_back(take_perms());
     while (n_done < m || P.n_passes == 0) {
         // try every ready gate as the seed of the next pass, keep the pass that retires the most gates
-        std::vector<int> best_order;
-        uint32_t best_R = 0, best_F = 0;
+        PassPick best;
         for (size_t sd = 0; sd < m; ++sd) {
             if (done[sd] || ng[sd].perm || !ready_in(sd, done)) continue;
             std::vector<char> dn = done;
-            std::vector<int> order;
-            uint32_t R, F;
-            grow((int)sd, dn, R, F, order);
-            if (order.size() > best_order.size()) {
-                best_order = order;
-                best_R = R;
-                best_F = F;
-            }
+            PassPick pk;
+            grow((int)sd, dn, pk);
+            if (pk.order.size() > best.order.size()) best = pk;
         }
+        const std::vector<int> &best_order = best.order;
+        const uint32_t best_R = best.R, best_F = best.F | best.Pm;  // register bits stay away from the MMA gate's lane bits
         QSV_CHECK(!best_order.empty() || n_done == m, "internal: pass scheduling made no progress");
         QSV_CHECK(P.n_passes < RT_MAX_PASSES, "internal: too many passes in a sweep");
         const int pi = P.n_passes++;
@@ -492,13 +520,23 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         // thread bits: lanes take the lowest positions (coalescing); among them, the first SW lane bits get
         // distinct positions mod SW when possible (conflict-free swizzled shared-memory accesses)
         std::vector<int> rest;
+        if (best.mma >= 0) {  // thread bit 0 = matrix LSB, thread bit 1 = matrix MSB of the tensor-core gate
+            rest.push_back(ng[best.mma].db);
+            rest.push_back(ng[best.mma].da);
+        }
         for (int p = 0; p < tb; ++p)
-            if (!(R >> p & 1)) rest.push_back(p);
+            if (!(R >> p & 1) && !(best.Pm >> p & 1)) rest.push_back(p);
         std::vector<int> lanes(rest.begin(), rest.begin() + 5), ordered;
         std::vector<char> used(5, 0);
         uint32_t seen = 0;
+        if (best.mma >= 0)
+            for (int q = 0; q < 2; ++q) {
+                ordered.push_back(lanes[q]);
+                used[q] = 1;
+                seen |= 1u << (lanes[q] % SW);
+            }
         for (int q = 0; q < 5 && (int)ordered.size() < SW; ++q)
-            if (!(seen >> (lanes[q] % SW) & 1)) {
+            if (!used[q] && !(seen >> (lanes[q] % SW) & 1)) {
                 seen |= 1u << (lanes[q] % SW);
                 ordered.push_back(lanes[q]);
                 used[q] = 1;
@@ -529,12 +567,32 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
             split(o.ctrl_loc | o.mask_loc[0] | o.mask_loc[1], reg, thr);
             return reg == 0;
         };
+        ps.mma_off = NO_MMA;
+        if (best.mma >= 0) {
+            // real 8x8 form over (re0, im0, ..., re3, im3), amplitude index t = 2 * bit(da) + bit(db)
+            const NormGate &o = ng[best.mma];
+            QSV_CHECK(thrbit_of[o.db] == 0 && thrbit_of[o.da] == 1, "internal: lane bits of the tensor-core gate");
+            QSV_CHECK(n_pool + 64 <= RT_POOL, "internal: constant pool overflow");
+            n_pool = (n_pool + 1) & ~1;  // 16-byte aligned pairs
+            ps.mma_off = (unsigned short)n_pool;
+            for (int t = 0; t < 4; ++t)
+                for (int u = 0; u < 4; ++u) {
+                    const double re = o.pool[2 * (t * 4 + u)], im = o.pool[2 * (t * 4 + u) + 1];
+                    P.pool[n_pool + (2 * t) * 8 + 2 * u] = re;
+                    P.pool[n_pool + (2 * t) * 8 + 2 * u + 1] = -im;
+                    P.pool[n_pool + (2 * t + 1) * 8 + 2 * u] = im;
+                    P.pool[n_pool + (2 * t + 1) * 8 + 2 * u + 1] = re;
+                }
+            n_pool += 64;
+            done[best.mma] = 1;
+            ++n_done;
+        }
         ps.gate_begin = (unsigned short)P.n_gates;
         for (int phase = 0; phase < 2; ++phase) {
             // phase 0: the thread-uniform diagonal gates (they commute with every other gate of the pass), phase 1: the rest
             for (int gi : best_order) {
                 const NormGate &o = ng[gi];
-                if (thread_uniform(o) != (phase == 0)) continue;
+                if (gi == best.mma || thread_uniform(o) != (phase == 0)) continue;
                 RegGate &t = P.gates[P.n_gates++];
                 t.kind = (unsigned char)o.kind;
                 unsigned reg, thr;

@@ -43,8 +43,10 @@ struct RegPass {
     unsigned short gate_begin;  // [gate_begin, udiag_end): thread-uniform diagonal gates, merged into one phase
     unsigned short udiag_end;   // [udiag_end, gate_end): everything else, in order
     unsigned short gate_end;
-    unsigned short pad0;
+    unsigned short mma_off;     // != NO_MMA: pool offset of the real 8x8 form of a 4x4 gate on thread bits 1 (MSB) and 0,
+                                // applied first in the pass through FP64 tensor-core MMA (complex128 kernels only)
 };
+constexpr unsigned short NO_MMA = 0xffff;
 
 struct GlobalMap {  // element offsets inside the shard (tile bits only)
     uint64_t thr[NTB_MAX], reg[RB_MAX], c;
@@ -334,12 +336,38 @@ __host__ __device__ __forceinline__ void reg_diag(A (&x)[NS], const T *mp, bool 
     }
 }
 
+// A complex 4x4 gate on the two lowest LANE bits through mma.sync.m8n8k4.f64: lane 4m+t holds amplitude t of quad m; the
+// real 8x8 form R of the gate is the B operand (this lane: R[lane/4][2*(lane%4)+s] for the k-step s = re / im inputs) and
+// the D fragment comes back as (re_t, im_t) of the same quad, i.e. in place (tools/probes/dmma_gate_probe.cu).  DMMA runs
+// on the same FP64 units as DFMA (profiles/r1_dmma_probe.txt) but needs 8x fewer issue slots per flop.
+#ifdef __CUDA_ARCH__
+template <int NS> __device__ __forceinline__ void mma_gate_4x4(double2 (&x)[NS], const double *rtab, uint32_t lane) {
+    const double2 bb = *reinterpret_cast<const double2 *>(rtab + (lane >> 2) * 8 + 2 * (lane & 3));
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double d0 = 0.0, d1 = 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d0), "+d"(d1) : "d"(x[j].x), "d"(bb.x));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d0), "+d"(d1) : "d"(x[j].y), "d"(bb.y));
+        x[j].x = d0;
+        x[j].y = d1;
+    }
+}
+#endif
+
 // All the arithmetic of one pass for one thread: x = the thread's 2^RB amplitudes, `outside` = index bits beyond the
 // tile, spool = gate constants in the kernel's precision.
 template <typename T, int RB, typename A>
 __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const RegProgram &P, const RegPass &ps, uint32_t tid,
                                                       uint64_t outside, const T *spool) {
     constexpr int NS = 1 << RB;
+#ifdef __CUDA_ARCH__
+    // the tensor-core gate of the pass (every warp is converged here); the CPU emulator applies it before calling this
+    if constexpr (sizeof(T) == 8) {
+        if (ps.mma_off != NO_MMA) mma_gate_4x4<NS>(x, spool + ps.mma_off, tid & 31u);
+    }
+#endif
     // Thread-uniform diagonal gates (no target or control on a register bit) commute with every other gate of the pass:
     // their phases are multiplied per thread and applied to the 2^RB amplitudes once.
     if (ps.udiag_end > ps.gate_begin) {

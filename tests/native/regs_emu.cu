@@ -79,6 +79,28 @@ template <typename T, int RB> void emulate_program(std::vector<typename Cx<T>::t
                     for (int j = 0; j < NS; ++j) x[j] = smem[slot_offset<RB>(st, sr, j)];
                 }
             }
+            if (ps.mma_off != NO_MMA) {
+                // the tensor-core gate of the pass: threads 4m .. 4m+3 hold amplitudes t = 0..3 of quad m (per slot); the real
+                // 8x8 table acts on (re0, im0, ..., re3, im3)
+                const double *R = P.pool + ps.mma_off;
+                for (uint32_t t0 = 0; t0 < (uint32_t)NT; t0 += 4)
+                    for (int j = 0; j < NS; ++j) {
+                        double in[8], out[8];
+                        for (int u = 0; u < 4; ++u) {
+                            in[2 * u] = (double)xs[(size_t)(t0 + u) * NS + j].x;
+                            in[2 * u + 1] = (double)xs[(size_t)(t0 + u) * NS + j].y;
+                        }
+                        for (int r = 0; r < 8; ++r) {
+                            double acc = 0.0;
+                            for (int k = 0; k < 8; ++k) acc += R[r * 8 + k] * in[k];
+                            out[r] = acc;
+                        }
+                        for (int u = 0; u < 4; ++u) {
+                            xs[(size_t)(t0 + u) * NS + j].x = (T)out[2 * u];
+                            xs[(size_t)(t0 + u) * NS + j].y = (T)out[2 * u + 1];
+                        }
+                    }
+            }
             for (uint32_t tid = 0; tid < (uint32_t)NT; ++tid) {
                 A(&x)[NS] = *reinterpret_cast<A(*)[NS]>(&xs[(size_t)tid * NS]);
                 pass_compute<T, RB>(x, P, ps, tid, outside, spool.data());
@@ -113,8 +135,15 @@ void run_all(std::vector<typename Cx<T>::type> &psi, int n, int dtype, int rb, i
         for (int i : sw.gates) cur.push_back(&merged[i]);
         build_reg_program(n, dtype, 0, cur, sw.need, L, rb, P);
         stats[1] += P.n_passes;
-        stats[2] += (int64_t)cur.size() - P.n_gates;  // gates folded into pass boundaries
-        for (int p = 0; p < P.n_passes; ++p) stats[3] += P.passes[p].udiag_end - P.passes[p].gate_begin;
+        {
+            int64_t n_mma = 0;
+            for (int p = 0; p < P.n_passes; ++p) n_mma += P.passes[p].mma_off != NO_MMA ? 1 : 0;
+            stats[2] += (int64_t)cur.size() - P.n_gates - n_mma;  // gates folded into pass boundaries
+        }
+        for (int p = 0; p < P.n_passes; ++p) {
+            stats[3] += P.passes[p].udiag_end - P.passes[p].gate_begin;
+            stats[5] += P.passes[p].mma_off != NO_MMA ? 1 : 0;
+        }
         if (rb == 4)
             emulate_program<T, 4>(psi, n, P);
         else
@@ -152,8 +181,8 @@ extern "C" double regs_emu_time_host_side(const void *ops_handle, int n, int dty
 }
 
 // ops = a qsv_ops handle of libqsv_b200.so; state = 2^n interleaved (re, im) doubles, updated in place (complex64 runs
-// the float kernel code on a float copy).  stats[5] = {sweeps, passes, folded permutation gates, merged diagonal gates,
-// lone gates}.  Returns 0 on success.
+// the float kernel code on a float copy).  stats[6] = {sweeps, passes, folded permutation gates, merged diagonal gates,
+// lone gates, tensor-core gates}.  Returns 0 on success.
 extern "C" int regs_emu_apply_ops(const void *ops_handle, int n, int dtype, int rb, int low_bits, int dag, double *state,
                                   int64_t *stats) {
     try {
@@ -167,7 +196,7 @@ extern "C" int regs_emu_apply_ops(const void *ops_handle, int n, int dtype, int 
                 gates.push_back(lower_matrix(n, op.matrix.data(), {}, op.wires, op.inverse));
         }
         const std::vector<LoweredGate> merged = prepare_gates_regs(gates);
-        for (int i = 0; i < 5; ++i) stats[i] = 0;
+        for (int i = 0; i < 6; ++i) stats[i] = 0;
         const uint64_t N = 1ull << n;
         const int L = low_bits > 0 ? low_bits : 4;
         if (dtype == QSV_C128) {

@@ -34,11 +34,11 @@ def run_emulated(emu, ops, psi0, dtype=np.complex128, rb=4, low=0, dag=True):
     n = int(np.log2(psi0.size))
     rec = q.Ops(ops)
     buf = np.ascontiguousarray(psi0.astype(np.complex128)).view(np.float64).copy()
-    stats = (C.c_int64 * 5)()
+    stats = (C.c_int64 * 6)()
     rc = emu.regs_emu_apply_ops(rec._h, n, 1 if dtype == np.complex128 else 0, rb, low, int(dag),
                                 buf.ctypes.data_as(C.POINTER(C.c_double)), stats)
     assert rc == 0
-    names = ("sweeps", "passes", "folded", "merged_diag", "lone")
+    names = ("sweeps", "passes", "folded", "merged_diag", "lone", "mma")
     return buf.view(np.complex128), dict(zip(names, list(stats)))
 
 
@@ -100,7 +100,7 @@ def test_mixed_circuits_match_oracle(emu, n, seed, rb):
 
 
 @pytest.mark.parametrize("env", [{}, {"QSV_REGS_FOLD": "0"}, {"QSV_REGS_UDIAG": "0"}, {"QSV_REGS_DAG": "0"},
-                                 {"QSV_REGS_FOLD": "0", "QSV_REGS_UDIAG": "0"}, {"QSV_MERGE_1Q": "0"}])
+                                 {"QSV_REGS_FOLD": "0", "QSV_REGS_UDIAG": "0"}, {"QSV_MERGE_1Q": "0"}, {"QSV_REGS_MMA": "0"}])
 def test_feature_switches(emu, env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -114,6 +114,10 @@ def test_feature_switches(emu, env, monkeypatch):
         assert st["folded"] == 0
     if env.get("QSV_REGS_UDIAG") == "0":
         assert st["merged_diag"] == 0
+    if env.get("QSV_REGS_MMA") == "0":
+        assert st["mma"] == 0
+    elif not env:
+        assert st["mma"] > 0
 
 
 def test_permutation_only_and_ladders(emu):
