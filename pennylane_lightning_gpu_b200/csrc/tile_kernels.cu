@@ -649,7 +649,7 @@ std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGa
     const uint64_t low = (1ull << L) - 1ull;
     std::vector<SweepPlan> plan;
     auto pool_of = [](const LoweredGate &g) {
-        return (g.kind == LoweredGate::DENSE && !(g.k == 1 && g.tgt_bits.size() == 1)) ? 66 : 8;  // 4x4: up to a real 8x8
+        return (g.kind == LoweredGate::DENSE && !(g.k == 1 && g.tgt_bits.size() == 1)) ? 66 : 8;  // 4x4: up to a real 8x8 (tensor-core block)
     };
     // one maximal run of fusable gates (indices into `gates`), packed over its dependency DAG
     auto pack_segment = [&](const std::vector<int> &seg) {

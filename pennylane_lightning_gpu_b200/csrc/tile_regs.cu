@@ -393,9 +393,16 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     }
 
     // complex128: uncontrolled 4x4 blocks may run on two lane bits through DMMA (one such gate per pass, applied first)
-    const bool use_mma = dtype == QSV_C128 && rb == 4 && env_flag("QSV_REGS_MMA", 1);
-    for (size_t i = 0; i < m; ++i)
-        ng[i].mma_ok = use_mma && ng[i].kind == RG_D2 && ng[i].ctrl_loc == 0 && ng[i].ctrl_out == 0 && ng[i].perm == 0;
+    // QSV_REGS_MMA: 0 = off, 1 = one 4x4 gate per pass, 2 (default) = a 4x4 BLOCK per pass: the pass scheduler multiplies
+    // uncontrolled 2x2 and 4x4 gates on the block's two positions into it for as long as nothing else in the pass has touched
+    // those positions (a 2x2 alone runs as U (x) 1: twice the flops, a quarter of the instructions)
+    const int mma_mode = (dtype == QSV_C128 && rb == 4) ? env_int_regs("QSV_REGS_MMA", 2) : 0;
+    const bool use_mma = mma_mode > 0;
+    for (size_t i = 0; i < m; ++i) {
+        const bool plain = ng[i].ctrl_loc == 0 && ng[i].ctrl_out == 0 && ng[i].perm == 0;
+        const bool d1 = ng[i].kind == RG_D1 || ng[i].kind == RG_D1_REAL || ng[i].kind == RG_D1_RX;
+        ng[i].mma_ok = use_mma && plain && (ng[i].kind == RG_D2 || (mma_mode >= 2 && d1));
+    }
 
     // ---- list-schedule into passes -----------------------------------------------------------------
     // gate j depends on an earlier gate i when they share a tile bit that one of them touches non-diagonally
@@ -427,28 +434,31 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         }
         return v;
     };
+    bool mma_allowed = use_mma;  // switched off for the rest of the sweep if the constant pool could not hold another block
     struct PassPick {
-        uint32_t R = 0, F = 0, Pm = 0;  // register bits, forbidden positions, the two positions of the MMA gate
-        int mma = -1;                   // gate applied through DMMA (first in the pass), or -1
+        uint32_t R = 0, F = 0, Pm = 0;  // register bits, forbidden positions, the (one or two) positions of the MMA block
+        std::vector<int> mma;           // gates multiplied into the MMA block (applied first in the pass), in order
         std::vector<int> order;
     };
     auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk) {
-        // greedy: keep adding the ready gate that needs the fewest new register bits.  An uncontrolled 4x4 block whose bits
-        // nothing in the pass has touched yet becomes the pass's tensor-core gate (no register bits at all); it runs first,
-        // and every later gate of the pass that looks at its bits follows it in dependency order anyway.
+        // greedy: keep adding the ready gate that needs the fewest new register bits.  Uncontrolled dense gates on positions
+        // that nothing else in the pass has touched join the pass's tensor-core block (no register bits at all); the block
+        // runs first, and every later gate of the pass that looks at its positions follows it in dependency order anyway.
         pk = PassPick();
-        uint32_t touched = 0;
+        uint32_t touched_other = 0;  // positions looked at by the non-block gates of the pass
         auto mma_fits = [&](int j) {
-            return ng[j].mma_ok && pk.mma < 0 && !(ng[j].dense & (pk.R | touched | pk.F));
+            if (!mma_allowed || !ng[j].mma_ok || (ng[j].dense & (pk.R | pk.F | touched_other))) return false;
+            if (mma_mode == 1 && !pk.mma.empty()) return false;
+            return __builtin_popcount(pk.Pm | ng[j].dense) <= 2;
         };
         auto add = [&](int j, bool as_mma) {
             pk.order.push_back(j);
             dn[j] = 1;
-            touched |= ng[j].bits;
             if (as_mma) {
-                pk.mma = j;
-                pk.Pm = ng[j].dense;
+                pk.mma.push_back(j);
+                pk.Pm |= ng[j].dense;
             } else {
+                touched_other |= ng[j].bits;
                 pk.R |= ng[j].dense;
                 pk.F |= ng[j].forbid;
             }
@@ -462,7 +472,6 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
                 if (mma_fits((int)j)) {
                     next = (int)j;
                     next_mma = true;
-                    best_new = -1;
                     break;
                 }
                 const uint32_t u = pk.R | ng[j].dense;
@@ -493,8 +502,29 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
             grow((int)sd, dn, pk);
             if (pk.order.size() > best.order.size()) best = pk;
         }
+        if (!best.mma.empty()) {
+            // every remaining gate may still need its own constants: keep room for them
+            size_t need_pool = (size_t)n_pool + 66;
+            for (size_t j = 0; j < m; ++j)
+                if (!done[j] && std::find(best.mma.begin(), best.mma.end(), (int)j) == best.mma.end()) need_pool += ng[j].pool.size();
+            if (need_pool > (size_t)RT_POOL) {
+                mma_allowed = false;
+                continue;  // choose this pass again without a tensor-core block
+            }
+        }
         const std::vector<int> &best_order = best.order;
-        const uint32_t best_R = best.R, best_F = best.F | best.Pm;  // register bits stay away from the MMA gate's lane bits
+        // the MMA block's two positions (ma = matrix MSB); a block on one position gets the lowest free position as partner
+        int ma = -1, mb = -1;
+        if (!best.mma.empty()) {
+            uint32_t pm = best.Pm;
+            for (int p = 0; p < tb && __builtin_popcount(pm) < 2; ++p)
+                if (!((pm | best.R | best.F) >> p & 1)) pm |= 1u << p;
+            QSV_CHECK(__builtin_popcount(pm) == 2, "internal: no partner position for the tensor-core block");
+            best.Pm = pm;
+            mb = __builtin_ctz(pm);
+            ma = 31 - __builtin_clz(pm);
+        }
+        const uint32_t best_R = best.R, best_F = best.F | best.Pm;  // register bits stay away from the MMA block's lane bits
         QSV_CHECK(!best_order.empty() || n_done == m, "internal: pass scheduling made no progress");
         QSV_CHECK(P.n_passes < RT_MAX_PASSES, "internal: too many passes in a sweep");
         const int pi = P.n_passes++;
@@ -520,16 +550,16 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         // thread bits: lanes take the lowest positions (coalescing); among them, the first SW lane bits get
         // distinct positions mod SW when possible (conflict-free swizzled shared-memory accesses)
         std::vector<int> rest;
-        if (best.mma >= 0) {  // thread bit 0 = matrix LSB, thread bit 1 = matrix MSB of the tensor-core gate
-            rest.push_back(ng[best.mma].db);
-            rest.push_back(ng[best.mma].da);
+        if (ma >= 0) {  // thread bit 0 = matrix LSB, thread bit 1 = matrix MSB of the tensor-core block
+            rest.push_back(mb);
+            rest.push_back(ma);
         }
         for (int p = 0; p < tb; ++p)
             if (!(R >> p & 1) && !(best.Pm >> p & 1)) rest.push_back(p);
         std::vector<int> lanes(rest.begin(), rest.begin() + 5), ordered;
         std::vector<char> used(5, 0);
         uint32_t seen = 0;
-        if (best.mma >= 0)
+        if (ma >= 0)
             for (int q = 0; q < 2; ++q) {
                 ordered.push_back(lanes[q]);
                 used[q] = 1;
@@ -568,31 +598,67 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
             return reg == 0;
         };
         ps.mma_off = NO_MMA;
-        if (best.mma >= 0) {
-            // real 8x8 form over (re0, im0, ..., re3, im3), amplitude index t = 2 * bit(da) + bit(db)
-            const NormGate &o = ng[best.mma];
-            QSV_CHECK(thrbit_of[o.db] == 0 && thrbit_of[o.da] == 1, "internal: lane bits of the tensor-core gate");
-            QSV_CHECK(n_pool + 64 <= RT_POOL, "internal: constant pool overflow");
+        if (ma >= 0) {
+            QSV_CHECK(thrbit_of[mb] == 0 && thrbit_of[ma] == 1, "internal: lane bits of the tensor-core block");
+            // product of the member gates as a 4x4 in the (ma, mb) basis
+            cplx M4[16];
+            for (int q = 0; q < 16; ++q) M4[q] = (q / 4 == q % 4) ? cplx(1.0, 0.0) : cplx(0.0, 0.0);
+            for (int gi : best.mma) {
+                const NormGate &o = ng[gi];
+                cplx G[16];
+                if (o.kind == RG_D2) {
+                    const bool same = o.da == ma;
+                    QSV_CHECK((same && o.db == mb) || (o.da == mb && o.db == ma), "internal: tensor-core block positions");
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = 0; c < 4; ++c) {
+                            const int sr = same ? r : ((r & 1) << 1) | (r >> 1), sc = same ? c : ((c & 1) << 1) | (c >> 1);
+                            G[r * 4 + c] = cplx(o.pool[2 * (sr * 4 + sc)], o.pool[2 * (sr * 4 + sc) + 1]);
+                        }
+                } else {
+                    cplx U[4];
+                    for (int q = 0; q < 4; ++q) U[q] = cplx(o.pool[2 * q], o.pool[2 * q + 1]);
+                    const bool on_msb = o.da == ma;
+                    QSV_CHECK(on_msb || o.da == mb, "internal: tensor-core block position");
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = 0; c < 4; ++c) {
+                            const int rh = r >> 1, rl = r & 1, ch = c >> 1, cl = c & 1;
+                            G[r * 4 + c] = on_msb ? (rl == cl ? U[rh * 2 + ch] : cplx(0.0, 0.0))
+                                                  : (rh == ch ? U[rl * 2 + cl] : cplx(0.0, 0.0));
+                        }
+                }
+                cplx T4[16];
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c < 4; ++c) {
+                        cplx acc(0.0, 0.0);
+                        for (int k = 0; k < 4; ++k) acc += G[r * 4 + k] * M4[k * 4 + c];
+                        T4[r * 4 + c] = acc;
+                    }
+                for (int q = 0; q < 16; ++q) M4[q] = T4[q];
+                done[gi] = 1;
+                ++n_done;
+                ++P.n_mma_gates;
+            }
+            // real 8x8 form over (re0, im0, ..., re3, im3), amplitude index t = 2 * bit(ma) + bit(mb)
+            QSV_CHECK(n_pool + 66 <= RT_POOL, "internal: constant pool overflow");
             n_pool = (n_pool + 1) & ~1;  // 16-byte aligned pairs
             ps.mma_off = (unsigned short)n_pool;
             for (int t = 0; t < 4; ++t)
                 for (int u = 0; u < 4; ++u) {
-                    const double re = o.pool[2 * (t * 4 + u)], im = o.pool[2 * (t * 4 + u) + 1];
+                    const double re = M4[t * 4 + u].real(), im = M4[t * 4 + u].imag();
                     P.pool[n_pool + (2 * t) * 8 + 2 * u] = re;
                     P.pool[n_pool + (2 * t) * 8 + 2 * u + 1] = -im;
                     P.pool[n_pool + (2 * t + 1) * 8 + 2 * u] = im;
                     P.pool[n_pool + (2 * t + 1) * 8 + 2 * u + 1] = re;
                 }
             n_pool += 64;
-            done[best.mma] = 1;
-            ++n_done;
         }
         ps.gate_begin = (unsigned short)P.n_gates;
         for (int phase = 0; phase < 2; ++phase) {
             // phase 0: the thread-uniform diagonal gates (they commute with every other gate of the pass), phase 1: the rest
             for (int gi : best_order) {
                 const NormGate &o = ng[gi];
-                if (gi == best.mma || thread_uniform(o) != (phase == 0)) continue;
+                if (std::find(best.mma.begin(), best.mma.end(), gi) != best.mma.end()) continue;
+                if (thread_uniform(o) != (phase == 0)) continue;
                 RegGate &t = P.gates[P.n_gates++];
                 t.kind = (unsigned char)o.kind;
                 unsigned reg, thr;
@@ -629,6 +695,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         slot_perms.push_back(take_perms());
     }
     QSV_CHECK((int)slot_perms.size() == P.n_passes + 1, "internal: permutation slots");
+    for (const auto &v : slot_perms) P.n_folded += (int)v.size();
 
     // ---- address maps --------------------------------------------------------------------------------
     auto to_global = [&](uint32_t v) {

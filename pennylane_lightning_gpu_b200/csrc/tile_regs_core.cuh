@@ -65,6 +65,8 @@ struct RegProgram {
     double pool[POOL];                // gate constants (complex128 kernels read them from here or from shared memory)
     float poolf[POOL];                // the same in single precision for the complex64 kernels
     int uniform_consts;               // != 0: uncontrolled dense gates read their matrix straight from this struct
+    int n_folded;                     // host-side statistics: gates folded into pass boundaries ...
+    int n_mma_gates;                  // ... and gates multiplied into tensor-core blocks
     int pad1;
 };
 
@@ -341,17 +343,20 @@ __host__ __device__ __forceinline__ void reg_diag(A (&x)[NS], const T *mp, bool 
 // the D fragment comes back as (re_t, im_t) of the same quad, i.e. in place (tools/probes/dmma_gate_probe.cu).  DMMA runs
 // on the same FP64 units as DFMA (profiles/r1_dmma_probe.txt) but needs 8x fewer issue slots per flop.
 #ifdef __CUDA_ARCH__
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b, double c0, double c1) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
 template <int NS> __device__ __forceinline__ void mma_gate_4x4(double2 (&x)[NS], const double *rtab, uint32_t lane) {
     const double2 bb = *reinterpret_cast<const double2 *>(rtab + (lane >> 2) * 8 + 2 * (lane & 3));
+    constexpr int G = 4;  // slots in flight: the two MMAs of a slot depend on each other, different slots do not
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-        double d0 = 0.0, d1 = 0.0;
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(d0), "+d"(d1) : "d"(x[j].x), "d"(bb.x));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(d0), "+d"(d1) : "d"(x[j].y), "d"(bb.y));
-        x[j].x = d0;
-        x[j].y = d1;
+    for (int j = 0; j < NS; j += G) {
+        double t0[G], t1[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) dmma_8x8x4(t0[q], t1[q], x[j + q].x, bb.x, 0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < G; ++q) dmma_8x8x4(x[j + q].x, x[j + q].y, x[j + q].y, bb.y, t0[q], t1[q]);
     }
 }
 #endif

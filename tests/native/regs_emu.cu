@@ -135,15 +135,9 @@ void run_all(std::vector<typename Cx<T>::type> &psi, int n, int dtype, int rb, i
         for (int i : sw.gates) cur.push_back(&merged[i]);
         build_reg_program(n, dtype, 0, cur, sw.need, L, rb, P);
         stats[1] += P.n_passes;
-        {
-            int64_t n_mma = 0;
-            for (int p = 0; p < P.n_passes; ++p) n_mma += P.passes[p].mma_off != NO_MMA ? 1 : 0;
-            stats[2] += (int64_t)cur.size() - P.n_gates - n_mma;  // gates folded into pass boundaries
-        }
-        for (int p = 0; p < P.n_passes; ++p) {
-            stats[3] += P.passes[p].udiag_end - P.passes[p].gate_begin;
-            stats[5] += P.passes[p].mma_off != NO_MMA ? 1 : 0;
-        }
+        stats[2] += P.n_folded;  // gates folded into pass boundaries
+        for (int p = 0; p < P.n_passes; ++p) stats[3] += P.passes[p].udiag_end - P.passes[p].gate_begin;
+        stats[5] += P.n_mma_gates;
         if (rb == 4)
             emulate_program<T, 4>(psi, n, P);
         else

@@ -13,10 +13,10 @@ run() {
   echo "== $label" >> $OUT
   env "$@" timeout 300 $B 2>&1 | tail -1 | python -c "$P" >> $OUT 2>&1
 }
-run "default (MMA on)" QSV_DUMMY=1
+run "default (MMA mode 2: merged 4x4 block per pass)" QSV_DUMMY=1
 run "MMA off" QSV_REGS_MMA=0
-run "MMA on, L=5" QSV_REGS_LOW=5
-run "MMA on, L=3" QSV_REGS_LOW=3
+run "MMA mode 1 (one 4x4 gate per pass)" QSV_REGS_MMA=1
+run "MMA mode 2, L=5" QSV_REGS_LOW=5
 echo "== adjoint config 3 + config 1" >> $OUT
 timeout 600 python bench.py --steps 1 --warmup 3 --sweeps 0 --e2e 0 --cpu-baseline 0 --adjoint 1 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps(d["detail"]["adjoint_config3"])[:400]); print(json.dumps(d["detail"]["config1_sel20"])[:300])' >> $OUT 2>&1
 echo "== ncu full, 2 launches (default)" >> $OUT
