@@ -35,6 +35,9 @@ constexpr int RT_MAX_GATES = MAX_GATES;
 constexpr int RT_MAX_PASSES = MAX_PASSES;
 constexpr int RT_POOL = POOL;
 
+// per-SM arrival counters of the current launch: (epoch << 32) | CTAs that have started on this SM
+__device__ unsigned long long g_sm_arrivals[256];
+
 template <typename T, int RB, int MINB>
 __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     k_tile_regs(void *single, void *const *table, const __grid_constant__ RegProgram P) {
@@ -64,12 +67,38 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
             }
         }
     }
+    // Every tile costs the same, so the CTAs resident on an SM -- and on the whole GPU -- would run in lockstep: all of them
+    // load from HBM at the same time, then all of them compute, and the phases add up instead of overlapping (measured:
+    // time per tile = HBM time + FP64 time + transposition time).  The k-th CTA to arrive on each SM (k < CTAs per SM)
+    // therefore waits k / (CTAs per SM) of a tile time, once; after that the CTA slots of the SM stay out of phase.
+    __shared__ unsigned s_arrival;
+    if (tid == 0) {
+        unsigned mine = 0;
+        if (P.stagger_ns > 0 && blockIdx.x < 1024u && blockIdx.y == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned long long *w = &g_sm_arrivals[smid & 255u];
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(w);
+            for (;;) {
+                const bool fresh = (unsigned)(old >> 32) != P.epoch;
+                const unsigned long long want = fresh ? ((unsigned long long)P.epoch << 32) | 1ull : old + 1ull;
+                const unsigned long long seen = atomicCAS(w, old, want);
+                if (seen == old) {
+                    mine = fresh ? 0u : (unsigned)(old & 0xffffffffull);
+                    break;
+                }
+                old = seen;
+            }
+        }
+        s_arrival = mine;
+    }
     // Gate constants go to shared memory once per CTA (in the kernel's precision) and are then read with uniform,
     // broadcast LDS: indexed constant-bank loads (LDC) inside the thread-divergent gate code run on the ADU pipe,
     // which ncu showed to be the busiest unit of the first version of this kernel (52 % vs 33 % FP64).
     T *spool = reinterpret_cast<T *>(smem_raw + (sizeof(A) << RT_TB));
     for (int i = tid; i < P.pool_used; i += NT) spool[i] = (T)P.pool[i];
     __syncthreads();
+    if (s_arrival >= 1u && s_arrival < (unsigned)MINB) __nanosleep(P.stagger_ns * s_arrival);
 
     A x[NS];
     {
@@ -732,6 +761,20 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         global_cols(inv, 0, P.gl_load);
     }
     P.pool_used = n_pool;
+    {
+        // a rough tile time divided by the CTAs per SM: HBM share of a 64 KiB tile + FP pipe time of the gates + transposes, in SM clocks
+        double fp = 0.0;
+        for (int gi = 0; gi < P.n_gates; ++gi) {
+            const int k = P.gates[gi].kind;
+            fp += k == RG_D2 ? 256 : k == RG_D1 ? 128 : k == RG_D1_SWAP ? 0 : 64;
+        }
+        for (int pi = 0; pi < P.n_passes; ++pi) fp += P.passes[pi].mma_off != NO_MMA ? 256 : 0;
+        const double amp = dtype == QSV_C128 ? 1.0 : 0.5;
+        const double clk = amp * (5800.0 + 4.0 * fp + 1000.0 * (P.n_passes - 1));
+        const int forced = env_int_regs("QSV_REGS_STAGGER_NS", -1);
+        const int ctas_per_sm = (dtype == QSV_C128 || rb == 3) ? 2 : 3;  // MINB of launch_regs_t
+        P.stagger_ns = forced >= 0 ? (unsigned)forced : (unsigned)(clk / ctas_per_sm / 1.9);
+    }
     for (int i = 0; i < n_pool; ++i) P.poolf[i] = (float)P.pool[i];
     P.uniform_consts = env_flag("QSV_REGS_UCONST", 1) ? 1 : 0;
     P.prefetch = std::max(0, env_int_regs("QSV_REGS_PREFETCH", 0));
@@ -742,6 +785,8 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     const int rb = regs_rb();
     RegProgram P;
     build_reg_program(sv.n, sv.dtype, sv.index_hi, gates, need, L, rb, P);
+    static unsigned launch_epoch = 0;
+    P.epoch = ++launch_epoch == 0 ? ++launch_epoch : launch_epoch;  // never 0: the counters start zeroed
     sv.stat_launches += 1;
     sv.stat_sweeps += 1;
     if (sv.dtype == QSV_C128) {

@@ -67,6 +67,8 @@ struct RegProgram {
     int uniform_consts;               // != 0: uncontrolled dense gates read their matrix straight from this struct
     int n_folded;                     // host-side statistics: gates folded into pass boundaries ...
     int n_mma_gates;                  // ... and gates multiplied into tensor-core blocks
+    unsigned stagger_ns;              // > 0: the second CTA to arrive on each SM waits this long once (see k_tile_regs)
+    unsigned epoch;                   // launch number (tags the per-SM arrival counters)
     int pad1;
 };
 
