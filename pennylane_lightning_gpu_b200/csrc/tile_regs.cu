@@ -97,19 +97,6 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     // which ncu showed to be the busiest unit of the first version of this kernel (52 % vs 33 % FP64).
     T *spool = reinterpret_cast<T *>(smem_raw + (sizeof(A) << RT_TB));
     for (int i = tid; i < P.pool_used; i += NT) spool[i] = (T)P.pool[i];
-    // ... and so do the gate and pass descriptors (8-byte words): ncu attributed ~10 % of all warp stalls to waits on the
-    // indexed constant-bank loads of the decode
-    RegGate *sgates = reinterpret_cast<RegGate *>(smem_raw + (sizeof(A) << RT_TB) + RT_POOL * sizeof(T));
-    RegPass *spasses = reinterpret_cast<RegPass *>(sgates + RT_MAX_GATES);
-    {
-        const int ng8 = P.n_gates * (int)(sizeof(RegGate) / 8), np8 = P.n_passes * (int)(sizeof(RegPass) / 8);
-        const unsigned long long *src_g = reinterpret_cast<const unsigned long long *>(P.gates);
-        const unsigned long long *src_p = reinterpret_cast<const unsigned long long *>(P.passes);
-        unsigned long long *dst_g = reinterpret_cast<unsigned long long *>(sgates);
-        unsigned long long *dst_p = reinterpret_cast<unsigned long long *>(spasses);
-        for (int i = tid; i < ng8; i += NT) dst_g[i] = src_g[i];
-        for (int i = tid; i < np8; i += NT) dst_p[i] = src_p[i];
-    }
     __syncthreads();
     if (s_arrival >= 1u && s_arrival < (unsigned)MINB) __nanosleep(P.stagger_ns * s_arrival);
 
@@ -128,8 +115,8 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         // warp-uniform again, so that pass / gate descriptors and gate constants are fetched with uniform loads (LDCU) into
         // uniform registers instead of per-thread LDC + vector registers
         const int p = __shfl_sync(0xffffffffu, pv, 0);
-        const RegPass &ps = spasses[p];
-        pass_compute<T, RB>(x, P, ps, tid, outside, spool, sgates);
+        const RegPass &ps = P.passes[p];
+        pass_compute<T, RB>(x, P, ps, tid, outside, spool);
         if (p == last) break;
         // transpose through shared memory: store in this pass's layout (folded permutations included), load in the next one's
         if (p > 0) __syncthreads();  // every thread has finished reading the previous layout
@@ -143,7 +130,7 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         }
         __syncthreads();
         {
-            const RegPass &pn = spasses[p + 1];
+            const RegPass &pn = P.passes[p + 1];
             const uint32_t st = thread_offset<NTB>(pn.ld_thr, pn.ld_c, tid);
             uint32_t sr[RB_MAX];
 #pragma unroll
@@ -248,8 +235,7 @@ template <typename T, int RB> void launch_regs_t(State &sv, const RegProgram &P,
     // register budget: 16 amplitudes per thread need 2 CTAs of 256 threads (128 registers); 8 amplitudes per thread run as
     // 2 CTAs of 512 threads (64 registers)
     constexpr int MINB = RB == 4 ? (sizeof(T) == 8 ? 2 : 3) : 2;
-    const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T) +
-                        RT_MAX_GATES * sizeof(RegGate) + RT_MAX_PASSES * sizeof(RegPass);
+    const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
     static bool configured[64] = {false};  // per device: function attributes belong to the device's context
     auto kern = k_tile_regs<T, RB, MINB>;
     if (!configured[sv.device & 63]) {

@@ -47,7 +47,6 @@ struct RegPass {
                                 // applied first in the pass through FP64 tensor-core MMA (complex128 kernels only)
 };
 constexpr unsigned short NO_MMA = 0xffff;
-static_assert(sizeof(RegGate) % 8 == 0 && sizeof(RegPass) % 8 == 0, "descriptors are copied to shared memory in 8-byte words");
 
 struct GlobalMap {  // element offsets inside the shard (tile bits only)
     uint64_t thr[NTB_MAX], reg[RB_MAX], c;
@@ -365,11 +364,10 @@ template <int NS> __device__ __forceinline__ void mma_gate_4x4(double2 (&x)[NS],
 #endif
 
 // All the arithmetic of one pass for one thread: x = the thread's 2^RB amplitudes, `outside` = index bits beyond the
-// tile, spool = gate constants in the kernel's precision, gates = the gate descriptors (the kernel passes its shared-memory
-// copy: indexed constant-bank loads have several times the latency of LDS and sat on the critical path of every gate).
+// tile, spool = gate constants in the kernel's precision.
 template <typename T, int RB, typename A>
 __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const RegProgram &P, const RegPass &ps, uint32_t tid,
-                                                      uint64_t outside, const T *spool, const RegGate *gates) {
+                                                      uint64_t outside, const T *spool) {
     constexpr int NS = 1 << RB;
 #ifdef __CUDA_ARCH__
     // the tensor-core gate of the pass (every warp is converged here); the CPU emulator applies it before calling this
@@ -383,7 +381,7 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
         T pr = (T)1, pi = (T)0;
         bool any = false;
         for (int gi = ps.gate_begin; gi < ps.udiag_end; ++gi) {
-            const RegGate &g = gates[gi];
+            const RegGate &g = P.gates[gi];
             if ((outside & g.out_ctrl) != g.out_ctrl) continue;
             if ((tid & g.ctrl_thr) != g.ctrl_thr) continue;
             const int tb0 = (popc32(tid & g.thr_mask[0]) ^ popc64(outside & g.out_mask[0])) & 1;
@@ -405,7 +403,7 @@ __host__ __device__ __forceinline__ void pass_compute(A (&x)[1 << RB], const Reg
         }
     }
     for (int gi = ps.udiag_end; gi < ps.gate_end; ++gi) {
-        const RegGate &g = gates[gi];
+        const RegGate &g = P.gates[gi];
         if ((outside & g.out_ctrl) != g.out_ctrl) continue;  // CTA-uniform
         const bool thr_on = (tid & g.ctrl_thr) == g.ctrl_thr;
         const T *mp = spool + g.mat_off;

@@ -103,7 +103,7 @@ template <typename T, int RB> void emulate_program(std::vector<typename Cx<T>::t
             }
             for (uint32_t tid = 0; tid < (uint32_t)NT; ++tid) {
                 A(&x)[NS] = *reinterpret_cast<A(*)[NS]>(&xs[(size_t)tid * NS]);
-                pass_compute<T, RB>(x, P, ps, tid, outside, spool.data(), P.gates);
+                pass_compute<T, RB>(x, P, ps, tid, outside, spool.data());
                 if (last) {
                     const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
                     for (int j = 0; j < NS; ++j) psi[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
