@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
             }
         }
     }
-    // Every tile costs the same, so the CTAs resident on an SM -- and on the whole GPU -- would run in lockstep: all of them
-    // load from HBM at the same time, then all of them compute, and the phases add up instead of overlapping (measured:
-    // time per tile = HBM time + FP64 time + transposition time).  The k-th CTA to arrive on each SM (k < CTAs per SM)
+    // Experiment (off by default): every tile costs the same, so the CTAs resident on an SM -- and on the whole GPU -- might
+    // run in lockstep, all of them loading from HBM at the same time, then all of them computing (time per tile looks like
+    // HBM time + FP64 time + transposition time).  The k-th CTA to arrive on each SM (k < CTAs per SM)
     // therefore waits k / (CTAs per SM) of a tile time, once; after that the CTA slots of the SM stay out of phase.
     __shared__ unsigned s_arrival;
     if (tid == 0) {
@@ -771,7 +771,9 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         for (int pi = 0; pi < P.n_passes; ++pi) fp += P.passes[pi].mma_off != NO_MMA ? 256 : 0;
         const double amp = dtype == QSV_C128 ? 1.0 : 0.5;
         const double clk = amp * (5800.0 + 4.0 * fp + 1000.0 * (P.n_passes - 1));
-        const int forced = env_int_regs("QSV_REGS_STAGGER_NS", -1);
+        // QSV_REGS_STAGGER_NS: 0 (default) = off, -1 = the estimate above, > 0 = nanoseconds per CTA slot.  Measured on B200
+        // (profiles/r1_ab_mma.txt): no effect at any setting -- the resident CTAs are not in lockstep; kept as an experiment.
+        const int forced = env_int_regs("QSV_REGS_STAGGER_NS", 0);
         const int ctas_per_sm = (dtype == QSV_C128 || rb == 3) ? 2 : 3;  // MINB of launch_regs_t
         P.stagger_ns = forced >= 0 ? (unsigned)forced : (unsigned)(clk / ctas_per_sm / 1.9);
     }
