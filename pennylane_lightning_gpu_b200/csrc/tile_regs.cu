@@ -733,10 +733,72 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
             if (v >> p & 1) o |= 1ull << gpos[p];
         return o;
     };
-    auto smem_cols = [&](const AffineMap &mp, int pi, unsigned short *thr, unsigned short *reg, unsigned short &c) {
-        for (int k = 0; k < ntb; ++k) thr[k] = (unsigned short)swz(mp.col[lay_t[pi][k]], SW);
-        for (int k = 0; k < rb; ++k) reg[k] = (unsigned short)swz(mp.col[lay_r[pi][k]], SW);
-        c = (unsigned short)swz(mp.c, SW);
+    // Shared-memory swizzle of one transposition: low SW bits ^= XOR over the set high bits p of lcol[p].  Every choice of
+    // lcol is a bijection; a warp-wide 128-bit (complex64: 64-bit) access is conflict-free when the first SW thread bits --
+    // the lanes of one access phase -- land on linearly independent low parts.  The store of pass p (with the folded
+    // permutations in its columns) and the load of pass p + 1 share the buffer, so one lcol must serve both lane sets.
+    struct Swizzle {
+        unsigned char lcol[RT_TB];
+    };
+    auto swz_with = [&](uint32_t v, const Swizzle &sw) {
+        uint32_t low = v & ((1u << SW) - 1u);
+        for (int p = SW; p < tb; ++p)
+            if (v >> p & 1) low ^= sw.lcol[p];
+        return (v & ~((1u << SW) - 1u)) | low;
+    };
+    auto default_swizzle = [&]() {
+        Swizzle sw;
+        for (int p = 0; p < tb; ++p) sw.lcol[p] = (unsigned char)(p < SW ? 0 : 1u << (p % SW));
+        return sw;
+    };
+    auto low_rank = [&](const uint32_t *vecs, int k, const Swizzle &sw) {  // rank over GF(2) of the swizzled low parts
+        uint32_t basis[8] = {0};
+        int rank = 0;
+        for (int i = 0; i < k; ++i) {
+            uint32_t v = swz_with(vecs[i], sw) & ((1u << SW) - 1u);
+            for (int b = SW - 1; b >= 0 && v; --b)
+                if (v >> b & 1) {
+                    if (basis[b])
+                        v ^= basis[b];
+                    else {
+                        basis[b] = v;
+                        ++rank;
+                        v = 0;
+                    }
+                }
+        }
+        return rank;
+    };
+    const bool tune_swizzle = env_flag("QSV_REGS_SWIZZLE_SEARCH", 1);
+    auto choose_swizzle = [&](const AffineMap &store_map, int p_store, int p_load) {
+        Swizzle best = default_swizzle();
+        if (!tune_swizzle) return best;
+        uint32_t sv_[4], lv_[4];
+        for (int i = 0; i < SW; ++i) {
+            sv_[i] = store_map.col[lay_t[p_store][i]];
+            lv_[i] = 1u << lay_t[p_load][i];
+        }
+        int best_score = low_rank(sv_, SW, best) + low_rank(lv_, SW, best);
+        uint32_t rng = 0x9e3779b9u;
+        for (int tries = 0; tries < 256 && best_score < 2 * SW; ++tries) {
+            Swizzle cand;
+            for (int p = 0; p < tb; ++p) {
+                rng = rng * 1664525u + 1013904223u;
+                cand.lcol[p] = (unsigned char)(p < SW ? 0 : (rng >> 24) & ((1u << SW) - 1u));
+            }
+            const int score = low_rank(sv_, SW, cand) + low_rank(lv_, SW, cand);
+            if (score > best_score) {
+                best_score = score;
+                best = cand;
+            }
+        }
+        return best;
+    };
+    auto smem_cols = [&](const AffineMap &mp, int pi, const Swizzle &sw, unsigned short *thr, unsigned short *reg,
+                         unsigned short &c) {
+        for (int k = 0; k < ntb; ++k) thr[k] = (unsigned short)swz_with(mp.col[lay_t[pi][k]], sw);
+        for (int k = 0; k < rb; ++k) reg[k] = (unsigned short)swz_with(mp.col[lay_r[pi][k]], sw);
+        c = (unsigned short)swz_with(mp.c, sw);
     };
     auto global_cols = [&](const AffineMap &mp, int pi, GlobalMap &g) {
         for (int k = 0; k < ntb; ++k) g.thr[k] = to_global(mp.col[lay_t[pi][k]]);
@@ -745,13 +807,16 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     };
     for (int pi = 0; pi < P.n_passes; ++pi) {
         RegPass &ps = P.passes[pi];
-        smem_cols(AffineMap(), pi, ps.ld_thr, ps.ld_reg, ps.ld_c);
         AffineMap after;  // permutations between this pass and the next: the value held for index e is stored at pi(e)
         for (int gi : slot_perms[pi + 1]) after.then(ng[gi]);
-        if (pi + 1 < P.n_passes)
-            smem_cols(after, pi, ps.st_thr, ps.st_reg, ps.st_c);
-        else
+        if (pi + 1 < P.n_passes) {
+            const Swizzle sw = choose_swizzle(after, pi, pi + 1);
+            smem_cols(after, pi, sw, ps.st_thr, ps.st_reg, ps.st_c);
+            RegPass &pn = P.passes[pi + 1];
+            smem_cols(AffineMap(), pi + 1, sw, pn.ld_thr, pn.ld_reg, pn.ld_c);
+        } else {
             global_cols(after, pi, P.gl_store);
+        }
     }
     {
         // slot 0: the first pass wants S'[e] = S[pi^-1(e)]; every folded permutation is an involution, so the inverse is the
