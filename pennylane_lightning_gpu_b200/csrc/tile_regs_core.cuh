@@ -73,24 +73,26 @@ struct RegProgram {
 };
 
 template <typename T> __host__ __device__ __forceinline__ const T *const_pool(const RegProgram &P);
-// where the unpredicated dense paths read their matrix from: the kernel-parameter constant bank (default) or the
-// shared-memory copy (-DQSV_PLAIN_SMEM, an A/B build)
+// where the unpredicated dense paths read their matrix from: the kernel-parameter constant bank (complex128) or the
+// shared-memory copy (complex64; -DQSV_PLAIN_SMEM forces it for both, an A/B build)
 template <typename T> __host__ __device__ __forceinline__ const T *plain_consts(const RegProgram &P, const T *spool);
 template <> __host__ __device__ __forceinline__ const double *const_pool<double>(const RegProgram &P) { return P.pool; }
 template <> __host__ __device__ __forceinline__ const float *const_pool<float>(const RegProgram &P) { return P.poolf; }
 template <typename T> __host__ __device__ __forceinline__ const T *plain_consts(const RegProgram &P, const T *spool) {
+    // measured on B200 (profiles/r1_ab_fold.txt): equal for complex128, shared memory 4 % faster for complex64
 #ifdef QSV_PLAIN_SMEM
     (void)P;
     return spool;
 #else
-    (void)spool;
-    return const_pool<T>(P);
+    if constexpr (sizeof(T) == 4) {
+        (void)P;
+        return spool;
+    } else {
+        (void)spool;
+        return const_pool<T>(P);
+    }
 #endif
 }
-
-template <typename T> struct Cx;
-template <> struct Cx<double> { using type = double2; static constexpr int SW = 3; };
-template <> struct Cx<float> { using type = float2; static constexpr int SW = 4; };
 
 // XOR swizzle of the shared-memory tile: the low SW bits (one 128-byte line) are XORed with every higher
 // SW-bit field, so that lanes differing in any bits with distinct positions mod SW hit distinct banks.
