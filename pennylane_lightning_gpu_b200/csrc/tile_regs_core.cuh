@@ -94,6 +94,10 @@ template <typename T> __host__ __device__ __forceinline__ const T *plain_consts(
 #endif
 }
 
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; static constexpr int SW = 3; };
+template <> struct Cx<float> { using type = float2; static constexpr int SW = 4; };
+
 // XOR swizzle of the shared-memory tile: the low SW bits (one 128-byte line) are XORed with every higher
 // SW-bit field, so that lanes differing in any bits with distinct positions mod SW hit distinct banks.
 __host__ __device__ __forceinline__ uint32_t swz(uint32_t e, int sw) {
