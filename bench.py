@@ -275,7 +275,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": sweep_bytes if fused else None,
                 "traffic_source": ("ncu dram__bytes_read+write per fused sweep launch = 34.3 GB = 2*B*N at 30q c128 "
-                                   "(profiles/r1_ncu_regs_summary.txt)") if fused else
+                                   "(profiles/r1_ncu_regs_final_summary.txt)") if fused else
                                   "ncu: 34.4 GB per full-state gate launch (profiles/r1_ncu_summary.txt); controlled gates move less",
                 "kernel": fused_kernel if fused else "k_apply_dense / k_apply_diag (one sweep per gate)",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
