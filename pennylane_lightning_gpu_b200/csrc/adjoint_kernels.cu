@@ -28,7 +28,8 @@ struct GenDesc {
                          // 2: Pauli word (X/Y letters on tile bits, Z letters anywhere)
     int slot;            // complex output slot
     unsigned tbit;       // kind 1: tile-local position of the target bit; kind 2: tile-local flip mask
-    unsigned pad0;
+    unsigned pad0;       // kind 0: bits 0-2 = parity mask on the thread's three amplitude-index bits (tile bits 8..10), bit 8 =
+                         // a control sits on one of them (generic per-amplitude path)
     uint64_t ctrl;       // global bits that must be 1
     uint64_t zmask;      // kind 0 / 2: global bits whose parity selects the phase / the sign
     uint64_t xg;         // kind 2: flip mask on global bits
@@ -69,28 +70,68 @@ __global__ void __launch_bounds__(GT_NT)
     }
     __syncthreads();
 
-    // t0 = conj(bra_i) * ket_i of the thread's own amplitudes: shared by every diagonal / parity generator
-    double t0r[GT_EPT], t0i[GT_EPT];
+    // Diagonal / parity generators: conj(b_i) * p(i) * k_i with t0_i = conj(b_i) * k_i shared by all of them.  The thread's
+    // 8 amplitudes differ in tile bits 8..10 (j = 0..7), everything else of the index is thread-constant, so
+    //   sum_j p(parity_j) t0_j = e_a * (W[0] + W[m]) / 2 + e_b * (W[0] - W[m]) / 2,   W[m] = sum_j (-1)^{popc(j & m)} t0_j
+    // with m = the generator's parity mask restricted to the three j bits and (e_a, e_b) = the two phases ordered by the
+    // thread-constant part of the parity: one Walsh-Hadamard transform per thread, then ~12 FP64 operations per generator
+    // instead of ~8 per generator AND amplitude.
+    double Wr[GT_EPT], Wi[GT_EPT];
 #pragma unroll
     for (int j = 0; j < GT_EPT; ++j) {
         const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
-        t0r[j] = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
-        t0i[j] = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
+        Wr[j] = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
+        Wi[j] = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
     }
+#pragma unroll
+    for (int h = 1; h < GT_EPT; h <<= 1)
+#pragma unroll
+        for (int j = 0; j < GT_EPT; ++j)
+            if (!(j & h)) {
+                const double ar = Wr[j], ai = Wi[j], br = Wr[j | h], bi = Wi[j | h];
+                Wr[j] = ar + br;
+                Wi[j] = ai + bi;
+                Wr[j | h] = ar - br;
+                Wi[j | h] = ai - bi;
+            }
 
     for (int k = 0; k < P.n_gens; ++k) {
         const GenDesc &g = P.g[k];
         double re = 0.0, im = 0.0;
-        if (g.kind == 0) {
-            // conj(b_i) * p(i) * k_i = p(i) * t0_i
+        if (g.kind == 0 && (g.pad0 >> 8) == 0u) {
+            // no control on a j bit: the control test is thread-constant too (gidx[0] has the j bits clear)
+            if ((gidx[0] & g.ctrl) == g.ctrl) {
+                const unsigned m = g.pad0 & 7u;
+                double wr, wi;
+                switch (m) {  // CTA-uniform
+                case 0: wr = Wr[0]; wi = Wi[0]; break;
+                case 1: wr = Wr[1]; wi = Wi[1]; break;
+                case 2: wr = Wr[2]; wi = Wi[2]; break;
+                case 3: wr = Wr[3]; wi = Wi[3]; break;
+                case 4: wr = Wr[4]; wi = Wi[4]; break;
+                case 5: wr = Wr[5]; wi = Wi[5]; break;
+                case 6: wr = Wr[6]; wi = Wi[6]; break;
+                default: wr = Wr[7]; wi = Wi[7]; break;
+                }
+                const bool odd = __popcll(gidx[0] & g.zmask) & 1;
+                const double ear = odd ? g.m[2] : g.m[0], eai = odd ? g.m[3] : g.m[1];
+                const double ebr = odd ? g.m[0] : g.m[2], ebi = odd ? g.m[1] : g.m[3];
+                const double Ar = 0.5 * (Wr[0] + wr), Ai = 0.5 * (Wi[0] + wi);
+                const double Br = 0.5 * (Wr[0] - wr), Bi = 0.5 * (Wi[0] - wi);
+                re = ear * Ar - eai * Ai + ebr * Br - ebi * Bi;
+                im = ear * Ai + eai * Ar + ebr * Bi + ebi * Br;
+            }
+        } else if (g.kind == 0) {
             const double e0r = g.m[0], e0i = g.m[1], e1r = g.m[2], e1i = g.m[3];
 #pragma unroll
             for (int j = 0; j < GT_EPT; ++j) {
                 if ((gidx[j] & g.ctrl) != g.ctrl) continue;
                 const bool odd = __popcll(gidx[j] & g.zmask) & 1;
                 const double pr = odd ? e1r : e0r, pi = odd ? e1i : e0i;
-                re += pr * t0r[j] - pi * t0i[j];
-                im += pr * t0i[j] + pi * t0r[j];
+                const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
+                const double yr = pr * (double)x.x - pi * (double)x.y, yi = pr * (double)x.y + pi * (double)x.x;
+                re += (double)b[j].x * yr + (double)b[j].y * yi;
+                im += (double)b[j].x * yi - (double)b[j].y * yr;
             }
         } else if (g.kind == 2) {
             // (P ket)_i = i^ny * (-1)^{popc(j & z)} * ket_j with j = i ^ x (optionally only where the control bits are set:
@@ -215,9 +256,20 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
             tile_bits.push_back(hi[j]);
         }
         P.tile_holes = make_holes(tile_bits.data(), (int)tile_bits.size(), 0);
+        static_assert(GT_TB - 3 >= GT_L, "the three per-thread amplitude bits are high tile bits");
         for (GenItem &it : take) {
             GenDesc &d = P.g[P.n_gens++];
             d = it.d;
+            if (d.kind == 0) {
+                // tile bits GT_TB-3 .. GT_TB-1 distinguish the 8 amplitudes of a thread (e = tid + 256 * j)
+                unsigned m = 0, cj = 0;
+                for (int q = 0; q < 3; ++q) {
+                    const int gbit = tile_bits[GT_TB - 3 + q];
+                    m |= (unsigned)((d.zmask >> gbit) & 1ull) << q;
+                    cj |= (unsigned)((d.ctrl >> gbit) & 1ull);
+                }
+                d.pad0 = m | (cj << 8);
+            }
             if (d.kind == 1) {
                 d.tbit = (unsigned)pos[it.tgt];
             } else if (d.kind == 2) {
