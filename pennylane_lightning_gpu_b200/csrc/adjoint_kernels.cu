@@ -21,6 +21,7 @@ namespace {
 constexpr int GT_TB = 11;        // tile bits: 2^11 amplitudes of ket in shared memory (32 KiB complex128)
 constexpr int GT_NT = 256;
 constexpr int GT_EPT = (1 << GT_TB) / GT_NT;  // 8 amplitudes per thread
+static_assert(GT_EPT == 8 && GT_NT == 256, "the kernel's index split assumes e = tid + 256 * j with j < 8");
 constexpr int GT_MAX = 32;       // generators per launch
 
 struct GenDesc {
@@ -57,14 +58,18 @@ __global__ void __launch_bounds__(GT_NT)
     for (int i = tid; i < 2 * GT_MAX; i += GT_NT) (&s_acc[0][0])[i] = 0.0;
 
     // element e of the tile (local index) lives at global index base | deposit(e)
+    // (e = tid + 256 * j: the thread part of the deposit is computed once, the three j bits are CTA-uniform columns)
     A b[GT_EPT];
     uint64_t gidx[GT_EPT];
+    uint64_t dep_tid = (uint32_t)tid & ((1u << P.L) - 1u);
+    for (int q = P.L; q < GT_TB - 3; ++q) dep_tid |= (uint64_t)(((uint32_t)tid >> q) & 1u) << P.hi_bits[q - P.L];
+    dep_tid |= base;
+    const uint64_t cj0 = 1ull << P.hi_bits[GT_TB - 3 - P.L], cj1 = 1ull << P.hi_bits[GT_TB - 2 - P.L],
+                   cj2 = 1ull << P.hi_bits[GT_TB - 1 - P.L];
 #pragma unroll
     for (int j = 0; j < GT_EPT; ++j) {
         const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
-        uint64_t off = e & ((1u << P.L) - 1u);
-        for (int q = P.L; q < GT_TB; ++q) off |= (uint64_t)((e >> q) & 1u) << P.hi_bits[q - P.L];
-        gidx[j] = base | off;
+        gidx[j] = dep_tid | ((j & 1) ? cj0 : 0ull) | ((j & 2) ? cj1 : 0ull) | ((j & 4) ? cj2 : 0ull);
         s[e] = reinterpret_cast<const A *>(ket)[gidx[j]];
         b[j] = reinterpret_cast<const A *>(bra)[gidx[j]];
     }
