@@ -360,8 +360,9 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers ----------------------------------
     e2e = None
-    if not distributed and args.e2e:
-        e2e = end_to_end(torch, q, sv, buf, ops, n_local, cdtype, tdtype, amp_bytes, alg_bytes_total, args)
+    if args.e2e:
+        e2e = end_to_end(torch, q, sv, buf, ops, n_local, cdtype, tdtype, amp_bytes, alg_bytes_total, args,
+                         dist if distributed else None)
 
     line = None
     if rank == 0:
@@ -592,18 +593,33 @@ def sparse_config4(torch, q, args):
             "pauli_words_call_s": t_pw, "algorithmic_gb": alg / 1e9}
 
 
-def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, args):
-    """StatePrep(host state) -> circuit -> <Z0> on the host, all through the public API."""
+def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, args, dist=None):
+    """StatePrep(host state) -> circuit -> <Z0> on the host, all through the public API.  On a sharded register every
+    rank uploads its own shard from its own pinned buffer (CopyHostDataToGpu of StateVectorCudaMPI), the expectation
+    value is all-reduced; the time is the slowest rank's."""
+    world = dist.get_world_size() if dist is not None else 1
+    ok = 1
     try:
         host = torch.empty(1 << n, dtype=tdtype, pin_memory=True)
     except RuntimeError:
+        ok = 0
+    if dist is not None:  # all ranks or none: a rank that dropped out would leave the others in a collective
+        flag = torch.tensor([ok], dtype=torch.int32, device=buf.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag)
+    if not ok:
         return None
     host.copy_(torch.view_as_complex(buf.view(-1, 2)))
     torch.cuda.synchronize()
     host_np = host.numpy()
     z0 = q.Observable.named("PauliZ", [0])
-    h2d = host_np.nbytes + sum(16 * len(np.atleast_1d(op.get("params", ()))) + (op["matrix"].nbytes if "matrix" in op else 0)
-                               for op in ops)
+    h2d = world * host_np.nbytes + sum(16 * len(np.atleast_1d(op.get("params", ()))) +
+                                       (op["matrix"].nbytes if "matrix" in op else 0) for op in ops)
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
 
     def step():
         sv.h2d(host_np)                      # HostToDevice of the prepared state (lightning_gpu.py:392-447)
@@ -612,14 +628,18 @@ def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, 
         return sv.expval(z0)                 # one double back to the host
 
     step()
-    torch.cuda.synchronize()
     k = max(1, min(args.steps, 3))
+    sync()
     t0 = time.perf_counter()
     for _ in range(k):
         val = step()
-    torch.cuda.synchronize()
+    sync()
     dt = (time.perf_counter() - t0) / k
-    return {"value": alg_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=buf.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t)
+    return {"value": alg_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * world,
             "ms_per_step": dt * 1e3, "result_check": float(val)}
 
 

@@ -15,6 +15,7 @@
 //     in flight per thread (Little's law: ~35 KB in flight per SM saturates HBM3e);
 //   * the matrix travels in the kernel parameter bank (constant cache, uniform operands).
 #include <algorithm>
+#include <type_traits>
 
 #include "device_utils.cuh"
 #include "qsv_internal.h"
@@ -261,6 +262,15 @@ unsigned grid_for(uint64_t items, uint64_t per_block) {
     return (unsigned)std::max<uint64_t>(g, 1);
 }
 
+int env_shape(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// launch shape of the single-target dense kernel; read on every launch so that an A/B can switch it inside one process
+constexpr int DENSE1_DEFAULT_SHAPE = 5;  // U=8, NT=128: +14 % over U=4, NT=256 (profiles/r1_ab_dense1.txt)
+int dense1_shape() { return env_shape("QSV_DENSE1_SHAPE", DENSE1_DEFAULT_SHAPE); }
+
 template <typename T, int K, int V>
 void launch_dense_t(State &sv, const LoweredGate &g, void *const *table, int n_vecs) {
     const int shift = V == 2 ? 1 : 0;
@@ -278,9 +288,39 @@ void launch_dense_t(State &sv, const LoweredGate &g, void *const *table, int n_v
     // groups per thread / threads per block by block size (register budget)
     constexpr int U = K == 0 ? 8 : (K == 1 ? 4 : (K == 2 ? 2 : 1));
     constexpr int NT = K <= 2 ? 256 : 128;
-    dim3 grid(grid_for(n_groups, (uint64_t)NT * U), (unsigned)n_vecs);
-    k_apply_dense<T, K, V, U, NT><<<grid, NT, 0, sv.stream>>>(table ? nullptr : sv.data, table, n_groups,
-                                                             holes, g.ctrl_mask >> shift, offs, m);
+    const uint64_t ctrl = g.ctrl_mask >> shift;
+    void *single = table ? nullptr : sv.data;
+    auto go = [&](auto u_tag, auto nt_tag) {
+        constexpr int UU = decltype(u_tag)::value, NN = decltype(nt_tag)::value;
+        dim3 grid(grid_for(n_groups, (uint64_t)NN * UU), (unsigned)n_vecs);
+        k_apply_dense<T, K, V, UU, NN><<<grid, NN, 0, sv.stream>>>(single, table, n_groups, holes, ctrl, offs, m);
+    };
+    using std::integral_constant;
+    if constexpr (K == 1 && V == 2 && std::is_same_v<T, double>) {
+        // A/B only (QSV_DENSE1_SHAPE=8): two neighbouring complex128 amplitudes per 256-bit access
+        go(integral_constant<int, 2>{}, integral_constant<int, 256>{});
+    } else if constexpr (K == 1) {
+        // launch shape of the single-target kernel (QSV_DENSE1_SHAPE, tools/ab_dense1.py, profiles/r1_ab_dense1.txt)
+        switch (dense1_shape()) {
+        case 0: go(integral_constant<int, 4>{}, integral_constant<int, 256>{}); break;
+        case 1: go(integral_constant<int, 2>{}, integral_constant<int, 256>{}); break;
+        case 2: go(integral_constant<int, 8>{}, integral_constant<int, 256>{}); break;
+        case 3: go(integral_constant<int, 4>{}, integral_constant<int, 128>{}); break;
+        case 4: go(integral_constant<int, 2>{}, integral_constant<int, 512>{}); break;
+        case 6: go(integral_constant<int, 1>{}, integral_constant<int, 512>{}); break;
+        default: go(integral_constant<int, 8>{}, integral_constant<int, 128>{}); break;  // 5, and 7 / 8 after their re-routing
+        }
+    } else if constexpr (K == 2) {
+        // QSV_DENSE2_SHAPE (tools/ab_shapes2.py): U=4, NT=128 is level with U=2, NT=256 on high bits, +12 % on bits 1 and 2
+        switch (env_shape("QSV_DENSE2_SHAPE", 1)) {
+        case 0: go(integral_constant<int, 2>{}, integral_constant<int, 256>{}); break;
+        case 2: go(integral_constant<int, 1>{}, integral_constant<int, 256>{}); break;
+        case 3: go(integral_constant<int, 2>{}, integral_constant<int, 128>{}); break;
+        default: go(integral_constant<int, 4>{}, integral_constant<int, 128>{}); break;
+        }
+    } else {
+        go(integral_constant<int, U>{}, integral_constant<int, NT>{});
+    }
     QSV_CUDA(cudaGetLastError());
 }
 
@@ -309,10 +349,20 @@ void launch_dense_bit0(State &sv, const LoweredGate &g, void *const *table, int 
         m.re[j] = (T)g.mat[j].real();
         m.im[j] = (T)g.mat[j].imag();
     }
-    constexpr int U = 4, NT = 256;
-    dim3 grid(grid_for(n_elems, (uint64_t)NT * U), (unsigned)n_vecs);
-    k_apply_dense_bit0<T, U, NT><<<grid, NT, 0, sv.stream>>>(table ? nullptr : sv.data, table, n_elems, holes,
-                                                            g.ctrl_mask >> 1, m);
+    void *single = table ? nullptr : sv.data;
+    auto go = [&](auto u_tag, auto nt_tag) {
+        constexpr int U = decltype(u_tag)::value, NT = decltype(nt_tag)::value;
+        dim3 grid(grid_for(n_elems, (uint64_t)NT * U), (unsigned)n_vecs);
+        k_apply_dense_bit0<T, U, NT><<<grid, NT, 0, sv.stream>>>(single, table, n_elems, holes, g.ctrl_mask >> 1, m);
+    };
+    using std::integral_constant;
+    // QSV_BIT0_SHAPE (tools/ab_shapes2.py): U=8, NT=128 +7 % over U=4, NT=256
+    switch (env_shape("QSV_BIT0_SHAPE", 1)) {
+    case 0: go(integral_constant<int, 4>{}, integral_constant<int, 256>{}); break;
+    case 2: go(integral_constant<int, 2>{}, integral_constant<int, 256>{}); break;
+    case 3: go(integral_constant<int, 8>{}, integral_constant<int, 256>{}); break;
+    default: go(integral_constant<int, 8>{}, integral_constant<int, 128>{}); break;
+    }
     QSV_CUDA(cudaGetLastError());
 }
 
@@ -363,11 +413,49 @@ void launch_diag_t(State &sv, const LoweredGate &g, void *const *table, int n_ve
         d.re[i] = (T)g.mat[i].real();
         d.im[i] = (T)g.mat[i].imag();
     }
-    constexpr int U = 4, NT = 256;
-    dim3 grid(grid_for(n_items, (uint64_t)NT * U), (unsigned)n_vecs);
-    k_apply_diag<T, V, U, NT><<<grid, NT, 0, sv.stream>>>(table ? nullptr : sv.data, table, n_items, holes,
-                                                         g.ctrl_mask >> shift, d);
+    void *single = table ? nullptr : sv.data;
+    auto go = [&](auto u_tag, auto nt_tag) {
+        constexpr int U = decltype(u_tag)::value, NT = decltype(nt_tag)::value;
+        dim3 grid(grid_for(n_items, (uint64_t)NT * U), (unsigned)n_vecs);
+        k_apply_diag<T, V, U, NT><<<grid, NT, 0, sv.stream>>>(single, table, n_items, holes, g.ctrl_mask >> shift, d);
+    };
+    using std::integral_constant;
+    // QSV_DIAG_SHAPE (tools/ab_shapes2.py): U=8, NT=256 +1 % (RZ) / +4 % (CZ) over U=4, NT=256
+    switch (env_shape("QSV_DIAG_SHAPE", 2)) {
+    case 0: go(integral_constant<int, 4>{}, integral_constant<int, 256>{}); break;
+    case 1: go(integral_constant<int, 8>{}, integral_constant<int, 128>{}); break;
+    case 3: go(integral_constant<int, 2>{}, integral_constant<int, 256>{}); break;
+    default: go(integral_constant<int, 8>{}, integral_constant<int, 256>{}); break;
+    }
     QSV_CUDA(cudaGetLastError());
+}
+
+bool dense1_pairs_up() { return dense1_shape() == 7; }
+
+// (2x2 gate on bit t) -> (gate (x) identity) on bits (t, s), s = the nearest free bit below t (else above), s >= lowest
+LoweredGate pair_up(const LoweredGate &g, int n, int lowest) {
+    const uint64_t tb = g.offs[1] ^ g.offs[0];
+    int t = 0;
+    while (!((tb >> t) & 1ull)) ++t;
+    auto used = [&](int b) { return std::find(g.holes.begin(), g.holes.end(), b) != g.holes.end(); };
+    int s = -1;
+    for (int b = t - 1; b >= lowest && s < 0; --b)
+        if (!used(b)) s = b;
+    for (int b = t + 1; b < n && s < 0; ++b)
+        if (!used(b)) s = b;
+    QSV_CHECK(s >= 0, "internal: no free bit to pair a single-target gate with");
+    LoweredGate r = g;
+    r.k = 2;
+    r.holes.push_back(s);
+    std::sort(r.holes.begin(), r.holes.end());
+    r.offs.assign(4, 0);
+    for (int c = 0; c < 4; ++c) r.offs[c] = g.offs[c >> 1] | ((uint64_t)(c & 1) << s);
+    r.mat.assign(16, cplx(0.0, 0.0));
+    for (int a = 0; a < 2; ++a)
+        for (int a2 = 0; a2 < 2; ++a2)
+            for (int b = 0; b < 2; ++b) r.mat[((a << 1) | b) * 4 + ((a2 << 1) | b)] = g.mat[a * 2 + a2];
+    r.tgt_bits.clear();
+    return r;
 }
 
 void launch_any(State &sv, const LoweredGate &g, void *const *table, int n_vecs) {
@@ -392,7 +480,20 @@ void launch_any(State &sv, const LoweredGate &g, void *const *table, int n_vecs)
                 launch_dense_bit0<double>(sv, g, table, n_vecs);
             return;
         }
-        if (!f32)
+        if (g.k == 1 && dense1_pairs_up() && (int)g.holes.size() < sv.n - (f32 && !bit0 ? 1 : 0)) {
+            // A/B (QSV_DENSE1_SHAPE=7): run the 2x2 gate as (gate (x) identity) on the target and a free neighbour bit
+            const LoweredGate g2 = pair_up(g, sv.n, f32 && !bit0 ? 1 : 0);
+            if (!f32)
+                launch_dense_k<double, 1>(sv, g2, table, n_vecs);
+            else if (bit0)
+                launch_dense_k<float, 1>(sv, g2, table, n_vecs);
+            else
+                launch_dense_k<float, 2>(sv, g2, table, n_vecs);
+            return;
+        }
+        if (!f32 && g.k == 1 && !bit0 && sv.n >= 2 && dense1_shape() == 8)
+            launch_dense_t<double, 1, 2>(sv, g, table, n_vecs);  // A/B: two neighbouring amplitudes per 256-bit access
+        else if (!f32)
             launch_dense_k<double, 1>(sv, g, table, n_vecs);
         else if (bit0 || sv.n < 1)
             launch_dense_k<float, 1>(sv, g, table, n_vecs);

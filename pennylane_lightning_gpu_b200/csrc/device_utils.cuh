@@ -29,6 +29,10 @@ template <typename T, int V> struct VecOf;
 template <> struct VecOf<double, 1> { using type = double2; };
 template <> struct VecOf<float, 1> { using type = float2; };
 template <> struct VecOf<float, 2> { using type = float4; };
+struct alignas(32) Double4 {
+    double x, y, z, w;
+};
+template <> struct VecOf<double, 2> { using type = Double4; };  // 256-bit access (LDG.E.ENL2.256), see load_elem below
 
 template <typename T, int V>
 __device__ __forceinline__ void load_elem(T (&c)[2 * V], const void *base, uint64_t idx) {
@@ -42,6 +46,13 @@ __device__ __forceinline__ void load_elem(T (&c)[2 * V], const void *base, uint6
     }
 }
 
+// two neighbouring complex128 amplitudes with one 256-bit access
+template <>
+__device__ __forceinline__ void load_elem<double, 2>(double (&c)[4], const void *base, uint64_t idx) {
+    const double *p = reinterpret_cast<const double *>(base) + 4 * idx;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c[0]), "=d"(c[1]), "=d"(c[2]), "=d"(c[3]) : "l"(p));
+}
+
 template <typename T, int V>
 __device__ __forceinline__ void store_elem(void *base, uint64_t idx, const T (&c)[2 * V]) {
     using VT = typename VecOf<T, V>::type;
@@ -53,6 +64,12 @@ __device__ __forceinline__ void store_elem(void *base, uint64_t idx, const T (&c
         v.w = c[3];
     }
     reinterpret_cast<VT *>(base)[idx] = v;
+}
+
+template <>
+__device__ __forceinline__ void store_elem<double, 2>(void *base, uint64_t idx, const double (&c)[4]) {
+    double *p = reinterpret_cast<double *>(base) + 4 * idx;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(c[0]), "d"(c[1]), "d"(c[2]), "d"(c[3]) : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -113,6 +113,19 @@ class DistributedStateVector:
         _check(lib().qsv_dist_set_state_vector(self.local._h, ia.ctypes.data_as(_cabi._I64P), va.ctypes.data_as(_cabi._P),
                                                len(ia)))
 
+    def h2d(self, shard):
+        """This rank's shard from host memory, canonical layout (CopyHostDataToGpu of StateVectorCudaMPI); resets the
+        qubit map.  Collective in the sense that every rank has to call it."""
+        a = np.ascontiguousarray(shard, dtype=self.local.np_dtype).reshape(-1)
+        _check(lib().qsv_dist_h2d(self.local._h, a.ctypes.data_as(_cabi._P), a.size))
+
+    def d2h(self, out: np.ndarray | None = None) -> np.ndarray:
+        """This rank's shard in the canonical layout (CopyGpuDataToHost of StateVectorCudaMPI)."""
+        if out is None:
+            out = np.empty(1 << self.n_local, dtype=self.local.np_dtype)
+        _check(lib().qsv_dist_d2h(self.local._h, out.ctypes.data_as(_cabi._P), out.size))
+        return out
+
     def apply(self, name: str, wires, params=(), adjoint=False, matrix=None):
         """One gate on the whole register (applyOperation, MPI.hpp:392-470)."""
         self.apply_ops(Ops([{"name": name, "wires": list(wires), "params": list(params), "adjoint": adjoint,
