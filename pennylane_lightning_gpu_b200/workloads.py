@@ -58,6 +58,21 @@ def gate_bytes(op: dict, n: int, amp_bytes: int) -> int:
     return 2 * amp_bytes * (1 << n) >> n_ctrl
 
 
+_DIAGONAL = {"Identity", "PauliZ", "S", "T", "PhaseShift", "RZ", "CZ", "CRZ", "ControlledPhaseShift", "IsingZZ", "MultiRZ"}
+_N_CONTROLS = {"CNOT": 1, "CY": 1, "CRX": 1, "CRY": 1, "CRot": 1, "Toffoli": 2, "CSWAP": 1}
+
+
+def gate_bit_masks(op: dict, n: int) -> tuple[int, int]:
+    """(dense, diag): index bits (bit = n - 1 - wire) a gate changes / only looks at (controls, phases).  Two gates
+    commute structurally when they share no bit or only bits on which both are diagonal; a sharded register needs
+    the dense bits local and nothing else (csrc/dist.cu: gate_bit_masks)."""
+    bits = [n - 1 - int(w) for w in op["wires"]]
+    if op["name"] in _DIAGONAL:
+        return 0, sum(1 << b for b in bits)
+    c = _N_CONTROLS.get(op["name"], 0)
+    return sum(1 << b for b in bits[c:]), sum(1 << b for b in bits[:c])
+
+
 def hardware_efficient_ansatz(n: int, layers: int = 4, seed: int = 11):
     """C3: layers x [RY, RZ on every wire; CNOT(i, i+1) ladder]."""
     rng = np.random.default_rng(seed)

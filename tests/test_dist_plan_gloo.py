@@ -116,21 +116,22 @@ def _worker(rank, world, port, n_total, seed, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_swap_plan_reproduces_full_state_with_gloo(world):
+@pytest.mark.parametrize("world,dag", [(2, 1), (2, 0), (4, 1)])
+def test_swap_plan_reproduces_full_state_with_gloo(world, dag, monkeypatch):
     from pennylane_lightning_gpu_b200 import _build
 
     _build.build_lib()
+    monkeypatch.setenv("QSV_DIST_DAG", str(dag))  # inherited by the spawned ranks
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + os.getpid() % 2000
+    port = 29500 + (os.getpid() + 7 * world + dag) % 2000
     mp.spawn(_worker, args=(world, port, 7, 11, ret), nprocs=world, join=True)
     assert ret["ok"]
     assert ret["n_gates"] == 44
     assert 0 < ret["n_swaps"] < 20
 
 
-def test_plan_properties():
+def test_plan_properties(monkeypatch):
     """No exchange for controls / diagonal gates on global wires; dense targets are local when applied."""
     from pennylane_lightning_gpu_b200 import Ops, _build
     from pennylane_lightning_gpu_b200.distributed import plan
@@ -141,17 +142,92 @@ def test_plan_properties():
             {"name": "CNOT", "wires": [2, 5]}, {"name": "IsingZZ", "wires": [0, 1], "params": [0.1]},
             {"name": "PhaseShift", "wires": [0], "params": [0.4]}, {"name": "Toffoli", "wires": [0, 1, 9]},
             {"name": "MultiRZ", "wires": [0, 1, 2, 3], "params": [0.5]}, {"name": "CRZ", "wires": [5, 0], "params": [0.3]}]
-    steps, fm = plan(Ops(free), n_total, n_local)
-    assert all(s[0] == "gate" for s in steps) and fm == list(range(n_total))
-    # a dense target on global wire 0 (bit 9) costs exactly one exchange, and stays local afterwards
-    ops = [{"name": "RX", "wires": [0], "params": [0.1]}, {"name": "RY", "wires": [0], "params": [0.2]},
-           {"name": "Hadamard", "wires": [0]}]
-    steps, fm = plan(Ops(ops), n_total, n_local)
-    assert [s[0] for s in steps] == ["swap", "gate", "gate", "gate"]
-    assert steps[0][1] == 9 and fm[9] == steps[0][2] and steps[0][2] >= n_local - 8
-    # Belady: the evicted qubit is the one needed latest
-    ops = [{"name": "RX", "wires": [0], "params": [0.1]}] + \
-          [{"name": "RX", "wires": [w], "params": [0.1]} for w in (3, 4, 5, 6, 7, 8)]  # bits 6..1 used soon
-    steps, fm = plan(Ops(ops), n_total, n_local)
-    assert steps[0][0] == "swap" and steps[0][2] == 0  # bit 0 (wire 9) is never used again
-    assert sum(1 for s in steps if s[0] == "swap") == 1
+    rx_chain = [{"name": "RX", "wires": [0], "params": [0.1]}, {"name": "RY", "wires": [0], "params": [0.2]},
+                {"name": "Hadamard", "wires": [0]}]
+    belady = [{"name": "RX", "wires": [0], "params": [0.1]}] + \
+             [{"name": "RX", "wires": [w], "params": [0.1]} for w in (3, 4, 5, 6, 7, 8)]  # bits 6..1 used soon
+    for dag in ("0", "1"):
+        monkeypatch.setenv("QSV_DIST_DAG", dag)
+        steps, fm = plan(Ops(free), n_total, n_local)
+        assert all(s[0] == "gate" for s in steps) and fm == list(range(n_total))
+        assert sorted(s[1] for s in steps) == list(range(len(free)))
+        # a dense target on global wire 0 (bit 9) costs exactly one exchange, and stays local afterwards
+        steps, fm = plan(Ops(rx_chain), n_total, n_local)
+        assert steps == [("swap", 9, steps[0][2]), ("gate", 0), ("gate", 1), ("gate", 2)]
+        assert fm[9] == steps[0][2] and steps[0][2] >= n_local - 8
+        steps, fm = plan(Ops(belady), n_total, n_local)
+        assert sum(1 for s in steps if s[0] == "swap") == 1
+        if dag == "0":
+            # program order, Belady: the evicted qubit is the one needed latest -- bit 0 (wire 9) is never used again
+            assert steps[0][0] == "swap" and steps[0][2] == 0
+        else:
+            # dependency order: everything that is local runs first, the exchange comes last
+            assert [s[0] for s in steps] == ["gate"] * 6 + ["swap", "gate"] and steps[-1] == ("gate", 0)
+
+
+def _n_swaps(steps):
+    return sum(1 for s in steps if s[0] == "swap")
+
+
+def _check_plan(ops, steps, final_map, n_total, n_local):
+    """Every gate exactly once, dense targets local when it runs, non-commuting pairs in program order."""
+    from pennylane_lightning_gpu_b200 import workloads
+
+    phys = list(range(n_total))
+    log = list(range(n_total))
+    pos = {}
+    for k, st in enumerate(steps):
+        if st[0] == "swap":
+            _, gp, l = st
+            assert gp >= n_local > l >= 0
+            a, b = log[gp], log[l]
+            log[gp], log[l] = b, a
+            phys[a], phys[b] = l, gp
+        else:
+            i = st[1]
+            assert i not in pos
+            pos[i] = k
+            dense, _ = workloads.gate_bit_masks(ops[i], n_total)
+            for b in range(n_total):
+                if dense >> b & 1:
+                    assert phys[b] < n_local, (i, ops[i], b)
+    assert sorted(pos) == list(range(len(ops))) and phys == final_map
+    masks = [workloads.gate_bit_masks(op, n_total) for op in ops]
+    for i in range(len(ops)):
+        for j in range(i):
+            conflict = (masks[i][0] & (masks[j][0] | masks[j][1])) or (masks[i][1] & masks[j][0])
+            if conflict:
+                assert pos[j] < pos[i], (j, i, ops[j], ops[i])
+
+
+@pytest.mark.parametrize("n_total,n_local", [(31, 30), (32, 30), (33, 30), (36, 33), (12, 6)])
+def test_dependency_order_needs_fewer_exchanges(n_total, n_local, monkeypatch):
+    """The bench circuits (config 2 / config 5 sizes): the dependency-ordered schedule is valid and never needs more
+    exchanges than the program-order schedule; at 4 and 8 GPUs it needs fewer."""
+    from pennylane_lightning_gpu_b200 import Ops, _build, workloads
+    from pennylane_lightning_gpu_b200.distributed import plan
+
+    _build.build_lib()
+    ops = workloads.random_gate_circuit(n_total, 200, 2024)
+    rec = Ops(ops)
+    monkeypatch.setenv("QSV_DIST_DAG", "0")
+    s0, f0 = plan(rec, n_total, n_local)
+    monkeypatch.setenv("QSV_DIST_DAG", "1")
+    s1, f1 = plan(rec, n_total, n_local)
+    _check_plan(ops, s0, f0, n_total, n_local)
+    _check_plan(ops, s1, f1, n_total, n_local)
+    assert _n_swaps(s1) <= _n_swaps(s0)
+    if n_total - n_local >= 2:
+        assert _n_swaps(s1) < _n_swaps(s0)
+
+
+def test_cyclic_use_of_more_qubits_than_fit():
+    """Four qubits used round-robin with three local slots: program order exchanges every round, the dependency
+    order (all RX gates commute across wires) exchanges once."""
+    from pennylane_lightning_gpu_b200 import Ops, _build
+    from pennylane_lightning_gpu_b200.distributed import plan
+
+    _build.build_lib()
+    ops = [{"name": "RX", "wires": [w], "params": [0.1 * (r + 1)]} for r in range(4) for w in range(4)]
+    steps, _ = plan(Ops(ops), 4, 3)
+    assert _n_swaps(steps) == 1
