@@ -235,6 +235,10 @@ int qsv_dist_uses_peer_access(const qsv_state *local);
  * (kind, a, b): kind 0 = swap physical global bit a with local bit b, kind 1 = apply op number a */
 int qsv_dist_plan(const qsv_ops *ops, int n_total, int n_local, int *steps, int max_steps, int *n_steps,
                   int *final_phys_of_logical_bit);
+/* the same, starting from a given qubit map (initial_phys_of_logical_bit[n_total], NULL = identity): what a second
+ * qsv_dist_apply_ops on the same register would do, since the map persists between calls */
+int qsv_dist_plan_from(const qsv_ops *ops, int n_total, int n_local, const int *initial_phys_of_logical_bit, int *steps,
+                       int max_steps, int *n_steps, int *final_phys_of_logical_bit);
 
 #ifdef __cplusplus
 }

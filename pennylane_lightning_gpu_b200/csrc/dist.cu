@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 
 #include "qsv_internal.h"
 
@@ -253,117 +254,134 @@ std::vector<DistStep> plan_dist_steps(const std::vector<uint64_t> &dense, const 
             indeg[i] = (int)preds.size();
         }
     }
-    auto global_mask = [&]() {
-        uint64_t m = 0;
-        for (int q = 0; q < n_total; ++q)
-            if (phys_of[q] >= n_local) m |= 1ull << q;
-        return m;
-    };
     std::vector<char> done(n, 0);
     std::vector<int> ready;  // ready and not yet executed, kept sorted (program order among ready gates)
     for (size_t i = 0; i < n; ++i)
         if (indeg[i] == 0) ready.push_back((int)i);
-    size_t n_done = 0;
-    // run every ready gate that is local under `gmask`; returns the number executed.  With record != nullptr the
-    // run is a simulation: executed gates are listed there and undone by the caller.
+    size_t n_done = 0;  // includes the gates of a simulation in progress
+    // run every ready gate whose dense bits avoid `gmask` (the global qubits); returns the number executed.  With
+    // record != nullptr the run is a simulation: executed gates are listed there and undone by the caller.
     auto run = [&](uint64_t gmask, std::vector<int> *record, size_t cap) {
         size_t count = 0;
-        bool progress = true;
-        while (progress && count < cap) {
-            progress = false;
-            for (size_t r = 0; r < ready.size() && count < cap;) {
-                const int i = ready[r];
-                if (dense[i] & gmask) {
-                    ++r;
-                    continue;
-                }
-                ready.erase(ready.begin() + r);
-                done[i] = 1;
-                ++count;
-                if (record)
-                    record->push_back(i);
-                else
-                    steps.push_back({1, i, 0});
-                for (int sidx : succ[i])
-                    if (--indeg[sidx] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), sidx), sidx);
-                progress = true;
-                // the insertion may have landed before r: restart the scan (ready lists are short)
-                r = 0;
+        for (size_t r = 0; r < ready.size() && count < cap;) {
+            const int i = ready[r];
+            if (dense[i] & gmask) {
+                ++r;
+                continue;
             }
+            ready.erase(ready.begin() + r);
+            done[i] = 1;
+            ++count;
+            ++n_done;
+            if (record)
+                record->push_back(i);
+            else
+                steps.push_back({1, i, 0});
+            for (int sidx : succ[i])
+                if (--indeg[sidx] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), sidx), sidx);
+            r = 0;  // a successor may have been inserted before r (ready lists are short)
         }
         return count;
     };
     auto undo = [&](const std::vector<int> &record, const std::vector<int> &ready_before) {
         for (auto it = record.rbegin(); it != record.rend(); ++it) {
             done[*it] = 0;
+            --n_done;
             for (int sidx : succ[*it]) ++indeg[sidx];
         }
         ready = ready_before;
     };
     const size_t LOOKAHEAD = 2048;
+    const long FINISHED = 1l << 40;  // score of an exchange after which the circuit runs to its end
     size_t first_pending = 0;
+    auto next_use = [&](int q) {  // program-order position of the next pending gate that changes qubit q
+        size_t scanned = 0;
+        for (size_t j = first_pending; j < n && scanned < 4 * LOOKAHEAD; ++j) {
+            if (done[j]) continue;
+            ++scanned;
+            if (dense[j] >> q & 1) return j;
+        }
+        return n + 1;
+    };
+    struct Choice {
+        long score = -1;
+        size_t next = 0;
+        int q = -1, l = -1;
+    };
+    const int window_lo = std::max(0, n_local - 8);  // evict from the top bits: few, large contiguous blocks
+    // best (incoming qubit, evicted local bit) at a stall under the map (phys, log); depth 2 adds the best score of
+    // the following stall
+    std::function<Choice(const std::vector<int> &, const std::vector<int> &, int)> choose =
+        [&](const std::vector<int> &phys, const std::vector<int> &log, int depth) {
+            uint64_t gmask = 0;
+            for (int q = 0; q < n_total; ++q)
+                if (phys[q] >= n_local) gmask |= 1ull << q;
+            uint64_t want = 0;  // global qubits the ready gates are waiting for
+            for (int i : ready) want |= dense[i] & gmask;
+            Choice best;
+            std::vector<int> record;
+            const std::vector<int> ready_before = ready;
+            for (int q = 0; q < n_total; ++q) {
+                if (!(want >> q & 1)) continue;
+                for (int l = n_local - 1; l >= window_lo; --l) {
+                    const int out = log[l];
+                    const uint64_t trial = (gmask & ~(1ull << q)) | (1ull << out);
+                    record.clear();
+                    const size_t count = run(trial, &record, LOOKAHEAD);
+                    long score = (long)count;
+                    if (n_done == n) {
+                        score += FINISHED;
+                    } else if (depth > 1 && count > 0 && count < LOOKAHEAD) {
+                        std::vector<int> phys2 = phys, log2 = log;
+                        const int gp = phys2[q];
+                        log2[gp] = out;
+                        log2[l] = q;
+                        phys2[q] = l;
+                        phys2[out] = gp;
+                        score += std::max(0l, choose(phys2, log2, depth - 1).score);
+                    }
+                    undo(record, ready_before);
+                    const size_t nu = next_use(out);
+                    if (score > best.score || (score == best.score && nu > best.next)) {
+                        best.score = score;
+                        best.next = nu;
+                        best.q = q;
+                        best.l = l;
+                    }
+                }
+            }
+            return best;
+        };
+    const int depth = n <= 4096 ? 2 : 1;
     while (true) {
-        n_done += run(global_mask(), nullptr, n + 1);
+        uint64_t gmask = 0;
+        for (int q = 0; q < n_total; ++q)
+            if (phys_of[q] >= n_local) gmask |= 1ull << q;
+        run(gmask, nullptr, n + 1);
         if (n_done == n) break;
         QSV_CHECK(!ready.empty(), "internal: the exchange planner found no ready gate");
         while (first_pending < n && done[first_pending]) ++first_pending;
-        const uint64_t gmask = global_mask();
-        uint64_t want = 0;  // global qubits the ready gates are waiting for
-        for (int i : ready) want |= dense[i] & gmask;
-        auto next_use = [&](int q) {  // program-order distance to the next pending gate that changes qubit q
-            size_t scanned = 0;
-            for (size_t j = first_pending; j < n && scanned < 4 * LOOKAHEAD; ++j) {
-                if (done[j]) continue;
-                ++scanned;
-                if (dense[j] >> q & 1) return j;
-            }
-            return n + 1;
-        };
-        const int window_lo = std::max(0, n_local - 8);  // evict from the top bits: few, large contiguous blocks
-        long best_count = -1;
-        size_t best_next = 0;
-        int best_q = -1, best_l = -1;
-        std::vector<int> record;
-        const std::vector<int> ready_before = ready;
-        for (int q = 0; q < n_total; ++q) {
-            if (!(want >> q & 1)) continue;
-            for (int l = n_local - 1; l >= window_lo; --l) {
-                const int out = log_of[l];
-                const uint64_t trial = (gmask & ~(1ull << q)) | (1ull << out);
-                record.clear();
-                const long count = (long)run(trial, &record, LOOKAHEAD);
-                undo(record, ready_before);
-                const size_t nu = next_use(out);
-                if (count > best_count || (count == best_count && nu > best_next)) {
-                    best_count = count;
-                    best_next = nu;
-                    best_q = q;
-                    best_l = l;
-                }
-            }
-        }
-        if (best_count <= 0) {
+        Choice best = choose(phys_of, log_of, depth);
+        if (best.score <= 0) {
             // the ready gates wait for more than one global qubit each: serve the first of them, never evicting
             // a qubit it needs itself (so its number of global qubits falls with every exchange)
             const int i0 = ready.front();
-            best_q = -1;
-            for (int q = 0; q < n_total && best_q < 0; ++q)
-                if ((dense[i0] & gmask) >> q & 1) best_q = q;
-            best_l = -1;
-            best_next = 0;
-            for (int pass = 0; pass < 2 && best_l < 0; ++pass)
+            best = Choice{};
+            for (int q = 0; q < n_total && best.q < 0; ++q)
+                if ((dense[i0] & gmask) >> q & 1) best.q = q;
+            for (int pass = 0; pass < 2 && best.l < 0; ++pass)
                 for (int l = n_local - 1; l >= (pass == 0 ? window_lo : 0); --l) {
                     const int out = log_of[l];
                     if (dense[i0] >> out & 1) continue;
                     const size_t nu = next_use(out);
-                    if (best_l < 0 || nu > best_next) {
-                        best_l = l;
-                        best_next = nu;
+                    if (best.l < 0 || nu > best.next) {
+                        best.l = l;
+                        best.next = nu;
                     }
                 }
-            QSV_CHECK(best_q >= 0 && best_l >= 0, "no local qubit can be evicted");
+            QSV_CHECK(best.q >= 0 && best.l >= 0, "no local qubit can be evicted");
         }
-        do_swap(phys_of[best_q], best_l);
+        do_swap(phys_of[best.q], best.l);
     }
     return steps;
 }
@@ -1787,11 +1805,20 @@ int qsv_dist_total_swap_stats(qsv_state *sv, int *n_swaps, uint64_t *bytes_sent,
  * Used by the gloo (CPU) tests of the N > 1 path. */
 int qsv_dist_plan(const qsv_ops *ops, int n_total, int n_local, int *steps, int max_steps, int *n_steps,
                   int *final_phys_of_logical_bit) {
+    return qsv_dist_plan_from(ops, n_total, n_local, nullptr, steps, max_steps, n_steps, final_phys_of_logical_bit);
+}
+
+int qsv_dist_plan_from(const qsv_ops *ops, int n_total, int n_local, const int *initial_phys_of_logical_bit, int *steps,
+                       int max_steps, int *n_steps, int *final_phys_of_logical_bit) {
     QSV_API_BEGIN
     QSV_CHECK(ops != nullptr && n_steps != nullptr, "null argument");
     QSV_CHECK(n_local >= 1 && n_local <= n_total && n_total <= 48, "invalid register sizes");
-    std::vector<int> phys_of(n_total), log_of(n_total);
-    for (int b = 0; b < n_total; ++b) phys_of[b] = log_of[b] = b;
+    std::vector<int> phys_of(n_total), log_of(n_total, -1);
+    for (int b = 0; b < n_total; ++b) {
+        phys_of[b] = initial_phys_of_logical_bit ? initial_phys_of_logical_bit[b] : b;
+        QSV_CHECK(phys_of[b] >= 0 && phys_of[b] < n_total && log_of[phys_of[b]] < 0, "the initial qubit map is not a permutation");
+        log_of[phys_of[b]] = b;
+    }
     std::vector<uint64_t> dense, diag;
     std::vector<int> op_index;
     for (size_t i = 0; i < ops->ops.size(); ++i) {

@@ -16,14 +16,17 @@ from . import _cabi
 from ._cabi import Ops, StateVector, _check, lib
 
 
-def plan(ops: Ops, n_total: int, n_local: int):
+def plan(ops: Ops, n_total: int, n_local: int, initial_map=None):
     """Host-only view of the exchange schedule: -> (steps, final map).  steps = list of
-    ("swap", global_phys_bit, local_phys_bit) | ("gate", op_index)."""
+    ("swap", global_phys_bit, local_phys_bit) | ("gate", op_index).  initial_map = physical bit of every logical bit
+    before the circuit (None = identity); the map persists between calls of apply_ops, so feeding the final map back
+    in gives the schedule of a repeated application."""
     cap = 4 * len(ops) + 16
     steps = (C.c_int * (3 * cap))()
     n_steps = C.c_int(0)
     final = (C.c_int * n_total)()
-    _check(lib().qsv_dist_plan(ops._h, n_total, n_local, steps, cap, C.byref(n_steps), final))
+    first = (C.c_int * n_total)(*[int(x) for x in initial_map]) if initial_map is not None else None
+    _check(lib().qsv_dist_plan_from(ops._h, n_total, n_local, first, steps, cap, C.byref(n_steps), final))
     out = []
     for i in range(n_steps.value):
         kind, a, b = steps[3 * i], steps[3 * i + 1], steps[3 * i + 2]

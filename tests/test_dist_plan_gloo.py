@@ -169,12 +169,14 @@ def _n_swaps(steps):
     return sum(1 for s in steps if s[0] == "swap")
 
 
-def _check_plan(ops, steps, final_map, n_total, n_local):
+def _check_plan(ops, steps, final_map, n_total, n_local, initial_map=None):
     """Every gate exactly once, dense targets local when it runs, non-commuting pairs in program order."""
     from pennylane_lightning_gpu_b200 import workloads
 
-    phys = list(range(n_total))
-    log = list(range(n_total))
+    phys = list(initial_map) if initial_map is not None else list(range(n_total))
+    log = [0] * n_total
+    for q, p in enumerate(phys):
+        log[p] = q
     pos = {}
     for k, st in enumerate(steps):
         if st[0] == "swap":
@@ -231,3 +233,23 @@ def test_cyclic_use_of_more_qubits_than_fit():
     ops = [{"name": "RX", "wires": [w], "params": [0.1 * (r + 1)]} for r in range(4) for w in range(4)]
     steps, _ = plan(Ops(ops), 4, 3)
     assert _n_swaps(steps) == 1
+
+
+@pytest.mark.parametrize("n_total,n_local,expect", [(31, 30, 1), (32, 30, 3), (36, 33, 3)])
+def test_repeated_application_keeps_the_map(n_total, n_local, expect):
+    """bench.py applies the same circuit again and again; the qubit map persists between the calls.  Planned exchanges
+    per step in the steady state: 1 / 2-3 / 3 at 2 / 4 / 8 GPUs (program order: 2 / 6 / 6)."""
+    from pennylane_lightning_gpu_b200 import Ops, _build, workloads
+    from pennylane_lightning_gpu_b200.distributed import plan
+
+    _build.build_lib()
+    ops = workloads.random_gate_circuit(n_total, 200, 2024)
+    rec = Ops(ops)
+    m = None
+    for _ in range(6):
+        steps, m_next = plan(rec, n_total, n_local, m)
+        _check_plan(ops, steps, m_next, n_total, n_local, m)
+        assert _n_swaps(steps) <= expect
+        m = m_next
+    with pytest.raises(Exception):
+        plan(rec, n_total, n_local, [0] * n_total)  # not a permutation
