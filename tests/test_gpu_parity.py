@@ -613,6 +613,42 @@ def test_register_tile_feature_switches(q, env, dtype, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("env", [{"QSV_DENSE1_SHAPE": str(s)} for s in (0, 1, 2, 3, 4, 6, 7, 8)] +
+                         [{"QSV_BIT0_SHAPE": str(s)} for s in (0, 2, 3)] +
+                         [{"QSV_DENSE2_SHAPE": str(s)} for s in (0, 2, 3)] +
+                         [{"QSV_DIAG_SHAPE": str(s)} for s in (0, 1, 3)])
+def test_gate_kernel_launch_shapes(q, env, dtype, monkeypatch):
+    """csrc/apply_kernels.cu: the non-default launch shapes of the one-sweep-per-gate kernels (groups per thread /
+    threads per block, 256-bit accesses, 2x2 gate through the two-target kernel), kept for the A/B scripts
+    (tools/ab_dense1.py, tools/ab_shapes2.py); plain, controlled, low and high target bits, gate by gate."""
+    from pennylane_lightning_gpu_b200 import workloads
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 16
+    rng = np.random.default_rng(5)
+    u2, u4 = workloads.haar_unitary(rng, 2), workloads.haar_unitary(rng, 4)
+    ops = [{"name": "RX", "wires": [0], "params": [0.3]}, {"name": "RX", "wires": [n - 1], "params": [0.3]},
+           {"name": "RY", "wires": [n - 2], "params": [0.7]}, {"name": "Hadamard", "wires": [7], "params": []},
+           {"name": "CNOT", "wires": [3, 12], "params": []}, {"name": "CNOT", "wires": [n - 2, n - 1], "params": []},
+           {"name": "CNOT", "wires": [n - 1, n - 2], "params": []}, {"name": "CRX", "wires": [0, n - 1], "params": [0.9]},
+           {"name": "Toffoli", "wires": [1, 5, 9], "params": []}, {"name": "Toffoli", "wires": [n - 3, n - 1, n - 2], "params": []},
+           {"name": "QubitUnitary", "wires": [n - 1], "params": [], "matrix": u2},
+           {"name": "QubitUnitary", "wires": [4], "params": [], "matrix": u2},
+           {"name": "QubitUnitary", "wires": [0, 1], "params": [], "matrix": u4},
+           {"name": "QubitUnitary", "wires": [n - 2, n - 1], "params": [], "matrix": u4},
+           {"name": "QubitUnitary", "wires": [n - 1, 5], "params": [], "matrix": u4},
+           {"name": "RZ", "wires": [0], "params": [1.1]}, {"name": "RZ", "wires": [n - 1], "params": [0.4]},
+           {"name": "CZ", "wires": [3, 4], "params": []}, {"name": "IsingZZ", "wires": [1, n - 1], "params": [0.2]},
+           {"name": "PhaseShift", "wires": [n - 2], "params": [0.6]}, {"name": "MultiRZ", "wires": [0, 4, 9], "params": [0.8]}]
+    psi = random_state(n, 33)
+    want = orc.apply_ops(psi, ops)
+    sv = gpu_state(q, psi, dtype)
+    sv.apply_ops(q.Ops(ops), fuse=False)
+    assert_close(sv.d2h(), want, dtype, scale=10, what=f"env={env}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [11, 13, 17])
 def test_fused_pauli_word_expvals(q, n, dtype):
     """csrc/adjoint_kernels.cu (Pauli kind): many words per read of the state, incl. words whose X/Y letters do not fit one
