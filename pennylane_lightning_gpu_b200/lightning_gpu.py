@@ -341,6 +341,7 @@ class LightningGPU(_Base):
             warnings.warn("Requested adjoint differentiation to be computed with finite shots. The derivative is "
                           "always exact when using the adjoint differentiation method.", UserWarning)
         operations = list(operations)
+        self._check_adjdiff_supported_operations(operations)
         if not observables:
             return np.array([], dtype=self.R_DTYPE)
         if starting_state is not None:
@@ -363,11 +364,34 @@ class LightningGPU(_Base):
             fn = adj.adjoint_jacobian_batched if self._batch_obs else adj.adjoint_jacobian
         return np.asarray(fn(self._gpu_state, obs, rec, tp))
 
+    @staticmethod
+    def _check_adjdiff_supported_operations(operations):
+        """lightning_gpu.py:622-636: operations with more than one parameter other than Rot cannot be differentiated."""
+        for op in operations:
+            if len(getattr(op, "parameters", ())) > 1 and op.name != "Rot" and op.name not in _STATE_PREPS:
+                raise ValueError(f'The {op.name} operation is not supported using the "adjoint" differentiation method')
+
     def vjp(self, operations, observables, dy, trainable_params=None, **kw) -> np.ndarray:
-        """Vector-Jacobian product dy^T J (lightning_gpu.py:771-810)."""
+        """Vector-Jacobian product dy^T J (lightning_gpu.py:771-810).  As in the reference the observables are combined
+        into one Hamiltonian sum_i dy_i O_i first, so the reverse sweep carries one bra instead of one per observable."""
+        if np.iscomplexobj(dy):
+            raise ValueError("The vjp method only works with a real-valued dy when the tape is returning an expectation value")
         dy = np.asarray(dy, dtype=self.R_DTYPE).reshape(-1)
         if np.allclose(dy, 0):
             n = len(trainable_params) if trainable_params is not None else 0
             return np.zeros(n, dtype=self.R_DTYPE)
-        jac = self.adjoint_jacobian(operations, observables, trainable_params, **kw)
+        if len(dy) != len(observables):
+            raise ValueError("Number of observables in the tape must be the same as the length of dy in the vjp method")
+        coeffs, terms = [], []
+        for w, o in zip(dy, observables):
+            if o.name == "Hamiltonian":
+                coeffs += [float(w) * float(c) for c in o.coeffs]
+                terms += list(o.terms)
+            else:
+                coeffs.append(float(w))
+                terms.append(o)
+        if all(t.name in ("PauliX", "PauliY", "PauliZ", "Hadamard", "Identity", "Hermitian", "Tensor") for t in terms):
+            ham = Obs("Hamiltonian", coeffs=coeffs, terms=terms)
+            return np.asarray(self.adjoint_jacobian(operations, [ham], trainable_params, **kw)).reshape(-1)
+        jac = self.adjoint_jacobian(operations, observables, trainable_params, **kw)  # sparse / nested observables
         return dy @ jac.reshape(len(dy), -1)

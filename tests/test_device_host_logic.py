@@ -1,0 +1,49 @@
+"""Host-side logic of the LightningGPU device mirror that needs no GPU: argument validation of vjp and the
+operation check of the adjoint method (reference: pennylane_lightning_gpu/lightning_gpu.py:622-636, 771-810)."""
+import numpy as np
+import pytest
+
+from pennylane_lightning_gpu_b200 import _build
+
+
+@pytest.fixture(scope="module")
+def lg():
+    _build.build_all()
+    from pennylane_lightning_gpu_b200 import lightning_gpu
+
+    return lightning_gpu
+
+
+def _bare_device(lg):
+    dev = object.__new__(lg.LightningGPU)  # no GPU state: the checks below run before any call into the binary
+    dev.R_DTYPE, dev.C_DTYPE, dev.shots = np.float64, np.complex128, None
+    return dev
+
+
+def test_vjp_argument_checks(lg):
+    dev = _bare_device(lg)
+    ops = [lg.Op("RX", [0], [0.1])]
+    obs = [lg.Obs("PauliZ", [0])]
+    with pytest.raises(ValueError, match="real-valued dy"):
+        dev.vjp(ops, obs, [1j], trainable_params=[0])
+    with pytest.raises(ValueError, match="same as the length of dy"):
+        dev.vjp(ops, obs, [1.0, 2.0], trainable_params=[0])
+    out = dev.vjp(ops, obs, [0.0], trainable_params=[0])  # dy == 0: zeros without touching the device
+    assert out.shape == (1,) and out[0] == 0.0
+
+
+def test_adjoint_operation_check(lg):
+    ok = [lg.Op("Rot", [0], [0.1, 0.2, 0.3]), lg.Op("RX", [1], [0.3]), lg.Op("CNOT", [0, 1]),
+          lg.Op("QubitStateVector", [0], [np.array([1.0, 0.0]), 0])]
+    lg.LightningGPU._check_adjdiff_supported_operations(ok)
+    with pytest.raises(ValueError, match='CRot operation is not supported using the "adjoint"'):
+        lg.LightningGPU._check_adjdiff_supported_operations([lg.Op("CRot", [0, 1], [0.1, 0.2, 0.3])])
+
+
+def test_constructor_argument_checks(lg):
+    with pytest.raises(TypeError, match="Unsupported complex Type"):
+        lg.LightningGPU(2, c_dtype=np.float64)
+    with pytest.raises(TypeError, match="mpi_buf_size"):
+        lg.LightningGPU(2, mpi_buf_size=-1)
+    with pytest.raises(TypeError, match="power of 2"):
+        lg.LightningGPU(2, mpi_buf_size=3)
