@@ -304,6 +304,11 @@ def run_ours(args):
             "frac_of_770_measured_peer_copy": ((swap_bytes / 1e9) / (swap_ms * 1e-3) / 770.0) if swap_ms > 0 else None,
             "swap_ms_per_step": swap_ms / args.steps,
         }
+        n_oop, n_carried = sv.fused_exchange_stats()
+        if n_oop:  # QSV_DIST_FUSED_SWAP=1: exchanges stored by the sweep before them (not part of the swap timing above)
+            total_steps = args.steps + max(args.warmup, 3)
+            detail["nvlink_swaps"]["out_of_place_exchanges_per_step"] = n_oop / total_steps
+            detail["nvlink_swaps"]["carried_by_sweeps_per_step"] = n_carried / total_steps
         kernel_ms = ms_total - detail["nvlink_swaps"]["swap_ms_per_step"] * args.steps
         if launches > 0 and kernel_ms > 0:
             roofline["ms_per_launch"] = kernel_ms / launches

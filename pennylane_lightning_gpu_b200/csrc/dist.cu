@@ -64,6 +64,12 @@ struct DistCtx {
     };
     std::vector<Companion> comp;
     bool skip_main = false;                // adjoint sweep: the register itself stays where it is
+    // exchanges fused into sweeps (QSV_DIST_FUSED_SWAP=1): a second shard-sized buffer, peer-mapped like the first;
+    // a fused sweep reads the buffer the register lives in and writes this rank's and the partner's other buffer
+    void *shadow = nullptr;
+    PeerBuf shadow_pb;
+    bool shadow_tried = false;
+    int n_fused = 0, n_oop = 0;            // statistics: exchanges through the second buffer, and how many of them a sweep carried
     void **tab_dev = nullptr;              // device table of vector pointers for batched launches
     std::vector<void *> tab_cache;
 };
@@ -442,6 +448,34 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Out-of-place form of the exchange for the double-buffer protocol (dist_apply_ops, QSV_DIST_FUSED_SWAP=1) when the last
+// sweep of a batch cannot carry it: every 16-byte unit of `in` goes to the same offset of this rank's other buffer when
+// its exchanged bit equals this rank's value of the global bit, else to the partner's other buffer with the bit flipped.
+template <int U>
+__global__ void __launch_bounds__(256)
+    k_xchg_oop(const uint4 *__restrict__ in, uint4 *__restrict__ out_mine, uint4 *__restrict__ out_peer, uint64_t count,
+               uint64_t bit_mask, uint64_t keep) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * U;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 * U + threadIdx.x; i0 < count; i0 += stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) {
+                if ((i & bit_mask) == keep)
+                    out_mine[i] = v[u];
+                else
+                    out_peer[i ^ bit_mask] = v[u];
+            }
+        }
+    }
+}
+
 void handshake(State &sv, int peer) {
     DistCtx &d = *sv.dist;
     QSV_NCCL(ncclGroupStart());
@@ -583,6 +617,39 @@ void swap_logical_in(State &sv, int gphys, int l, size_t chunk_bytes) {
 
 }  // namespace
 
+namespace {
+
+bool fused_swap_enabled() {
+    const char *e = std::getenv("QSV_DIST_FUSED_SWAP");
+    return e && std::atoi(e) != 0;
+}
+
+// Collective (every rank calls it at the same point of the same plan): allocate and peer-map the second buffer.  Any
+// rank short of memory, or any failed mapping, switches the feature off on all ranks.
+bool ensure_shadow(State &sv) {
+    DistCtx &d = *sv.dist;
+    if (d.shadow_tried) return d.shadow != nullptr && d.shadow_pb.ok;
+    d.shadow_tried = true;
+    if (!d.p2p || !d.main.ok) return false;
+    size_t free_b = 0, total_b = 0;
+    void *buf = nullptr;
+    const size_t bytes = std::max<size_t>(sv.bytes(), (size_t)2 << 20);  // own IPC handle, see TempVec
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > bytes + ((size_t)2 << 30)) {
+        if (cudaMalloc(&buf, bytes) != cudaSuccess) buf = nullptr;
+    }
+    cudaGetLastError();
+    d.shadow_pb = register_peer_buffer(sv, buf);  // null on any rank => not ok on every rank
+    if (!d.shadow_pb.ok) {
+        release_peer_buffer(d.shadow_pb);
+        if (buf) cudaFree(buf);
+        return false;
+    }
+    d.shadow = buf;
+    return true;
+}
+
+}  // namespace
+
 void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     sv.use();
     QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
@@ -605,25 +672,96 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     const std::vector<DistStep> steps = plan_dist_steps(dense, diag, plan_phys, plan_log, n_local);
 
     std::vector<LoweredGate> batch;
-    auto flush = [&]() {
+    auto flush = [&](FusedExchange *fx) {
         if (batch.empty()) return;
         if (fuse) {
-            apply_gates_tiled(sv, batch, nullptr, 1);
+            apply_gates_tiled(sv, batch, nullptr, 1, fx);
         } else {
             for (const auto &g : batch) launch_gate(sv, g);
         }
         batch.clear();
     };
+    // Exchanges fused into the last sweep of the batch before them (off unless QSV_DIST_FUSED_SWAP=1): the register then
+    // alternates between its own buffer and the second one; `home` is restored when the call ends.
+    size_t n_exchanges = 0;
+    for (const DistStep &st : steps) n_exchanges += st.kind == 0 ? 1 : 0;
+    const bool try_fused = fuse && fused_swap_enabled() && n_exchanges > 0 && d.comp.empty() && !d.skip_main &&
+                           sv.data == d.main.local && ensure_shadow(sv);
+    void *const home = sv.data;
+    struct Home {  // the register's pointer is back in place whatever happens below
+        State &sv;
+        void *p;
+        ~Home() { sv.data = p; }
+    } restore_home{sv, home};
+    bool in_shadow = false;
     for (const DistStep &st : steps) {
         if (st.kind == 0) {
-            flush();
-            swap_logical_in(sv, st.a, st.b, chunk_bytes);
+            // 16-byte units: index bit 0 of a complex64 shard cannot be exchanged out of place (rank-independent test)
+            if (try_fused && !(sv.dtype == QSV_C64 && st.b == 0)) {
+                const int gb = st.a - n_local;
+                const int peer = d.rank ^ (1 << gb);
+                const PeerBuf &other_pb = in_shadow ? d.main : d.shadow_pb;
+                FusedExchange fx;
+                fx.out_mine = other_pb.local;
+                fx.out_peer = other_pb.peer[peer];
+                fx.local_bit = st.b;
+                fx.my_value = (d.rank >> gb) & 1;
+                // the partner has finished everything that read or wrote its other buffer (its previous fused sweep)
+                handshake(sv, peer);
+                flush(&fx);
+                if (fx.done) {
+                    d.n_fused += 1;
+                } else {
+                    // no sweep to carry it on this rank (empty batch, a lone gate last, or the exchanged bit is a tile
+                    // bit of the last sweep): the same stores from a copy pass.  The partner cannot tell the difference,
+                    // so this choice need not be the same on both sides.
+                    const int shift = sv.dtype == QSV_C128 ? 0 : 1;
+                    const uint64_t count = sv.length() >> shift;
+                    const uint64_t bit_mask = 1ull << (st.b - shift);
+                    constexpr int U = 4;
+                    const unsigned grid =
+                        (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), 148 * 16));
+                    k_xchg_oop<U><<<grid, 256, 0, sv.stream>>>((const uint4 *)sv.data, (uint4 *)fx.out_mine,
+                                                               (uint4 *)fx.out_peer, count, bit_mask,
+                                                               fx.my_value ? bit_mask : 0ull);
+                    QSV_CUDA(cudaGetLastError());
+                    sv.stat_launches += 1;
+                    sv.stat_sweeps += 1;
+                }
+                handshake(sv, peer);  // the partner has finished writing into this rank's other buffer
+                in_shadow = !in_shadow;
+                sv.data = in_shadow ? d.shadow : home;
+                const int a = d.log_of[st.a], b = d.log_of[st.b];
+                d.log_of[st.a] = b;
+                d.log_of[st.b] = a;
+                d.phys_of[a] = st.b;
+                d.phys_of[b] = st.a;
+                d.n_oop += 1;  // not in n_swaps / total_bytes / total_ms: those describe the timed in-place exchanges
+                continue;
+            }
+            flush(nullptr);
+            if (in_shadow) {
+                // the in-place exchange works on the peer mappings of the buffer the register lives in
+                std::swap(d.main, d.shadow_pb);
+                struct Unswap {
+                    DistCtx &d;
+                    ~Unswap() { std::swap(d.main, d.shadow_pb); }
+                } unswap{d};
+                swap_logical_in(sv, st.a, st.b, chunk_bytes);
+            } else {
+                swap_logical_in(sv, st.a, st.b, chunk_bytes);
+            }
             continue;
         }
         LoweredGate g = localize_gate(remap_gate(lowered[st.a], d.phys_of), n_local, sv.index_hi);
         if (g.kind != LoweredGate::NOP) batch.push_back(std::move(g));
     }
-    flush();
+    flush(nullptr);
+    if (in_shadow) {
+        // an odd number of fused exchanges: bring the register home (one device-to-device copy of the shard)
+        QSV_CUDA(cudaMemcpyAsync(home, d.shadow, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        sv.data = home;
+    }
     QSV_CHECK(d.phys_of == plan_phys, "internal: the executed exchanges do not match the planned qubit map");
 }
 
@@ -1319,6 +1457,10 @@ void dist_free(State &sv) {
     if (d->red_dev) cudaFree(d->red_dev);
     if (d->hs_dev) cudaFree(d->hs_dev);
     release_peer_buffer(d->main);
+    if (d->shadow) {
+        release_peer_buffer(d->shadow_pb);
+        cudaFree(d->shadow);
+    }
     for (auto &c : d->comp) release_peer_buffer(c.pb);
     if (d->tab_dev) cudaFree(d->tab_dev);
     delete d;
@@ -1783,6 +1925,14 @@ int qsv_dist_last_swap_stats(const qsv_state *sv, uint64_t *bytes_sent, float *m
 }
 
 int qsv_dist_uses_peer_access(const qsv_state *sv) { return sv && sv->dist && sv->dist->p2p ? 1 : 0; }
+
+int qsv_dist_fused_exchange_stats(const qsv_state *sv, int *n_out_of_place, int *n_carried_by_sweeps) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    if (n_out_of_place) *n_out_of_place = sv->dist->n_oop;
+    if (n_carried_by_sweeps) *n_carried_by_sweeps = sv->dist->n_fused;
+    QSV_API_END
+}
 
 int qsv_dist_total_swap_stats(qsv_state *sv, int *n_swaps, uint64_t *bytes_sent, float *ms, int reset) {
     QSV_API_BEGIN

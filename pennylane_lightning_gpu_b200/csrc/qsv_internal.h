@@ -205,8 +205,19 @@ void reduction_read(State &sv, const double *dev, double *host, size_t count);
 // circuits
 void apply_op(State &sv, const Op &op, bool extra_adjoint);
 void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
+// A global<->local index-bit exchange of a sharded register to be fused into the last sweep of a gate batch (dist.cu):
+// that sweep stores out of place, the tiles whose bit `local_bit` equals `my_value` to out_mine, the others to out_peer
+// (the partner's buffer, peer-mapped) with the bit flipped.  done is set when the batch ended in such a sweep.
+struct FusedExchange {
+    void *out_mine = nullptr;
+    void *out_peer = nullptr;
+    int local_bit = 0;
+    int my_value = 0;
+    bool done = false;
+};
 // same, on several vectors at once (dev_table = device array of n_vecs pointers, or null for sv.data)
-void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs);
+void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs,
+                       FusedExchange *fx = nullptr);
 // register-blocked tile kernel (tile_regs.cu) and its sweep planner (tile_kernels.cu)
 struct SweepPlan {
     std::vector<int> gates;  // indices into the (merged) gate list, in execution order
@@ -220,7 +231,8 @@ bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);
 bool regs_fusable(const LoweredGate &g, int n_local);
 uint64_t regs_need_bits(const LoweredGate &g);
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,
-                    void *const *table, int n_vecs);
+                    void *const *table, int n_vecs, const FusedExchange *fx = nullptr);
+bool regs_tile_contains_bit(int n, uint64_t need, int L, int bit);
 void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
 double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>
 void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,

@@ -752,7 +752,8 @@ bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b) {
     return ((da & bb) | (ba & db)) == 0;
 }
 
-static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
+static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
+                             FusedExchange *fx) {
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const std::vector<LoweredGate> merged = prepare_gates_regs(gates_in);
@@ -760,7 +761,8 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
         plan_sweeps_regs(sv.n, merged, L, env_int("QSV_REGS_DAG", 1) != 0, std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
                          std::max(1, env_int("QSV_REGS_WINDOW", 512)));
     std::vector<const LoweredGate *> cur;
-    for (const SweepPlan &sw : plan) {
+    for (size_t k = 0; k < plan.size(); ++k) {
+        const SweepPlan &sw = plan[k];
         if (!sw.fused) {
             const LoweredGate &g = merged[sw.gates[0]];
             if (dev_table)
@@ -771,14 +773,20 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
         }
         cur.clear();
         for (int i : sw.gates) cur.push_back(&merged[i]);
-        run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs);
+        // the last sweep of the batch carries the exchange when the exchanged bit is not one of its tile bits
+        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1 &&
+                           !regs_tile_contains_bit(sv.n, sw.need, L, fx->local_bit);
+        run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs, carry ? fx : nullptr);
+        if (carry) fx->done = true;
     }
 }
 
-void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs) {
+void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
+                       FusedExchange *fx) {
     sv.use();
+    if (fx) fx->done = false;
     if (sv.n >= 12 && env_int("QSV_TILE_KERNEL", 1) == 1) {
-        apply_gates_regs(sv, gates_in, dev_table, n_vecs);
+        apply_gates_regs(sv, gates_in, dev_table, n_vecs, fx);
         return;
     }
     const bool f32 = sv.dtype == QSV_C64;

@@ -17,6 +17,7 @@
 // The reference has no counterpart: one custatevecApplyMatrix per gate
 // (simulator/StateVectorCudaManaged.hpp:1433-1471), one full sweep each.
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include <vector>
@@ -38,9 +39,23 @@ constexpr int RT_POOL = POOL;
 // per-SM arrival counters of the current launch: (epoch << 32) | CTAs that have started on this SM
 __device__ unsigned long long g_sm_arrivals[256];
 
-template <typename T, int RB, int MINB>
+// Sweep fused with a global<->local index-bit exchange of a sharded register (XCHG = true, csrc/dist.cu): the sweep reads
+// the shard in place but stores out of place -- tiles whose index bit `bit` equals this rank's value of the exchanged
+// global bit go to the same offset of this rank's other buffer, all other tiles to the partner GPU's other buffer (a
+// peer mapping: plain stores over NVLink) at the offset with that bit flipped.  `bit` is never a tile bit, so the choice
+// is per CTA.  The transfer overlaps the arithmetic of the tiles in flight; no separate exchange pass, no staging.
+struct XchgArgs {
+    void *out_mine;
+    void *out_peer;
+    uint64_t bit_mask;  // 1 << (exchanged local bit)
+    uint64_t keep;      // bit_mask when this rank's value of the global bit is 1, else 0
+};
+struct NoXchg {};
+
+template <typename T, int RB, int MINB, bool XCHG = false>
 __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
-    k_tile_regs(void *single, void *const *table, const __grid_constant__ RegProgram P) {
+    k_tile_regs(void *single, void *const *table, const __grid_constant__ RegProgram P,
+                const std::conditional_t<XCHG, XchgArgs, NoXchg> xa) {
     using A = typename Cx<T>::type;
     constexpr int NS = 1 << RB;            // amplitudes per thread
     constexpr int NT = 1 << (RT_TB - RB);  // threads per CTA
@@ -147,12 +162,19 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         // whole kernel just to be reused here
         uint32_t tid_s = tid;
         asm volatile("" : "+r"(tid_s));
-        const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
+        uint64_t obase_idx = base;
+        A *obase = gbase;
+        if constexpr (XCHG) {
+            const bool stays = (base & xa.bit_mask) == xa.keep;
+            obase = reinterpret_cast<A *>(stays ? xa.out_mine : xa.out_peer);
+            obase_idx = stays ? base : base ^ xa.bit_mask;
+        }
+        const uint64_t gt = obase_idx ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
         uint64_t gr[RB_MAX];
 #pragma unroll
         for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
+        for (int j = 0; j < NS; ++j) obase[slot_offset<RB>(gt, gr, j)] = x[j];
     }
 }
 
@@ -231,19 +253,32 @@ uint64_t regs_need_bits(const LoweredGate &g) { return g.kind == LoweredGate::DE
 
 namespace {
 
-template <typename T, int RB> void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs) {
+template <typename T, int RB>
+void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs, const XchgArgs *xa) {
     // register budget: 16 amplitudes per thread need 2 CTAs of 256 threads (128 registers); 8 amplitudes per thread run as
     // 2 CTAs of 512 threads (64 registers)
     constexpr int MINB = RB == 4 ? (sizeof(T) == 8 ? 2 : 3) : 2;
     const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
+    dim3 grid((unsigned)(1ull << (sv.n - RT_TB)), (unsigned)n_vecs);
+    if (xa) {
+        QSV_CHECK(table == nullptr && n_vecs == 1, "internal: a sweep fused with an exchange works on one vector");
+        static bool configured_x[64] = {false};
+        auto kern = k_tile_regs<T, RB, MINB, true>;
+        if (!configured_x[sv.device & 63]) {
+            QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_x[sv.device & 63] = true;
+        }
+        kern<<<grid, 1 << (RT_TB - RB), smem, sv.stream>>>(sv.data, nullptr, P, *xa);
+        QSV_CUDA(cudaGetLastError());
+        return;
+    }
     static bool configured[64] = {false};  // per device: function attributes belong to the device's context
     auto kern = k_tile_regs<T, RB, MINB>;
     if (!configured[sv.device & 63]) {
         QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[sv.device & 63] = true;
     }
-    dim3 grid((unsigned)(1ull << (sv.n - RT_TB)), (unsigned)n_vecs);
-    kern<<<grid, 1 << (RT_TB - RB), smem, sv.stream>>>(table ? nullptr : sv.data, table, P);
+    kern<<<grid, 1 << (RT_TB - RB), smem, sv.stream>>>(table ? nullptr : sv.data, table, P, NoXchg{});
     QSV_CUDA(cudaGetLastError());
 }
 
@@ -265,6 +300,23 @@ int regs_rb() {
 
 }  // namespace
 
+// tile bits above the low L ones: the needed high bits, then the lowest free bits (ascending)
+std::vector<int> regs_tile_high_bits(int n, uint64_t need, int L) {
+    std::vector<int> hi;
+    for (int b = L; b < n; ++b)
+        if (need >> b & 1) hi.push_back(b);
+    for (int b = L; b < n && (int)hi.size() < RT_TB - L; ++b)
+        if (!(need >> b & 1)) hi.push_back(b);
+    std::sort(hi.begin(), hi.end());
+    return hi;
+}
+
+bool regs_tile_contains_bit(int n, uint64_t need, int L, int bit) {
+    if (bit < L) return true;
+    const std::vector<int> hi = regs_tile_high_bits(n, need, L);
+    return std::find(hi.begin(), hi.end(), bit) != hi.end();
+}
+
 // Program of one sweep of the register kernel over `gates` (all regs_fusable, dense-touched bits >= L listed in `need`).
 void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<const LoweredGate *> &gates, uint64_t need,
                        int L, int rb, RegProgram &P) {
@@ -278,13 +330,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     const bool merge_diag = env_flag("QSV_REGS_UDIAG", 1);
     const bool diag_as_d1 = env_flag("QSV_REGS_DIAG1", 1);
 
-    // tile bits: the low L bits, the needed high bits, then the lowest free bits
-    std::vector<int> hi;
-    for (int b = L; b < n; ++b)
-        if (need >> b & 1) hi.push_back(b);
-    for (int b = L; b < n && (int)hi.size() < tb - L; ++b)
-        if (!(need >> b & 1)) hi.push_back(b);
-    std::sort(hi.begin(), hi.end());
+    std::vector<int> hi = regs_tile_high_bits(n, need, L);
     QSV_CHECK((int)hi.size() == tb - L, "internal: tile bit selection");
     int pos[64];
     int gpos[RT_TB];  // global bit of tile-local position p
@@ -848,7 +894,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
 }
 
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,
-                    int n_vecs) {
+                    int n_vecs, const FusedExchange *fx) {
     const int rb = regs_rb();
     RegProgram P;
     build_reg_program(sv.n, sv.dtype, sv.index_hi, gates, need, L, rb, P);
@@ -856,16 +902,26 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     P.epoch = ++launch_epoch == 0 ? ++launch_epoch : launch_epoch;  // never 0: the counters start zeroed
     sv.stat_launches += 1;
     sv.stat_sweeps += 1;
+    XchgArgs xa_store;
+    const XchgArgs *xa = nullptr;
+    if (fx) {
+        QSV_CHECK(!regs_tile_contains_bit(sv.n, need, L, fx->local_bit), "internal: the exchanged bit is a tile bit");
+        xa_store.out_mine = fx->out_mine;
+        xa_store.out_peer = fx->out_peer;
+        xa_store.bit_mask = 1ull << fx->local_bit;
+        xa_store.keep = fx->my_value ? xa_store.bit_mask : 0ull;
+        xa = &xa_store;
+    }
     if (sv.dtype == QSV_C128) {
         if (rb == 4)
-            launch_regs_t<double, 4>(sv, P, table, n_vecs);
+            launch_regs_t<double, 4>(sv, P, table, n_vecs, xa);
         else
-            launch_regs_t<double, 3>(sv, P, table, n_vecs);
+            launch_regs_t<double, 3>(sv, P, table, n_vecs, xa);
     } else {
         if (rb == 4)
-            launch_regs_t<float, 4>(sv, P, table, n_vecs);
+            launch_regs_t<float, 4>(sv, P, table, n_vecs, xa);
         else
-            launch_regs_t<float, 3>(sv, P, table, n_vecs);
+            launch_regs_t<float, 3>(sv, P, table, n_vecs, xa);
     }
 }
 

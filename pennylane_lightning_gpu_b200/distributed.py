@@ -79,6 +79,12 @@ class DistributedStateVector:
         _check(lib().qsv_dist_total_swap_stats(self.local._h, C.byref(n), C.byref(b), C.byref(ms), int(reset)))
         return n.value, b.value, ms.value
 
+    def fused_exchange_stats(self):
+        """(exchanges done through the second buffer, how many of them a gate sweep carried) -- QSV_DIST_FUSED_SWAP=1."""
+        a, b = C.c_int(0), C.c_int(0)
+        _check(lib().qsv_dist_fused_exchange_stats(self.local._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def uses_peer_access(self) -> bool:
         return bool(lib().qsv_dist_uses_peer_access(self.local._h))

@@ -296,6 +296,39 @@ def device_mirror(rank, world, g):
     return failures
 
 
+def fused_exchange_check(rank, local_rank, world, g):
+    """QSV_DIST_FUSED_SWAP=1 (off by default): exchanges through the second buffer, carried by the sweep before them where
+    the exchanged bit is not one of its tile bits.  20 local qubits so that sweeps can carry them; 13 so that the
+    copy-pass form runs too; repeated application (odd and even numbers of exchanges, register back home each time)."""
+    failures = []
+    os.environ["QSV_DIST_FUSED_SWAP"] = "1"
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 5e-5)):
+        for n_local in (13, 20):
+            n_total = n_local + g
+            ops = circuit(n_total, seed=100 + n_total)
+            want = orc.basis_state(n_total)
+            sv = DistributedStateVector(n_total, dtype, device=local_rank)
+            for rep in range(3):
+                sv.apply_ops(q.Ops(ops), fuse=True)
+                want = orc.apply_ops(want, ops)
+            n_oop, n_carried = sv.fused_exchange_stats()
+            nrm = sv.norm2()
+            sv.canonicalize()
+            shard = torch.from_numpy(sv.local_state().astype(np.complex128).view(np.float64)).cuda()
+            parts = [torch.empty_like(shard) for _ in range(world)]
+            dist.all_gather(parts, shard)
+            full = np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
+            err = float(np.max(np.abs(full - want)))
+            tag = f"fused exchange dtype={np.dtype(dtype).name} n_local={n_local}"
+            if err > tol * 30 or abs(nrm - 1) > tol * 100 or n_oop == 0:
+                failures.append(f"{tag}: state err {err:.2e}, norm {nrm}, out-of-place exchanges {n_oop}")
+            if rank == 0:
+                print(f"[dist_check] {tag}: err={err:.2e} exchanges={n_oop} carried_by_sweeps={n_carried}", flush=True)
+            sv.close()
+    os.environ.pop("QSV_DIST_FUSED_SWAP", None)
+    return failures
+
+
 def main():
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -304,6 +337,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = int(math.log2(world))
     failures = []
+    if os.environ.get("DIST_CHECK_FUSED") == "1":
+        failures = fused_exchange_check(rank, local_rank, world, g)
+        ok = torch.tensor([0 if failures else 1], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_CHECK", "PASS" if int(ok) == 1 else "FAIL", failures, flush=True)
+        dist.destroy_process_group()
+        sys.exit(0 if int(ok) == 1 else 1)
     for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 2e-5)):
         for n_total in (g + 6, g + 13):
             n_local = n_total - g
