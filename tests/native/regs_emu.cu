@@ -7,6 +7,7 @@
 // (__host__ __device__ code of csrc/tile_regs_core.cuh); only the thread/CTA loops and the memories are emulated.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../pennylane_lightning_gpu_b200/csrc/qsv_internal.h"
@@ -172,6 +173,57 @@ extern "C" double regs_emu_time_host_side(const void *ops_handle, int n, int dty
         }
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+
+// Per-sweep structure of the programs the host side builds for a circuit (no state needed): for sweep k,
+// out[8 k ..] = {passes, gates in the program, D2 blocks, D1-type gates, diagonal gates, tensor-core passes, gates folded
+// into pass boundaries, gates of the sweep before normalisation}.  Returns the number of sweeps (lone gates: passes = 0).
+extern "C" int regs_emu_sweep_stats(const void *ops_handle, int n, int dtype, int rb, int low_bits, int dag, int64_t *out,
+                                    int max_sweeps) {
+    const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
+    static RegProgram P;
+    std::vector<LoweredGate> gates;
+    for (const auto &op : ops->ops) {
+        if (op.name == "Identity") continue;
+        if (find_gate(op.name) != nullptr)
+            gates.push_back(lower_named(n, op.name, op.wires, op.params, op.inverse));
+        else
+            gates.push_back(lower_matrix(n, op.matrix.data(), {}, op.wires, op.inverse));
+    }
+    const std::vector<LoweredGate> merged = prepare_gates_regs(gates);
+    const int L = low_bits > 0 ? low_bits : 4;
+    auto env_or = [](const char *name, int dflt) {
+        const char *v = std::getenv(name);
+        return v ? std::atoi(v) : dflt;
+    };
+    const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, L, dag != 0, std::min(48, env_or("QSV_REGS_MAX_GATES", 48)),
+                                                         std::max(1, env_or("QSV_REGS_WINDOW", 512)));
+    std::vector<const LoweredGate *> cur;
+    int k = 0;
+    for (const SweepPlan &sw : plan) {
+        if (k >= max_sweeps) break;
+        int64_t *o = out + 8 * k++;
+        for (int i = 0; i < 8; ++i) o[i] = 0;
+        o[7] = (int64_t)sw.gates.size();
+        if (!sw.fused) continue;
+        cur.clear();
+        for (int i : sw.gates) cur.push_back(&merged[i]);
+        build_reg_program(n, dtype, 0, cur, sw.need, L, rb, P);
+        o[0] = P.n_passes;
+        o[1] = P.n_gates;
+        for (int g = 0; g < P.n_gates; ++g) {
+            const int kind = P.gates[g].kind;
+            if (kind == RG_D2)
+                ++o[2];
+            else if (kind == RG_DIAG || kind == RG_D1_DIAG)
+                ++o[4];
+            else
+                ++o[3];
+        }
+        for (int p = 0; p < P.n_passes; ++p) o[5] += P.passes[p].mma_off != NO_MMA ? 1 : 0;
+        o[6] = P.n_folded;
+    }
+    return k;
 }
 
 // ops = a qsv_ops handle of libqsv_b200.so; state = 2^n interleaved (re, im) doubles, updated in place (complex64 runs
