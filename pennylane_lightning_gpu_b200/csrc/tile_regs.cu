@@ -515,7 +515,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         std::vector<int> mma;           // gates multiplied into the MMA block (applied first in the pass), in order
         std::vector<int> order;
     };
-    auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk) {
+    auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk, bool seed_may_be_block = true) {
         // greedy: keep adding the ready gate that needs the fewest new register bits.  Uncontrolled dense gates on positions
         // that nothing else in the pass has touched join the pass's tensor-core block (no register bits at all); the block
         // runs first, and every later gate of the pass that looks at its positions follows it in dependency order anyway.
@@ -538,7 +538,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
                 pk.F |= ng[j].forbid;
             }
         };
-        add(seed, mma_fits(seed));
+        add(seed, seed_may_be_block && mma_fits(seed));
         for (;;) {
             int next = -1, best_new = 99;
             bool next_mma = false;
@@ -567,15 +567,114 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     const int ntb = tb - rb;
     int lay_r[RT_MAX_PASSES][RB_MAX], lay_t[RT_MAX_PASSES][NTB_MAX];
     slot_perms.push_back(take_perms());
+    // Beam search over pass sequences (QSV_REGS_BEAM, default 4 from 26 qubits up, where a pass costs more than the search):
+    // the greedy rule below -- the pass that retires most gates -- is short-sighted; a register pass costs 1 ms and a
+    // tensor-core block another 0.85 ms at 30 qubits (tools/sweep_cost_model.py), so the cheapest sequence under that model
+    // is searched for among the shortest ones and those one pass longer.
+    std::vector<PassPick> planned;
+    size_t plan_pos = 0;
+    {
+        const int beam = std::max(1, env_int_regs("QSV_REGS_BEAM", n >= 26 ? 4 : 1));
+        // cost of a sequence in 1/100 ms at 30 qubits complex128 (tools/sweep_cost_model.py, fitted to 17 measured
+        // sweeps / circuits: a pass 0.96 ms, its tensor-core block 0.85 ms, a 4x4 / 2x2 gate on register bits 1.03 / 0.56 ms)
+        auto pass_cost = [&](const PassPick &pk) {
+            long c = 96 + (pk.mma.empty() ? 0 : 85);
+            for (int j : pk.order) {
+                if (std::find(pk.mma.begin(), pk.mma.end(), j) != pk.mma.end()) continue;
+                c += ng[j].kind == RG_D2 ? 103 : (ng[j].kind == RG_DIAG ? 0 : (ng[j].kind == RG_D1_SWAP ? 0 : 56));
+            }
+            return c;
+        };
+        struct Node {
+            std::vector<char> dn;
+            std::vector<PassPick> seq;
+            size_t retired = 0;
+            long cost = 0;
+        };
+        auto sim_perms = [&](std::vector<char> &dn, size_t &retired) {
+            for (bool progress = true; progress;) {
+                progress = false;
+                for (size_t j = 0; j < m; ++j)
+                    if (!dn[j] && ng[j].perm && ready_in(j, dn)) {
+                        dn[j] = 1;
+                        ++retired;
+                        progress = true;
+                    }
+            }
+        };
+        if (beam > 1 && n_done < m) {
+            std::vector<Node> level(1);
+            level[0].dn = done;
+            level[0].retired = n_done;
+            long best_cost = -1;
+            int extra_levels = 1;  // sequences one pass longer than the shortest are still compared by cost
+            for (int depth = 0; depth < RT_MAX_PASSES && !level.empty(); ++depth) {
+                std::vector<Node> next;
+                for (const Node &nd : level) {
+                    for (size_t sd2 = 0; sd2 < 2 * m; ++sd2) {
+                        // every ready gate as the seed, on register bits or (if it may) as the tensor-core block
+                        const size_t sd = sd2 >> 1;
+                        const bool as_block = (sd2 & 1) == 0;
+                        if (nd.dn[sd] || ng[sd].perm || !ready_in(sd, nd.dn)) continue;
+                        if (!as_block && !(mma_allowed && ng[sd].mma_ok)) continue;  // same pass as the as_block variant
+                        Node c;
+                        c.dn = nd.dn;
+                        PassPick pk;
+                        grow((int)sd, c.dn, pk, as_block);
+                        c.retired = nd.retired + pk.order.size();
+                        c.cost = nd.cost + pass_cost(pk);
+                        sim_perms(c.dn, c.retired);
+                        bool dup = false;
+                        for (Node &o : next)
+                            if (o.dn == c.dn) {
+                                dup = true;
+                                if (c.cost < o.cost) {  // same gates retired, cheaper way
+                                    o.cost = c.cost;
+                                    o.seq = nd.seq;
+                                    o.seq.push_back(pk);
+                                }
+                                break;
+                            }
+                        if (dup) continue;
+                        c.seq = nd.seq;
+                        c.seq.push_back(std::move(pk));
+                        next.push_back(std::move(c));
+                    }
+                }
+                // finished sequences compete by cost; unfinished ones go on, the most advanced (then cheapest) first
+                std::vector<Node> open;
+                for (Node &c : next) {
+                    if (c.retired == m) {
+                        if (best_cost < 0 || c.cost < best_cost) {
+                            best_cost = c.cost;
+                            planned = c.seq;
+                        }
+                    } else {
+                        open.push_back(std::move(c));
+                    }
+                }
+                if (best_cost >= 0 && extra_levels-- <= 0) break;
+                std::stable_sort(open.begin(), open.end(), [](const Node &a, const Node &b) {
+                    return a.retired != b.retired ? a.retired > b.retired : a.cost < b.cost;
+                });
+                if ((int)open.size() > beam) open.resize(beam);
+                level = std::move(open);
+            }
+        }
+    }
     while (n_done < m || P.n_passes == 0) {
-        // try every ready gate as the seed of the next pass, keep the pass that retires the most gates
         PassPick best;
-        for (size_t sd = 0; sd < m; ++sd) {
-            if (done[sd] || ng[sd].perm || !ready_in(sd, done)) continue;
-            std::vector<char> dn = done;
-            PassPick pk;
-            grow((int)sd, dn, pk);
-            if (pk.order.size() > best.order.size()) best = pk;
+        if (plan_pos < planned.size()) {
+            best = planned[plan_pos++];
+        } else {
+            // try every ready gate as the seed of the next pass, keep the pass that retires the most gates
+            for (size_t sd = 0; sd < m; ++sd) {
+                if (done[sd] || ng[sd].perm || !ready_in(sd, done)) continue;
+                std::vector<char> dn = done;
+                PassPick pk;
+                grow((int)sd, dn, pk);
+                if (pk.order.size() > best.order.size()) best = pk;
+            }
         }
         if (!best.mma.empty()) {
             // every remaining gate may still need its own constants: keep room for them
@@ -584,6 +683,8 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
                 if (!done[j] && std::find(best.mma.begin(), best.mma.end(), (int)j) == best.mma.end()) need_pool += ng[j].pool.size();
             if (need_pool > (size_t)RT_POOL) {
                 mma_allowed = false;
+                planned.clear();  // the searched sequence assumed tensor-core blocks: fall back to the greedy rule
+                plan_pos = 0;
                 continue;  // choose this pass again without a tensor-core block
             }
         }

@@ -177,7 +177,7 @@ extern "C" double regs_emu_time_host_side(const void *ops_handle, int n, int dty
 
 // Per-sweep structure of the programs the host side builds for a circuit (no state needed): for sweep k,
 // out[8 k ..] = {passes, gates in the program, D2 blocks, D1-type gates, diagonal gates, tensor-core passes, gates folded
-// into pass boundaries, gates of the sweep before normalisation}.  Returns the number of sweeps (lone gates: passes = 0).
+// into pass boundaries, 256 * (distinct dense-target bits of the sweep) + gates of the sweep before normalisation}.  Returns the number of sweeps (lone gates: passes = 0).
 extern "C" int regs_emu_sweep_stats(const void *ops_handle, int n, int dtype, int rb, int low_bits, int dag, int64_t *out,
                                     int max_sweeps) {
     const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
@@ -204,7 +204,28 @@ extern "C" int regs_emu_sweep_stats(const void *ops_handle, int n, int dtype, in
         if (k >= max_sweeps) break;
         int64_t *o = out + 8 * k++;
         for (int i = 0; i < 8; ++i) o[i] = 0;
-        o[7] = (int64_t)sw.gates.size();
+        uint64_t dense_bits = 0;
+        for (int i : sw.gates)
+            if (merged[i].kind == LoweredGate::DENSE)
+                for (uint64_t off : merged[i].offs) dense_bits |= off;
+        o[7] = 256 * (int64_t)__builtin_popcountll(dense_bits) + (int64_t)sw.gates.size();
+        if (std::getenv("REGS_EMU_DUMP")) {
+            std::printf("sweep %d:", k - 1);
+            for (int i : sw.gates) {
+                const LoweredGate &g = merged[i];
+                uint64_t db = 0;
+                if (g.kind == LoweredGate::DENSE)
+                    for (uint64_t off : g.offs) db |= off;
+                std::printf(" %s[", g.kind == LoweredGate::DENSE ? (g.k == 2 ? "D2" : "D1") : "diag");
+                for (int b = 0; b < n; ++b)
+                    if (db >> b & 1) std::printf("%d ", b);
+                std::printf("|c");
+                for (int b = 0; b < n; ++b)
+                    if (g.ctrl_mask >> b & 1) std::printf(" %d", b);
+                std::printf("]");
+            }
+            std::printf("\n");
+        }
         if (!sw.fused) continue;
         cur.clear();
         for (int i : sw.gates) cur.push_back(&merged[i]);

@@ -120,6 +120,30 @@ def test_feature_switches(emu, env, monkeypatch):
         assert st["mma"] > 0
 
 
+@pytest.mark.parametrize("beam", [2, 4, 16])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_pass_sequence_search(emu, beam, dtype, monkeypatch):
+    """csrc/tile_regs.cu: beam search over pass sequences (QSV_REGS_BEAM; the default from 26 qubits up).  The programs it
+    builds must give the oracle's state, and must not need more passes than the greedy rule does."""
+    passes = {}
+    for b in (1, beam):
+        monkeypatch.setenv("QSV_REGS_BEAM", str(b))
+        total = 0
+        for n, seed in ((12, 11), (14, 12), (15, 13)):
+            ops = random_mixed_circuit(n, 160, seed) if seed != 12 else workloads.random_gate_circuit(n, 200, 2024)
+            psi0 = rand_state(n, 50 + seed)
+            want = orc.apply_ops(psi0.copy(), ops)
+            got, st = run_emulated(emu, ops, psi0, dtype=dtype)
+            assert np.max(np.abs(got - want)) < (1e-12 if dtype == np.complex128 else 3e-5), (b, n, st)
+            total += st["passes"]
+        ladder, _ = workloads.hardware_efficient_ansatz(13, layers=3, seed=11)
+        psi0 = rand_state(13, 99)
+        got, st = run_emulated(emu, ladder, psi0, dtype=dtype)
+        assert np.max(np.abs(got - orc.apply_ops(psi0.copy(), ladder))) < (1e-12 if dtype == np.complex128 else 3e-5)
+        passes[b] = total + st["passes"]
+    assert passes[beam] <= passes[1], passes
+
+
 def test_permutation_only_and_ladders(emu):
     n = 12
     psi0 = rand_state(n, 3)
