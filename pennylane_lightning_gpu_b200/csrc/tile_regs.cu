@@ -515,14 +515,14 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
         std::vector<int> mma;           // gates multiplied into the MMA block (applied first in the pass), in order
         std::vector<int> order;
     };
-    auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk, bool seed_may_be_block = true) {
+    auto grow = [&](int seed, std::vector<char> &dn, PassPick &pk, bool seed_may_be_block = true, bool with_block = true) {
         // greedy: keep adding the ready gate that needs the fewest new register bits.  Uncontrolled dense gates on positions
         // that nothing else in the pass has touched join the pass's tensor-core block (no register bits at all); the block
         // runs first, and every later gate of the pass that looks at its positions follows it in dependency order anyway.
         pk = PassPick();
         uint32_t touched_other = 0;  // positions looked at by the non-block gates of the pass
         auto mma_fits = [&](int j) {
-            if (!mma_allowed || !ng[j].mma_ok || (ng[j].dense & (pk.R | pk.F | touched_other))) return false;
+            if (!with_block || !mma_allowed || !ng[j].mma_ok || (ng[j].dense & (pk.R | pk.F | touched_other))) return false;
             if (mma_mode == 1 && !pk.mma.empty()) return false;
             return __builtin_popcount(pk.Pm | ng[j].dense) <= 2;
         };
@@ -611,16 +611,18 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
             for (int depth = 0; depth < RT_MAX_PASSES && !level.empty(); ++depth) {
                 std::vector<Node> next;
                 for (const Node &nd : level) {
-                    for (size_t sd2 = 0; sd2 < 2 * m; ++sd2) {
-                        // every ready gate as the seed, on register bits or (if it may) as the tensor-core block
-                        const size_t sd = sd2 >> 1;
-                        const bool as_block = (sd2 & 1) == 0;
+                    for (size_t sd3 = 0; sd3 < 3 * m; ++sd3) {
+                        // every ready gate as the seed: as the tensor-core block (if it may), on register bits with a block
+                        // for others, or in a pass without a block (a block costs more than one 2x2 gate on register bits)
+                        const size_t sd = sd3 / 3;
+                        const int variant = (int)(sd3 % 3);
                         if (nd.dn[sd] || ng[sd].perm || !ready_in(sd, nd.dn)) continue;
-                        if (!as_block && !(mma_allowed && ng[sd].mma_ok)) continue;  // same pass as the as_block variant
+                        if (variant == 1 && !(mma_allowed && ng[sd].mma_ok)) continue;  // same pass as variant 0
+                        if (variant == 2 && !mma_allowed) continue;                     // same pass as variant 0
                         Node c;
                         c.dn = nd.dn;
                         PassPick pk;
-                        grow((int)sd, c.dn, pk, as_block);
+                        grow((int)sd, c.dn, pk, variant == 0, variant != 2);
                         c.retired = nd.retired + pk.order.size();
                         c.cost = nd.cost + pass_cost(pk);
                         sim_perms(c.dn, c.retired);
