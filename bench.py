@@ -298,6 +298,8 @@ def run_ours(args):
         # NCCL send/recv stream, this rank) over warm-up + timed steps
         detail["nvlink_swaps"] = {
             "transport": "peer load/store kernel over CUDA IPC mappings" if sv.uses_peer_access else "staged ncclSend/ncclRecv",
+            "schedule": "program order, farthest-next-use eviction" if os.environ.get("QSV_DIST_DAG") == "0" else
+                        "dependency order (gates run while any ready gate is local)",
             "n_swaps_per_step": n_swaps / args.steps,
             "gb_sent_per_swap": (swap_bytes / max(n_swaps, 1)) / 1e9,
             "gbs_per_direction": (swap_bytes / 1e9) / (swap_ms * 1e-3) if swap_ms > 0 else None,
