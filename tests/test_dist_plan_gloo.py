@@ -253,3 +253,64 @@ def test_repeated_application_keeps_the_map(n_total, n_local, expect):
         m = m_next
     with pytest.raises(Exception):
         plan(rec, n_total, n_local, [0] * n_total)  # not a permutation
+
+
+def test_reordered_plans_are_legal_for_every_gate_family():
+    """Random small circuits over one-, two-, three- and four-wire gates (two-level gates like SWAP and the excitations,
+    controlled rotations, diagonal families): the gates applied in the planned order give the state of the program order,
+    every gate runs exactly once, and the exchanges leave the qubit map the plan reports -- from the identity map and
+    from the map the previous application left behind, down to two local qubits."""
+    from oracle import np_oracle as orc
+    from pennylane_lightning_gpu_b200 import Ops, _build
+    from pennylane_lightning_gpu_b200.distributed import plan
+
+    _build.build_lib()
+    rng = np.random.default_rng(1)
+    names1 = ["RX", "RY", "RZ", "Hadamard", "PauliX", "S", "PhaseShift"]
+    names2 = ["CNOT", "CZ", "SWAP", "CRX", "CRZ", "IsingXX", "IsingZZ", "SingleExcitation", "ControlledPhaseShift"]
+    with_param = {"RX", "RY", "RZ", "PhaseShift", "CRX", "CRZ", "IsingXX", "IsingZZ", "SingleExcitation",
+                  "ControlledPhaseShift", "DoubleExcitation", "MultiRZ"}
+    for trial in range(60):
+        n_total = int(rng.integers(4, 9))
+        n_local = int(rng.integers(2, n_total))
+        ops = []
+        for _ in range(int(rng.integers(5, 50))):
+            r = rng.random()
+            if r < 0.4:
+                nm, k = names1[rng.integers(len(names1))], 1
+            elif r < 0.85:
+                nm, k = names2[rng.integers(len(names2))], 2
+            elif r < 0.93 and n_local >= 3:
+                nm, k = "Toffoli", 3
+            elif n_local >= 4:
+                nm, k = "DoubleExcitation", 4
+            else:
+                nm, k = "MultiRZ", 3
+            ops.append({"name": nm, "wires": [int(x) for x in rng.choice(n_total, k, replace=False)],
+                        "params": [float(rng.uniform(-3, 3))] if nm in with_param else []})
+        psi = rng.normal(size=1 << n_total) + 1j * rng.normal(size=1 << n_total)
+        psi /= np.linalg.norm(psi)
+        want = orc.apply_ops(psi.copy(), ops)
+        rec = Ops(ops)
+        m = None
+        for _ in range(2):
+            steps, m_next = plan(rec, n_total, n_local, m)
+            phys = list(m) if m is not None else list(range(n_total))
+            log = [0] * n_total
+            for qb, p in enumerate(phys):
+                log[p] = qb
+            got, seen = psi.copy(), []
+            for st in steps:
+                if st[0] == "swap":
+                    _, gp, l = st
+                    assert gp >= n_local > l >= 0
+                    a, b = log[gp], log[l]
+                    log[gp], log[l] = b, a
+                    phys[a], phys[b] = l, gp
+                else:
+                    o = ops[st[1]]
+                    seen.append(st[1])
+                    got = orc.apply_op(got, o["name"], o["wires"], o.get("params", ()))
+            assert sorted(seen) == list(range(len(ops))) and phys == m_next
+            assert np.max(np.abs(got - want)) < 1e-12, (trial, n_total, n_local)
+            m = m_next
