@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         uint64_t obase_idx = base;
         A *obase = gbase;
         if constexpr (XCHG) {
-            const bool stays = (base & xa.bit_mask) == xa.keep;
-            obase = reinterpret_cast<A *>(stays ? xa.out_mine : xa.out_peer);
-            obase_idx = stays ? base : base ^ xa.bit_mask;
+            const XchgTarget t = xchg_target(base, xa.bit_mask, xa.keep);
+            obase = reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer);
+            obase_idx = t.base;
         }
         const uint64_t gt = obase_idx ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
         uint64_t gr[RB_MAX];

@@ -72,6 +72,18 @@ struct RegProgram {
     int pad1;
 };
 
+// Sweep fused with a global<->local index-bit exchange (k_tile_regs<..., XCHG = true>, csrc/dist.cu): the tile whose base
+// offset has the exchanged bit equal to this rank's value of the global bit (`keep` = bit_mask or 0) stays on this rank, at
+// the same offset of its other buffer; every other tile goes to the partner's other buffer with that bit flipped.
+struct XchgTarget {
+    bool stays;
+    uint64_t base;
+};
+__host__ __device__ __forceinline__ XchgTarget xchg_target(uint64_t base, uint64_t bit_mask, uint64_t keep) {
+    const bool stays = (base & bit_mask) == keep;
+    return {stays, stays ? base : base ^ bit_mask};
+}
+
 template <typename T> __host__ __device__ __forceinline__ const T *const_pool(const RegProgram &P);
 // where the unpredicated dense paths read their matrix from: the kernel-parameter constant bank (complex128) or the
 // shared-memory copy (complex64; -DQSV_PLAIN_SMEM forces it for both, an A/B build)

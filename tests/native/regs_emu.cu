@@ -54,7 +54,16 @@ template <typename A> void apply_lowered_host(std::vector<A> &psi, int n, const 
     }
 }
 
-template <typename T, int RB> void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegProgram &P) {
+// what the XCHG = true kernel does with the stores of its last pass (null out_mine: the plain in-place kernel)
+template <typename A> struct EmuXchg {
+    A *out_mine = nullptr;
+    A *out_peer = nullptr;
+    uint64_t bit_mask = 0, keep = 0;
+};
+
+template <typename T, int RB>
+void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegProgram &P,
+                     const EmuXchg<typename Cx<T>::type> &xc = EmuXchg<typename Cx<T>::type>()) {
     using A = typename Cx<T>::type;
     constexpr int NS = 1 << RB, NT = 1 << (TB - RB), NTB = TB - RB;
     std::vector<A> smem(1 << TB);
@@ -105,7 +114,12 @@ template <typename T, int RB> void emulate_program(std::vector<typename Cx<T>::t
             for (uint32_t tid = 0; tid < (uint32_t)NT; ++tid) {
                 A(&x)[NS] = *reinterpret_cast<A(*)[NS]>(&xs[(size_t)tid * NS]);
                 pass_compute<T, RB>(x, P, ps, tid, outside, spool.data());
-                if (last) {
+                if (last && xc.out_mine) {
+                    const XchgTarget t = xchg_target(base, xc.bit_mask, xc.keep);
+                    A *dst = t.stays ? xc.out_mine : xc.out_peer;
+                    const uint64_t gt = t.base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
+                    for (int j = 0; j < NS; ++j) dst[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
+                } else if (last) {
                     const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
                     for (int j = 0; j < NS; ++j) psi[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
                 } else {
@@ -173,6 +187,75 @@ extern "C" double regs_emu_time_host_side(const void *ops_handle, int n, int dty
         }
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+
+// Two ranks of a register sharded on one global bit run the same batch of local gates and then exchange that global bit
+// with local bit `local_bit` the way dist_apply_ops does with QSV_DIST_FUSED_SWAP=1: the last sweep of the batch stores out
+// of place through xchg_target (carried = 1), or, when the exchanged bit is one of its tile bits or the batch ends in a lone
+// gate, the batch runs in place and a copy pass does the same stores (k_xchg_oop; carried = 0).  shard / out: 2^n_local
+// interleaved (re, im) doubles per rank.
+extern "C" int regs_emu_fused_exchange(const void *ops_handle, int n_local, int low_bits, int local_bit, const double *shard0,
+                                       const double *shard1, double *out0, double *out1, int *carried) {
+    try {
+        const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
+        std::vector<LoweredGate> gates;
+        for (const auto &op : ops->ops) {
+            if (op.name == "Identity") continue;
+            if (find_gate(op.name) != nullptr)
+                gates.push_back(lower_named(n_local, op.name, op.wires, op.params, op.inverse));
+            else
+                gates.push_back(lower_matrix(n_local, op.matrix.data(), {}, op.wires, op.inverse));
+        }
+        const std::vector<LoweredGate> merged = prepare_gates_regs(gates);
+        const int L = low_bits > 0 ? low_bits : 4;
+        const uint64_t N = 1ull << n_local;
+        const std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, true, 48, 512);
+        std::vector<double2> out[2] = {std::vector<double2>(N), std::vector<double2>(N)};
+        static RegProgram P;
+        for (int r = 0; r < 2; ++r) {
+            const double *in = r == 0 ? shard0 : shard1;
+            std::vector<double2> psi(N);
+            for (uint64_t i = 0; i < N; ++i) psi[i] = make_double2(in[2 * i], in[2 * i + 1]);
+            EmuXchg<double2> xc;
+            xc.out_mine = out[r].data();
+            xc.out_peer = out[1 - r].data();
+            xc.bit_mask = 1ull << local_bit;
+            xc.keep = r ? xc.bit_mask : 0;
+            bool done = false;
+            std::vector<const LoweredGate *> cur;
+            for (size_t k = 0; k < plan.size(); ++k) {
+                const SweepPlan &sw = plan[k];
+                if (!sw.fused) {
+                    apply_lowered_host(psi, n_local, merged[sw.gates[0]]);
+                    continue;
+                }
+                cur.clear();
+                for (int i : sw.gates) cur.push_back(&merged[i]);
+                build_reg_program(n_local, QSV_C128, 0, cur, sw.need, L, 4, P);
+                const bool carry = k + 1 == plan.size() && !regs_tile_contains_bit(n_local, sw.need, L, local_bit);
+                emulate_program<double, 4>(psi, n_local, P, carry ? xc : EmuXchg<double2>());
+                done = done || carry;
+            }
+            if (!done)  // the copy pass
+                for (uint64_t i = 0; i < N; ++i) {
+                    if ((i & xc.bit_mask) == xc.keep)
+                        xc.out_mine[i] = psi[i];
+                    else
+                        xc.out_peer[i ^ xc.bit_mask] = psi[i];
+                }
+            if (carried) *carried = done ? 1 : 0;
+        }
+        for (uint64_t i = 0; i < N; ++i) {
+            out0[2 * i] = out[0][i].x;
+            out0[2 * i + 1] = out[0][i].y;
+            out1[2 * i] = out[1][i].x;
+            out1[2 * i + 1] = out[1][i].y;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "regs_emu_fused_exchange: %s\n", e.what());
+        return 1;
+    }
 }
 
 // Per-sweep structure of the programs the host side builds for a circuit (no state needed): for sweep k,

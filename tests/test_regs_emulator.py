@@ -211,3 +211,42 @@ def test_two_qubit_blocks_absorb_neighbours(emu, merge2q, monkeypatch):
     if merge2q == "1":
         monkeypatch.setenv("QSV_MERGE_2Q", "0")
         assert plan["gates_after_merge"] < q.Ops(ops).plan_sweeps(n)["gates_after_merge"]
+
+
+def test_sweep_fused_with_exchange(emu):
+    """k_tile_regs<XCHG = true> (csrc/tile_regs.cu) + dist_apply_ops with QSV_DIST_FUSED_SWAP=1 (csrc/dist.cu), emulated
+    for the two ranks of a register sharded on one global bit: a batch of local gates whose last sweep stores out of place
+    through xchg_target (this rank's other buffer / the partner's, exchanged bit flipped), or the copy-pass form when that
+    sweep cannot carry it.  Must equal: gates on both shards, then global bit <-> local bit exchanged."""
+    import ctypes as C
+
+    import pennylane_lightning_gpu_b200 as q
+
+    dp = C.POINTER(C.c_double)
+    emu.regs_emu_fused_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    modes = set()
+    for n_local, local_bit, low in [(13, 12, 4), (14, 13, 4), (14, 9, 4), (13, 5, 4), (14, 12, 3), (13, 2, 4)]:
+        ops = random_mixed_circuit(n_local, 60, 70 + n_local + local_bit)
+        rec = q.Ops(ops)
+        shards = [rand_state(n_local, 200 + r) / np.sqrt(2) for r in range(2)]
+        want = [orc.apply_ops(s.copy(), ops) for s in shards]
+        # exchange of the rank bit with local bit `local_bit`: amplitude (rank = x, bit = y, rest) -> (rank = y, bit = x, rest)
+        idx = np.arange(1 << n_local)
+        bit = (idx >> local_bit) & 1
+        expect = [np.empty_like(want[0]), np.empty_like(want[0])]
+        for r in range(2):
+            for y in range(2):
+                src = idx[bit == y]                       # on rank r with the bit = y ...
+                dst = src ^ ((y ^ r) << local_bit)        # ... goes to rank y with the bit = r
+                expect[y][dst] = want[r][src]
+        out = [np.zeros(2 << n_local), np.zeros(2 << n_local)]
+        carried = C.c_int(-1)
+        ins = [np.ascontiguousarray(s).view(np.float64) for s in shards]
+        rc = emu.regs_emu_fused_exchange(rec._h, n_local, low, local_bit, ins[0].ctypes.data_as(dp), ins[1].ctypes.data_as(dp),
+                                         out[0].ctypes.data_as(dp), out[1].ctypes.data_as(dp), C.byref(carried))
+        assert rc == 0
+        for r in range(2):
+            got = out[r].view(np.complex128)
+            assert np.max(np.abs(got - expect[r])) < 1e-12, (n_local, local_bit, r, carried.value)
+        modes.add(carried.value)
+    assert modes == {0, 1}  # both forms ran: carried by the last sweep, and the copy pass (exchanged bit inside the tile)
