@@ -226,7 +226,9 @@ struct SweepPlan {
 };
 std::vector<LoweredGate> prepare_gates_regs(const std::vector<LoweredGate> &gates_in);
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag,
-                                        int max_gates, int window);
+                                        int max_gates, int window, int dtype = QSV_C128);
+// price of one fused sweep under the cost model of tools/sweep_cost_model.py (ms at 30 qubits complex128; only ratios matter)
+double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L);
 bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);
 bool regs_fusable(const LoweredGate &g, int n_local);
 uint64_t regs_need_bits(const LoweredGate &g);

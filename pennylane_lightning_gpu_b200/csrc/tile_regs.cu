@@ -300,6 +300,8 @@ int regs_rb() {
 
 }  // namespace
 
+static thread_local int t_beam_override = 0;  // > 0 while regs_sweep_model_cost prices candidates (greedy scheduler)
+
 // tile bits above the low L ones: the needed high bits, then the lowest free bits (ascending)
 std::vector<int> regs_tile_high_bits(int n, uint64_t need, int L) {
     std::vector<int> hi;
@@ -574,7 +576,7 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     std::vector<PassPick> planned;
     size_t plan_pos = 0;
     {
-        const int beam = std::max(1, env_int_regs("QSV_REGS_BEAM", n >= 26 ? 4 : 1));
+        const int beam = t_beam_override > 0 ? t_beam_override : std::max(1, env_int_regs("QSV_REGS_BEAM", n >= 26 ? 4 : 1));
         // cost of a sequence in 1/100 ms at 30 qubits complex128 (tools/sweep_cost_model.py, fitted to 17 measured
         // sweeps / circuits: a pass 0.96 ms, its tensor-core block 0.85 ms, a 4x4 / 2x2 gate on register bits 1.03 / 0.56 ms)
         auto pass_cost = [&](const PassPick &pk) {
@@ -994,6 +996,22 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     for (int i = 0; i < n_pool; ++i) P.poolf[i] = (float)P.pool[i];
     P.uniform_consts = env_flag("QSV_REGS_UCONST", 1) ? 1 : 0;
     P.prefetch = std::max(0, env_int_regs("QSV_REGS_PREFETCH", 0));
+}
+
+double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L) {
+    static thread_local RegProgram P;
+    t_beam_override = 1;
+    struct Reset {
+        ~Reset() { t_beam_override = 0; }
+    } reset;
+    build_reg_program(n, dtype, 0, gates, need, L, regs_rb(), P);
+    double c = 3.39 + 0.96 * P.n_passes;
+    for (int p = 0; p < P.n_passes; ++p) c += P.passes[p].mma_off != NO_MMA ? 0.85 : 0.0;
+    for (int g = 0; g < P.n_gates; ++g) {
+        const int k = P.gates[g].kind;
+        c += k == RG_D2 ? 1.03 : (k == RG_DIAG || k == RG_D1_DIAG) ? 0.20 : (k == RG_D1_SWAP ? 0.0 : 0.56);
+    }
+    return c;
 }
 
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,

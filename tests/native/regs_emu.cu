@@ -136,7 +136,7 @@ void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegPro
 template <typename T>
 void run_all(std::vector<typename Cx<T>::type> &psi, int n, int dtype, int rb, int L, bool dag, const std::vector<LoweredGate> &merged,
              int64_t *stats) {
-    const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, L, dag, 48, 512);
+    const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, L, dag, 48, 512, dtype);
     std::vector<const LoweredGate *> cur;
     static RegProgram P;
     for (const SweepPlan &sw : plan) {
@@ -280,7 +280,7 @@ extern "C" int regs_emu_sweep_stats(const void *ops_handle, int n, int dtype, in
         return v ? std::atoi(v) : dflt;
     };
     const std::vector<SweepPlan> plan = plan_sweeps_regs(n, merged, L, dag != 0, std::min(48, env_or("QSV_REGS_MAX_GATES", 48)),
-                                                         std::max(1, env_or("QSV_REGS_WINDOW", 512)));
+                                                         std::max(1, env_or("QSV_REGS_WINDOW", 512)), dtype);
     std::vector<const LoweredGate *> cur;
     int k = 0;
     for (const SweepPlan &sw : plan) {

@@ -144,6 +144,29 @@ def test_pass_sequence_search(emu, beam, dtype, monkeypatch):
     assert passes[beam] <= passes[1], passes
 
 
+@pytest.mark.parametrize("tries", [3, 8])
+def test_multi_start_sweep_packing(emu, tries, monkeypatch):
+    """csrc/tile_kernels.cu: plan_sweeps_regs tries several orders of offering the ready gates to first fit and keeps the
+    cheapest plan under the cost model (QSV_REGS_PACK_TRIES; default from 26 qubits up).  Whatever it picks must give the
+    oracle's state; on a layered ansatz it must not need more sweeps than program order."""
+    sweeps = {}
+    for t in (1, tries):
+        monkeypatch.setenv("QSV_REGS_PACK_TRIES", str(t))
+        for n, seed in ((13, 21), (15, 22)):
+            ops = random_mixed_circuit(n, 180, seed)
+            psi0 = rand_state(n, 60 + seed)
+            got, st = run_emulated(emu, ops, psi0)
+            assert np.max(np.abs(got - orc.apply_ops(psi0.copy(), ops))) < 1e-12, (t, n, st)
+        ladder, _ = workloads.hardware_efficient_ansatz(16, layers=4, seed=11)
+        psi0 = rand_state(16, 98)
+        got, st = run_emulated(emu, ladder, psi0)
+        assert np.max(np.abs(got - orc.apply_ops(psi0.copy(), ladder))) < 1e-12
+        got32, _ = run_emulated(emu, ladder, psi0, dtype=np.complex64)
+        assert np.max(np.abs(got32 - got)) < 3e-5
+        sweeps[t] = st["sweeps"]
+    assert sweeps[tries] <= sweeps[1], sweeps
+
+
 def test_permutation_only_and_ladders(emu):
     n = 12
     psi0 = rand_state(n, 3)

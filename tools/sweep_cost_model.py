@@ -11,7 +11,8 @@ Largest error 3.5 % on a single sweep, 2.5 % on a circuit.  Reading: a gate on r
 (2^30 amplitudes x 8 DFMA = 0.46 ms at 64 DFMA/clk/SM for a 2x2, 0.92 ms for a 4x4); a register pass costs what the
 shared-memory bandwidth needs for the transposition (2 x 16 GiB at 128 B/clk/SM = 0.92 ms); a tensor-core block costs
 0.85 ms however many gates were multiplied into it; 3.4 ms per sweep is HBM time the arithmetic does not hide (5.3 ms
-would be all of it).  The pass scheduler's beam search (csrc/tile_regs.cu, QSV_REGS_BEAM) minimises this model.
+would be all of it).  The pass scheduler's beam search (csrc/tile_regs.cu, QSV_REGS_BEAM) and the multi-start sweep
+packing (csrc/tile_kernels.cu, QSV_REGS_PACK_TRIES) minimise this model.
 Usage: python tools/sweep_cost_model.py [--fit]"""
 import ctypes as C
 import importlib.util
@@ -63,7 +64,7 @@ def main():
         a = np.array([[1, r[0], r[5], r[2], r[3], r[4]] for r in rows], float)
         print("per-sweep residuals (ms)", np.round(a @ COEF - np.array(MEASURED_MS), 2))
     print("config 2: sweeps", len(rows), "passes", sum(r[0] for r in rows), "tensor-core blocks", sum(r[5] for r in rows),
-          "predicted ms", round(predict(rows), 1), "(measured 111.7 with QSV_REGS_BEAM=1)")
+          "predicted ms", round(predict(rows), 1), "(measured 111.7 with QSV_REGS_BEAM=1 QSV_REGS_PACK_TRIES=1)")
     parts = COEF * np.array([len(rows), sum(r[0] for r in rows), sum(r[5] for r in rows), sum(r[2] for r in rows),
                              sum(r[3] for r in rows), sum(r[4] for r in rows)])
     print("  of which: sweeps %.1f, passes %.1f, tensor-core blocks %.1f, 4x4 gates %.1f, 2x2 gates %.1f, diagonal gates %.1f ms"
@@ -74,11 +75,11 @@ def main():
     hea, _ = workloads.hardware_efficient_ansatz(30, layers=4, seed=11)
     r = sweep_rows(lib, hea)
     print(f"30-qubit hardware-efficient ansatz: sweeps {len(r)} passes {sum(x[0] for x in r)} predicted {predict(r):.1f} "
-          "(measured 142.4 with QSV_REGS_BEAM=1)")
+          "(measured 142.4 with QSV_REGS_BEAM=1 QSV_REGS_PACK_TRIES=1)")
     sel, _ = workloads.strongly_entangling_layers(30, layers=2, seed=1337)
     r = sweep_rows(lib, sel)
     print(f"30-qubit StronglyEntanglingLayers x 2: sweeps {len(r)} passes {sum(x[0] for x in r)} predicted {predict(r):.1f} "
-          "(measured 77.5 with QSV_REGS_BEAM=1)")
+          "(measured 77.5 with QSV_REGS_BEAM=1 QSV_REGS_PACK_TRIES=1)")
 
 
 if __name__ == "__main__":
