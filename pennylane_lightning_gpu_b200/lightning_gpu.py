@@ -230,6 +230,55 @@ class LightningGPU(_Base):
             return "".join(_PAULI_LETTER[t.name] for t in o.terms), [t.wires[0] for t in o.terms]
         return None
 
+    _NAMED_MATRIX = {
+        "PauliX": np.array([[0, 1], [1, 0]], dtype=np.complex128),
+        "PauliY": np.array([[0, -1j], [1j, 0]], dtype=np.complex128),
+        "PauliZ": np.array([[1, 0], [0, -1]], dtype=np.complex128),
+        "Hadamard": np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2.0),
+        "Identity": np.eye(2, dtype=np.complex128),
+    }
+    _MAX_DENSE_WIRES = 10  # 2^10 x 2^10 complex128 = 16 MiB on the host; the reference builds qml.matrix up to 13 wires
+
+    @classmethod
+    def _matrix_of(cls, o: Obs):
+        """(wires, dense matrix on those wires in PennyLane order) of a named / Hermitian / Tensor / Hamiltonian observable:
+        what ``qml.matrix(observable)`` gives the reference (lightning_gpu.py:884-897, 936-960)."""
+        if o.name in cls._NAMED_MATRIX:
+            return list(o.wires), cls._NAMED_MATRIX[o.name]
+        if o.name == "Hermitian":
+            k = len(o.wires)
+            return list(o.wires), np.asarray(o.matrix, dtype=np.complex128).reshape(1 << k, 1 << k)
+        if o.name not in ("Tensor", "Hamiltonian"):
+            raise NotImplementedError(f"no dense matrix for observable {o.name}")
+        parts = [cls._matrix_of(t) for t in o.terms]
+        wires = []
+        for w, _ in parts:
+            wires += [x for x in w if x not in wires]
+        if len(wires) > cls._MAX_DENSE_WIRES:
+            raise NotImplementedError(f"dense matrix of an observable on {len(wires)} wires")
+        k = len(wires)
+
+        def embed(w, m):  # m on wires w -> the same operator on `wires`
+            if o.name == "Tensor" and any(x in seen for x in w):
+                raise ValueError("the factors of a tensor product must act on distinct wires")
+            rest = [x for x in wires if x not in w]
+            full = np.kron(m, np.eye(1 << len(rest), dtype=np.complex128)).reshape([2] * (2 * k))
+            order = list(w) + rest                          # current axis order of the row (and column) indices
+            perm = [order.index(x) for x in wires]
+            return full.transpose(perm + [k + p for p in perm]).reshape(1 << k, 1 << k)
+
+        seen = []
+        if o.name == "Tensor":
+            out = np.eye(1 << k, dtype=np.complex128)
+            for w, m in parts:
+                out = out @ embed(w, m)
+                seen += list(w)
+            return wires, out
+        out = np.zeros((1 << k, 1 << k), dtype=np.complex128)
+        for c, (w, m) in zip(o.coeffs, parts):
+            out = out + complex(c) * embed(w, m)
+        return wires, out
+
     def expval(self, observable: Obs, shot_range=None, bin_size=None) -> float:
         """Routing of lightning_gpu.py:820-897, except that a Hamiltonian of Pauli words always takes the
         fused Pauli-word kernels (the reference builds a dense 2^k x 2^k host matrix below 14 wires)."""
@@ -253,7 +302,9 @@ class LightningGPU(_Base):
         if word is not None and observable.name == "Tensor":
             return self._gpu_state.ExpectationValue([word[0]], [word[1]], np.ones(1, dtype=self.C_DTYPE))
         if observable.name == "Tensor":
-            raise NotImplementedError("tensor products with non-Pauli factors: use Obs('Hermitian', ...) of the product")
+            # factors other than Pauli letters (Hadamard, Hermitian): the dense matrix of the product, as the reference does
+            wires, m = self._matrix_of(observable)
+            return self._gpu_state.ExpectationValue(wires, m.astype(self.C_DTYPE).reshape(-1))
         return self._gpu_state.ExpectationValue(observable.name, list(observable.wires), [],
                                                 np.zeros(0, dtype=self.C_DTYPE))
 
@@ -264,11 +315,10 @@ class LightningGPU(_Base):
         mean = self.expval(observable)
         if observable.name in ("PauliX", "PauliY", "PauliZ", "Hadamard", "Identity") or self._pauli_word(observable):
             return 1.0 - mean**2
-        if observable.name == "Hermitian":
-            m = np.asarray(observable.matrix, dtype=np.complex128)
-            sq = self._gpu_state.ExpectationValue(list(observable.wires), (m @ m).astype(self.C_DTYPE).reshape(-1))
-            return sq - mean**2
-        raise NotImplementedError(f"variance of {observable.name}")
+        # <O^dagger O> - <O>^2 from the dense matrix of the observable (lightning_gpu.py:944-960)
+        wires, m = self._matrix_of(observable)
+        sq = self._gpu_state.ExpectationValue(wires, (m.conj().T @ m).astype(self.C_DTYPE).reshape(-1))
+        return sq - mean**2
 
     def probability(self, wires=None, shot_range=None, bin_size=None) -> np.ndarray:
         """Marginal probabilities in PennyLane order; the binary returns cuStateVec bit order and is

@@ -47,3 +47,32 @@ def test_constructor_argument_checks(lg):
         lg.LightningGPU(2, mpi_buf_size=-1)
     with pytest.raises(TypeError, match="power of 2"):
         lg.LightningGPU(2, mpi_buf_size=3)
+
+
+def test_dense_matrix_of_composite_observables(lg):
+    """LightningGPU._matrix_of (what qml.matrix(observable) is to the reference's expval / var): tensor products with
+    non-Pauli factors on unordered wires and Hamiltonians of them, against factor-by-factor application in the oracle."""
+    from oracle import np_oracle as orc
+
+    rng = np.random.default_rng(0)
+    h = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    h = h + h.conj().T
+    named = lg.LightningGPU._NAMED_MATRIX
+    t = lg.Obs("Tensor", terms=[lg.Obs("Hadamard", [2]), lg.Obs("Hermitian", [0, 3], matrix=h), lg.Obs("PauliY", [1])])
+    wires, m = lg.LightningGPU._matrix_of(t)
+    assert wires == [2, 0, 3, 1] and np.allclose(m, m.conj().T)
+    psi = rng.normal(size=16) + 1j * rng.normal(size=16)
+    psi /= np.linalg.norm(psi)
+    phi = orc.apply_matrix(psi.copy(), named["Hadamard"], [2])
+    phi = orc.apply_matrix(phi, h, [0, 3])
+    phi = orc.apply_matrix(phi, named["PauliY"], [1])
+    assert abs(orc.expval_matrix(psi, m, wires) - np.vdot(psi, phi)) < 1e-12
+    ham = lg.Obs("Hamiltonian", coeffs=[0.5, -2.0], terms=[lg.Obs("PauliZ", [3]), t])
+    wires2, m2 = lg.LightningGPU._matrix_of(ham)
+    phi2 = 0.5 * orc.apply_matrix(psi.copy(), named["PauliZ"], [3]) - 2.0 * phi
+    assert sorted(wires2) == [0, 1, 2, 3]
+    assert abs(orc.expval_matrix(psi, m2, wires2) - np.vdot(psi, phi2)) < 1e-12
+    with pytest.raises(ValueError, match="distinct wires"):
+        lg.LightningGPU._matrix_of(lg.Obs("Tensor", terms=[lg.Obs("PauliX", [0]), lg.Obs("Hadamard", [0])]))
+    with pytest.raises(NotImplementedError):
+        lg.LightningGPU._matrix_of(lg.Obs("Tensor", terms=[lg.Obs("Hadamard", [w]) for w in range(11)]))
