@@ -58,6 +58,15 @@ def test_apply_state_expval_var_probs(dev_mod, c_dtype, tol):
     ho = lg.Obs("Hermitian", [1], matrix=h)
     assert abs(dev.expval(ho) - orc.expval_matrix(psi, h, [1]).real) < tol * 10
     assert abs(dev.var(ho) - (orc.expval_matrix(psi, h @ h, [1]).real - orc.expval_matrix(psi, h, [1]).real ** 2)) < tol * 50
+    # tensor product with non-Pauli factors on unordered wires, and variances of composite observables: through the
+    # observable's dense matrix (lightning_gpu.py:884-897, 936-960)
+    t2 = lg.Obs("Tensor", terms=[lg.Obs("Hadamard", [3]), ho, lg.Obs("PauliY", [0])])
+    w2, m2 = lg.LightningGPU._matrix_of(t2)
+    e2 = orc.expval_matrix(psi, m2, w2).real
+    assert abs(dev.expval(t2) - e2) < tol * 10
+    assert abs(dev.var(t2) - (orc.expval_matrix(psi, m2 @ m2, w2).real - e2 ** 2)) < tol * 50
+    wh, mh = lg.LightningGPU._matrix_of(ham)
+    assert abs(dev.var(ham) - (orc.expval_matrix(psi, mh @ mh, wh).real - want_h ** 2)) < tol * 50
     for wires in ([0], [1, 3], [0, 2, 4], list(range(n))):
         assert np.max(np.abs(dev.probability(wires) - orc.probs(psi.astype(c_dtype), wires))) < tol
     with pytest.raises(RuntimeError, match="out-of-order"):
