@@ -17,6 +17,7 @@
 // Tile: 64 KiB (2^12 complex128 or 2^13 complex64), 256 threads, 3 CTAs / SM; the loads of one CTA
 // overlap the arithmetic and stores of its neighbours, so no intra-CTA pipeline is needed.
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 #include <map>
 
@@ -751,7 +752,8 @@ static std::vector<SweepPlan> plan_sweeps_once(int n_local, const std::vector<Lo
     return plan;
 }
 
-// Multi-start packing (QSV_REGS_PACK_TRIES; default 4 from 26 qubits up, else 1): first fit depends on the
+// Multi-start packing (QSV_REGS_PACK_TRIES; default 4 from 28 qubits up -- where its 2 ms of host time are under a tenth
+// of the circuit's GPU time even when nothing overlaps them -- else 1): first fit depends on the
 // order in which the ready gates are offered.  Program order is close to the best found for random circuits, but on layered
 // circuits (rotations on every wire + an entangling ladder) other orders need fewer sweeps and passes -- the 30-qubit
 // hardware-efficient ansatz: 9 sweeps / 25 passes instead of 11 / 30.  Every candidate is priced with the cost model of
@@ -760,7 +762,7 @@ static std::vector<SweepPlan> plan_sweeps_once(int n_local, const std::vector<Lo
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag, int max_gates,
                                         int window, int dtype) {
     std::vector<SweepPlan> best = plan_sweeps_once(n_local, gates, L, dag, max_gates, window, 0);
-    const int tries = dag && n_local >= 12 ? std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 26 ? 4 : 1)) : 1;
+    const int tries = dag && n_local >= 12 ? std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 28 ? 4 : 1)) : 1;
     if (tries <= 1) return best;
     std::vector<const LoweredGate *> cur;
     auto price = [&](const std::vector<SweepPlan> &plan) {
@@ -799,14 +801,77 @@ bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b) {
     return ((da & bb) | (ba & db)) == 0;
 }
 
+// Sweep plans of the circuits seen last, keyed by the structure of the merged gate list (kinds and index bits, not the
+// matrix entries: dependencies and tile needs are structural).  A variational loop or a benchmark applies the same
+// structure again and again; the multi-start packing then costs its 2 ms of host time once.
+namespace {
+struct PlanCacheEntry {
+    uint64_t h1 = 0, h2 = 0;
+    std::vector<SweepPlan> plan;
+};
+std::mutex g_plan_cache_mu;
+std::vector<PlanCacheEntry> g_plan_cache;  // most recently used first, at most 32 entries
+
+void structure_hash(const std::vector<LoweredGate> &gates, const int *params, int n_params, uint64_t &h1, uint64_t &h2) {
+    h1 = 0xcbf29ce484222325ull;
+    h2 = 0x9e3779b97f4a7c15ull;
+    auto mix = [&](uint64_t v) {
+        h1 = (h1 ^ v) * 0x100000001b3ull;
+        h2 = (h2 + v) * 0xff51afd7ed558ccdull;
+        h2 ^= h2 >> 33;
+    };
+    for (int i = 0; i < n_params; ++i) mix((uint64_t)(int64_t)params[i]);
+    for (const LoweredGate &g : gates) {
+        mix(0xabcdefull + (uint64_t)g.kind * 131u + (uint64_t)g.k);
+        mix(g.ctrl_mask);
+        mix(g.zmask);
+        mix(g.holes.size());
+        for (int h : g.holes) mix((uint64_t)h);
+        mix(g.tgt_bits.size());
+        for (int b : g.tgt_bits) mix((uint64_t)b);
+        mix(g.offs.size());
+        for (uint64_t o : g.offs) mix(o);
+    }
+}
+}  // namespace
+
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
                              FusedExchange *fx) {
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const std::vector<LoweredGate> merged = prepare_gates_regs(gates_in);
-    const std::vector<SweepPlan> plan =
-        plan_sweeps_regs(sv.n, merged, L, env_int("QSV_REGS_DAG", 1) != 0, std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
-                         std::max(1, env_int("QSV_REGS_WINDOW", 512)), sv.dtype);
+    const int dag = env_int("QSV_REGS_DAG", 1) != 0, max_gates = std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
+              window = std::max(1, env_int("QSV_REGS_WINDOW", 512));
+    std::vector<SweepPlan> plan;
+    const bool use_cache = env_int("QSV_REGS_PLAN_CACHE", 1) != 0;
+    uint64_t h1 = 0, h2 = 0;
+    bool hit = false;
+    if (use_cache) {
+        const int key[] = {sv.n, L, dag, max_gates, window, sv.dtype, env_int("QSV_REGS_PACK_TRIES", -1), env_int("QSV_REGS_RB", 4),
+                           env_int("QSV_REGS_MMA", 2), env_int("QSV_REGS_FOLD", 1), env_int("QSV_REGS_UDIAG", 1),
+                           env_int("QSV_REGS_DIAG1", 1)};
+        structure_hash(merged, key, (int)(sizeof(key) / sizeof(key[0])), h1, h2);
+        std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+        for (size_t i = 0; i < g_plan_cache.size(); ++i)
+            if (g_plan_cache[i].h1 == h1 && g_plan_cache[i].h2 == h2) {
+                plan = g_plan_cache[i].plan;
+                if (i != 0) std::rotate(g_plan_cache.begin(), g_plan_cache.begin() + i, g_plan_cache.begin() + i + 1);
+                hit = true;
+                break;
+            }
+    }
+    if (!hit) {
+        plan = plan_sweeps_regs(sv.n, merged, L, dag != 0, max_gates, window, sv.dtype);
+        if (use_cache) {
+            std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+            PlanCacheEntry e;
+            e.h1 = h1;
+            e.h2 = h2;
+            e.plan = plan;
+            g_plan_cache.insert(g_plan_cache.begin(), std::move(e));
+            if (g_plan_cache.size() > 32) g_plan_cache.pop_back();
+        }
+    }
     std::vector<const LoweredGate *> cur;
     for (size_t k = 0; k < plan.size(); ++k) {
         const SweepPlan &sw = plan[k];
