@@ -374,7 +374,7 @@ int qsv_ops_plan_sweeps(const qsv_ops *ops, int n_qubits, int dag, int low_bits,
     QSV_CHECK(n_qubits >= 12 && n_qubits <= 62, "sweep planning needs 12..62 qubits");
     const int L = std::max(1, std::min(low_bits > 0 ? low_bits : 4, 11));
     const std::vector<LoweredGate> merged = prepare_gates_regs(lower_all(n_qubits, ops));
-    const std::vector<SweepPlan> plan = plan_sweeps_regs(n_qubits, merged, L, dag != 0, 48, 512);
+    const std::vector<SweepPlan> plan = plan_sweeps_cached(n_qubits, merged, L, dag != 0, 48, 512, QSV_C128);
     // self-check: every gate exactly once, and every pair that does not commute structurally keeps its order
     std::vector<int64_t> pos(merged.size(), -1);
     int64_t at = 0, biggest = 0, total = 0;

@@ -227,6 +227,9 @@ struct SweepPlan {
 std::vector<LoweredGate> prepare_gates_regs(const std::vector<LoweredGate> &gates_in);
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag,
                                         int max_gates, int window, int dtype = QSV_C128);
+// the same through a small cache keyed by the structure of the gate list (kinds and index bits, not matrix entries)
+std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<LoweredGate> &merged, int L, bool dag, int max_gates,
+                                          int window, int dtype);
 // price of one fused sweep under the cost model of tools/sweep_cost_model.py (ms at 30 qubits complex128; only ratios matter)
 double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L);
 bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);

@@ -835,43 +835,41 @@ void structure_hash(const std::vector<LoweredGate> &gates, const int *params, in
 }
 }  // namespace
 
+std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<LoweredGate> &merged, int L, bool dag, int max_gates,
+                                          int window, int dtype) {
+    if (env_int("QSV_REGS_PLAN_CACHE", 1) == 0) return plan_sweeps_regs(n_local, merged, L, dag, max_gates, window, dtype);
+    uint64_t h1 = 0, h2 = 0;
+    const int key[] = {n_local, L, (int)dag, max_gates, window, dtype, env_int("QSV_REGS_PACK_TRIES", -1), env_int("QSV_REGS_RB", 4),
+                       env_int("QSV_REGS_MMA", 2), env_int("QSV_REGS_FOLD", 1), env_int("QSV_REGS_UDIAG", 1),
+                       env_int("QSV_REGS_DIAG1", 1)};
+    structure_hash(merged, key, (int)(sizeof(key) / sizeof(key[0])), h1, h2);
+    {
+        std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+        for (size_t i = 0; i < g_plan_cache.size(); ++i)
+            if (g_plan_cache[i].h1 == h1 && g_plan_cache[i].h2 == h2) {
+                if (i != 0) std::rotate(g_plan_cache.begin(), g_plan_cache.begin() + i, g_plan_cache.begin() + i + 1);
+                return g_plan_cache[0].plan;
+            }
+    }
+    std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, dag, max_gates, window, dtype);
+    std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+    PlanCacheEntry e;
+    e.h1 = h1;
+    e.h2 = h2;
+    e.plan = plan;
+    g_plan_cache.insert(g_plan_cache.begin(), std::move(e));
+    if (g_plan_cache.size() > 32) g_plan_cache.pop_back();
+    return plan;
+}
+
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
                              FusedExchange *fx) {
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const std::vector<LoweredGate> merged = prepare_gates_regs(gates_in);
-    const int dag = env_int("QSV_REGS_DAG", 1) != 0, max_gates = std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
-              window = std::max(1, env_int("QSV_REGS_WINDOW", 512));
-    std::vector<SweepPlan> plan;
-    const bool use_cache = env_int("QSV_REGS_PLAN_CACHE", 1) != 0;
-    uint64_t h1 = 0, h2 = 0;
-    bool hit = false;
-    if (use_cache) {
-        const int key[] = {sv.n, L, dag, max_gates, window, sv.dtype, env_int("QSV_REGS_PACK_TRIES", -1), env_int("QSV_REGS_RB", 4),
-                           env_int("QSV_REGS_MMA", 2), env_int("QSV_REGS_FOLD", 1), env_int("QSV_REGS_UDIAG", 1),
-                           env_int("QSV_REGS_DIAG1", 1)};
-        structure_hash(merged, key, (int)(sizeof(key) / sizeof(key[0])), h1, h2);
-        std::lock_guard<std::mutex> lock(g_plan_cache_mu);
-        for (size_t i = 0; i < g_plan_cache.size(); ++i)
-            if (g_plan_cache[i].h1 == h1 && g_plan_cache[i].h2 == h2) {
-                plan = g_plan_cache[i].plan;
-                if (i != 0) std::rotate(g_plan_cache.begin(), g_plan_cache.begin() + i, g_plan_cache.begin() + i + 1);
-                hit = true;
-                break;
-            }
-    }
-    if (!hit) {
-        plan = plan_sweeps_regs(sv.n, merged, L, dag != 0, max_gates, window, sv.dtype);
-        if (use_cache) {
-            std::lock_guard<std::mutex> lock(g_plan_cache_mu);
-            PlanCacheEntry e;
-            e.h1 = h1;
-            e.h2 = h2;
-            e.plan = plan;
-            g_plan_cache.insert(g_plan_cache.begin(), std::move(e));
-            if (g_plan_cache.size() > 32) g_plan_cache.pop_back();
-        }
-    }
+    const std::vector<SweepPlan> plan =
+        plan_sweeps_cached(sv.n, merged, L, env_int("QSV_REGS_DAG", 1) != 0, std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
+                           std::max(1, env_int("QSV_REGS_WINDOW", 512)), sv.dtype);
     std::vector<const LoweredGate *> cur;
     for (size_t k = 0; k < plan.size(); ++k) {
         const SweepPlan &sw = plan[k];

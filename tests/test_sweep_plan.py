@@ -58,3 +58,24 @@ def test_plan_rejects_unknown_gate(q):
     rec = q.Ops([{"name": "NoSuchGate", "wires": [0], "params": []}])
     with pytest.raises(q.QsvError):
         rec.plan_sweeps(20)
+
+
+def test_plan_cache_is_keyed_by_structure(q, monkeypatch):
+    """csrc/tile_kernels.cu: plan_sweeps_cached.  The same gate structure with other angles reuses the cached plan, another
+    structure does not, and every plan that comes back is valid for the circuit it was asked for."""
+    ops = workloads.random_gate_circuit(30, 200, 2024)
+    first = q.Ops(ops).plan_sweeps(30, dag=True)
+    again = q.Ops(ops).plan_sweeps(30, dag=True)
+    scaled = [dict(o) for o in ops]
+    for o in scaled:
+        if o.get("params"):
+            o["params"] = [0.5 * p + 0.1 for p in o["params"]]
+    same_structure = q.Ops(scaled).plan_sweeps(30, dag=True)
+    other = q.Ops(workloads.random_gate_circuit(30, 200, 7)).plan_sweeps(30, dag=True)
+    for p in (first, again, same_structure, other):
+        assert p["order_valid"]
+    assert first["sweeps"] == again["sweeps"] == same_structure["sweeps"]
+    assert first["gates_after_merge"] == same_structure["gates_after_merge"]
+    monkeypatch.setenv("QSV_REGS_PLAN_CACHE", "0")
+    uncached = q.Ops(ops).plan_sweeps(30, dag=True)
+    assert uncached["order_valid"] and uncached["sweeps"] == first["sweeps"]
