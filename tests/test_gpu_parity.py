@@ -586,7 +586,8 @@ def test_register_tile_kernel_stress(q, n, low, rb, dtype, monkeypatch):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("env", [{}, {"QSV_REGS_FOLD": "0"}, {"QSV_REGS_UDIAG": "0", "QSV_REGS_DIAG1": "0"},
                                  {"QSV_REGS_DAG": "0"}, {"QSV_REGS_PREFETCH": "3"}, {"QSV_REGS_RB": "3"}, {"QSV_REGS_MMA": "0"},
-                                 {"QSV_REGS_UCONST": "0"}, {"QSV_MERGE_2Q": "0"}, {"QSV_REGS_BEAM": "4"}])
+                                 {"QSV_REGS_UCONST": "0"}, {"QSV_MERGE_2Q": "0"}, {"QSV_REGS_BEAM": "4"},
+                                 {"QSV_REGS_PACK_TRIES": "4", "QSV_REGS_BEAM": "4"}, {"QSV_REGS_PLAN_CACHE": "0"}])
 def test_register_tile_feature_switches(q, env, dtype, monkeypatch):
     """csrc/tile_regs.cu: index permutations folded into pass boundaries (PauliX / CNOT / SWAP), merged thread-uniform
     diagonal gates, diagonal-as-2x2, DAG sweep packing and the L2 prefetch, each switched off in turn; CNOT ladders and
