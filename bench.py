@@ -291,6 +291,17 @@ def run_ours(args):
             ("fused sweeps are shared-memory-bandwidth-bound (1024 clk per gate per 64 KiB tile), not "
              "HBM-bound: see DESIGN.md 4.2; --fuse 0 gives the HBM-bound one-sweep-per-gate kernels")
 
+    if fused and regs_kernel and not distributed:
+        # the compute view of the same launches: fused multiply-adds the planner's programs execute (host-side count,
+        # qsv_ops_plan_work) against the FP64 / FP32 pipe: 64 DFMA (128 FFMA) per clock and SM, 148 SMs
+        work = rec.plan_work(n_local, cdtype)
+        flops = 2.0 * work["fma_per_amplitude"] * float(1 << n_local)
+        per_clk = 64 if args.dtype == "c128" else 128
+        roofline["compute"] = {"pipe": "fp64" if args.dtype == "c128" else "fp32",
+                               "fma_per_amplitude": work["fma_per_amplitude"], "passes_per_step": work["passes"],
+                               "tflops": flops / (ms_per_step * 1e-3) / 1e12,
+                               "peak_tflops_per_ghz": 148 * per_clk * 2 / 1e3}
+
     detail = {}
     if distributed:
         n_swaps, swap_bytes, swap_ms = sv.swap_stats()
@@ -389,6 +400,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "hbm_sweeps": sweeps, "clocks": clk.summary(), "detail": detail,
         }
+        comp = roofline.get("compute")
+        if comp and line["clocks"].get("sm_mhz"):
+            comp["peak_tflops"] = comp.pop("peak_tflops_per_ghz") * line["clocks"]["sm_mhz"] / 1e3
+            comp["frac"] = comp["tflops"] / comp["peak_tflops"]
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()

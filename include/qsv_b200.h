@@ -107,6 +107,10 @@ int qsv_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse);
  * exactly once and every pair of gates that does not commute structurally keeps its program order. */
 int qsv_ops_plan_sweeps(const qsv_ops *ops, int n_qubits, int dag, int low_bits, int64_t *n_gates_merged,
                         int64_t *n_sweeps, int64_t *max_gates_per_sweep, int *order_valid);
+/* host-only: the arithmetic apply_ops(fuse = 1) performs for this circuit with the default planner settings -- fused
+ * multiply-adds per amplitude (multiply by 2^n_qubits for the whole state), HBM sweeps and register passes */
+int qsv_ops_plan_work(const qsv_ops *ops, int n_qubits, int dtype, double *fma_per_amplitude, int64_t *n_sweeps,
+                      int64_t *n_passes);
 /* statistics of the last qsv_apply_ops on this state: kernel launches and HBM sweeps */
 int qsv_last_apply_stats(const qsv_state *sv, int64_t *launches, int64_t *sweeps);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "qsv_ops_size": (_I, [_P]),
     "qsv_apply_ops": (_I, [_P, _P, _I]),
     "qsv_ops_plan_sweeps": (_I, [_P, _I, _I, _I, _I64P, _I64P, _I64P, _IP]),
+    "qsv_ops_plan_work": (_I, [_P, _I, _I, _DP, _I64P, _I64P]),
     "qsv_last_apply_stats": (_I, [_P, _I64P, _I64P]),
     "qsv_expval_named": (_I, [_P, C.c_char_p, _IP, _I, _DP, _I, _DP]),
     "qsv_expval_matrix": (_I, [_P, _DP, _IP, _I, _DP]),
@@ -202,6 +203,14 @@ class Ops:
                                          C.byref(g), C.byref(ok)))
         return {"gates_after_merge": m.value, "sweeps": s.value, "max_gates_per_sweep": g.value,
                 "order_valid": bool(ok.value)}
+
+    def plan_work(self, n_qubits: int, dtype=np.complex128) -> dict:
+        """Host-only: arithmetic of apply_ops(fuse=True) on this circuit -- fused multiply-adds per amplitude, HBM sweeps
+        and register passes of the programs the planner builds (no device needed)."""
+        f, s, p = C.c_double(), C.c_int64(), C.c_int64()
+        code = QSV_C128 if np.dtype(dtype) == np.complex128 else QSV_C64
+        _check(lib().qsv_ops_plan_work(self._h, n_qubits, code, C.byref(f), C.byref(s), C.byref(p)))
+        return {"fma_per_amplitude": f.value, "sweeps": s.value, "passes": p.value}
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

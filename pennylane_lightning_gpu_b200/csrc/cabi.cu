@@ -367,6 +367,39 @@ int qsv_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse) {
     QSV_API_END
 }
 
+int qsv_ops_plan_work(const qsv_ops *ops, int n_qubits, int dtype, double *fma_per_amplitude, int64_t *n_sweeps,
+                      int64_t *n_passes) {
+    QSV_API_BEGIN
+    need(ops, "ops");
+    QSV_CHECK(n_qubits >= 12 && n_qubits <= 62, "sweep planning needs 12..62 qubits");
+    QSV_CHECK(dtype == QSV_C64 || dtype == QSV_C128, "dtype must be QSV_C64 or QSV_C128");
+    const std::vector<LoweredGate> merged = prepare_gates_regs(lower_all(n_qubits, ops));
+    const std::vector<SweepPlan> plan = plan_sweeps_cached(n_qubits, merged, 4, true, 48, 512, dtype);
+    double fma = 0.0;
+    int64_t passes = 0;
+    std::vector<const LoweredGate *> cur;
+    for (const SweepPlan &sw : plan) {
+        if (!sw.fused) {
+            // a lone gate through the one-sweep kernels: 2^k x 2^k block = 4 * 2^k multiply-adds per amplitude, diagonal 4
+            const LoweredGate &g = merged[sw.gates[0]];
+            const double w = g.kind == LoweredGate::DENSE ? 4.0 * (double)(1 << g.k) : 4.0;
+            fma += w / (double)(1ull << __builtin_popcountll(g.ctrl_mask));
+            continue;
+        }
+        cur.clear();
+        for (int i : sw.gates) cur.push_back(&merged[i]);
+        double f = 0.0;
+        int p = 0;
+        regs_sweep_work(n_qubits, dtype, cur, sw.need, 4, &f, &p);
+        fma += f;
+        passes += p;
+    }
+    if (fma_per_amplitude) *fma_per_amplitude = fma;
+    if (n_sweeps) *n_sweeps = (int64_t)plan.size();
+    if (n_passes) *n_passes = passes;
+    QSV_API_END
+}
+
 int qsv_ops_plan_sweeps(const qsv_ops *ops, int n_qubits, int dag, int low_bits, int64_t *n_gates_merged,
                         int64_t *n_sweeps, int64_t *max_gates_per_sweep, int *order_valid) {
     QSV_API_BEGIN

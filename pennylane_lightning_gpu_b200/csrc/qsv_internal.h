@@ -230,6 +230,9 @@ std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGa
 // the same through a small cache keyed by the structure of the gate list (kinds and index bits, not matrix entries)
 std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<LoweredGate> &merged, int L, bool dag, int max_gates,
                                           int window, int dtype);
+// arithmetic of one fused sweep: fused multiply-adds per amplitude and register passes of the program built for it
+void regs_sweep_work(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, double *fma_per_amp,
+                     int *passes);
 // price of one fused sweep under the cost model of tools/sweep_cost_model.py (ms at 30 qubits complex128; only ratios matter)
 double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L);
 bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);

@@ -1014,6 +1014,25 @@ double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGa
     return c;
 }
 
+// FP64 (FP32 for complex64) fused multiply-adds per amplitude that the program of one fused sweep executes, and its
+// passes: 2x2 gate 8 (real matrix or RX 4), 4x4 gate 16, tensor-core block 16 (the real 8x8 form on 4 amplitudes),
+// diagonal gate 4 (one complex multiplication); a controlled gate works on 1 / 2^controls of the amplitudes.
+void regs_sweep_work(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, double *fma_per_amp,
+                     int *passes) {
+    static thread_local RegProgram P;
+    build_reg_program(n, dtype, 0, gates, need, L, regs_rb(), P);
+    double f = 0.0;
+    for (int p = 0; p < P.n_passes; ++p) f += P.passes[p].mma_off != NO_MMA ? 16.0 : 0.0;
+    for (int g = 0; g < P.n_gates; ++g) {
+        const RegGate &t = P.gates[g];
+        const double w = t.kind == RG_D2 ? 16.0 : (t.kind == RG_D1 ? 8.0 : (t.kind == RG_D1_SWAP ? 0.0 : 4.0));
+        const int n_ctrl = __builtin_popcount(t.ctrl_reg) + __builtin_popcount(t.ctrl_thr) + __builtin_popcountll(t.out_ctrl);
+        f += w / (double)(1ull << n_ctrl);
+    }
+    if (fma_per_amp) *fma_per_amp = f;
+    if (passes) *passes = P.n_passes;
+}
+
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,
                     int n_vecs, const FusedExchange *fx) {
     const int rb = regs_rb();

@@ -79,3 +79,18 @@ def test_plan_cache_is_keyed_by_structure(q, monkeypatch):
     monkeypatch.setenv("QSV_REGS_PLAN_CACHE", "0")
     uncached = q.Ops(ops).plan_sweeps(30, dag=True)
     assert uncached["order_valid"] and uncached["sweeps"] == first["sweeps"]
+
+
+def test_plan_work_counts_arithmetic(q):
+    """qsv_ops_plan_work: multiply-adds per amplitude of the fused programs.  Two uncontrolled 2x2 gates on different
+    qubits cost 8 each (or one tensor-core block of 16 for both); a CNOT is folded into the address maps and costs nothing;
+    the config-2 circuit lands between its diagonal-only and all-dense bounds."""
+    w = q.Ops([{"name": "RX", "wires": [3], "params": [0.3]}, {"name": "Hadamard", "wires": [7], "params": []},
+               {"name": "CNOT", "wires": [1, 2], "params": []}]).plan_work(20)
+    assert w["sweeps"] == 1 and w["passes"] == 1 and 8.0 <= w["fma_per_amplitude"] <= 16.0
+    ops = workloads.random_gate_circuit(30, 200, 2024)
+    w = q.Ops(ops).plan_work(30)
+    assert w["sweeps"] <= 9 and w["passes"] >= w["sweeps"]
+    assert 4.0 * 60 < w["fma_per_amplitude"] < 16.0 * 200
+    w32 = q.Ops(ops).plan_work(30, np.complex64)
+    assert w32["sweeps"] == w["sweeps"]
