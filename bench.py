@@ -294,13 +294,16 @@ def run_ours(args):
     if fused and regs_kernel and not distributed:
         # the compute view of the same launches: fused multiply-adds the planner's programs execute (host-side count,
         # qsv_ops_plan_work) against the FP64 / FP32 pipe: 64 DFMA (128 FFMA) per clock and SM, 148 SMs
-        work = rec.plan_work(n_local, cdtype)
-        flops = 2.0 * work["fma_per_amplitude"] * float(1 << n_local)
-        per_clk = 64 if args.dtype == "c128" else 128
-        roofline["compute"] = {"pipe": "fp64" if args.dtype == "c128" else "fp32",
-                               "fma_per_amplitude": work["fma_per_amplitude"], "passes_per_step": work["passes"],
-                               "tflops": flops / (ms_per_step * 1e-3) / 1e12,
-                               "peak_tflops_per_ghz": 148 * per_clk * 2 / 1e3}
+        try:
+            work = rec.plan_work(n_local, cdtype)
+            flops = 2.0 * work["fma_per_amplitude"] * float(1 << n_local)
+            per_clk = 64 if args.dtype == "c128" else 128
+            roofline["compute"] = {"pipe": "fp64" if args.dtype == "c128" else "fp32",
+                                   "fma_per_amplitude": work["fma_per_amplitude"], "passes_per_step": work["passes"],
+                                   "tflops": flops / (ms_per_step * 1e-3) / 1e12,
+                                   "peak_tflops_per_ghz": 148 * per_clk * 2 / 1e3}
+        except Exception as e:  # a reporting extra must not cost the bench line
+            roofline["compute"] = {"error": str(e)}
 
     detail = {}
     if distributed:
@@ -401,7 +404,7 @@ def run_ours(args):
             "hbm_sweeps": sweeps, "clocks": clk.summary(), "detail": detail,
         }
         comp = roofline.get("compute")
-        if comp and line["clocks"].get("sm_mhz"):
+        if comp and "tflops" in comp and (line["clocks"] or {}).get("sm_mhz"):
             comp["peak_tflops"] = comp.pop("peak_tflops_per_ghz") * line["clocks"]["sm_mhz"] / 1e3
             comp["frac"] = comp["tflops"] / comp["peak_tflops"]
         print(json.dumps(line), flush=True)
