@@ -320,7 +320,10 @@ def run_ours(args):
             "frac_of_770_measured_peer_copy": ((swap_bytes / 1e9) / (swap_ms * 1e-3) / 770.0) if swap_ms > 0 else None,
             "swap_ms_per_step": swap_ms / args.steps,
         }
-        n_oop, n_carried = sv.fused_exchange_stats()
+        try:
+            n_oop, n_carried = sv.fused_exchange_stats()
+        except Exception:  # a reporting extra must not cost the bench line
+            n_oop, n_carried = 0, 0
         if n_oop:  # QSV_DIST_FUSED_SWAP=1: exchanges stored by the sweep before them (not part of the swap timing above)
             total_steps = args.steps + max(args.warmup, 3)
             detail["nvlink_swaps"]["out_of_place_exchanges_per_step"] = n_oop / total_steps
