@@ -569,14 +569,15 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     const int ntb = tb - rb;
     int lay_r[RT_MAX_PASSES][RB_MAX], lay_t[RT_MAX_PASSES][NTB_MAX];
     slot_perms.push_back(take_perms());
-    // Beam search over pass sequences (QSV_REGS_BEAM, default 4 from 26 qubits up, where a pass costs more than the search):
+    // Beam search over pass sequences (QSV_REGS_BEAM, default 4 from 28 qubits up, where its 0.5 ms of host time per 200 gates are
+    // small against the passes it saves even when nothing overlaps them):
     // the greedy rule below -- the pass that retires most gates -- is short-sighted; a register pass costs 1 ms and a
     // tensor-core block another 0.85 ms at 30 qubits (tools/sweep_cost_model.py), so the cheapest sequence under that model
     // is searched for among the shortest ones and those one pass longer.
     std::vector<PassPick> planned;
     size_t plan_pos = 0;
     {
-        const int beam = t_beam_override > 0 ? t_beam_override : std::max(1, env_int_regs("QSV_REGS_BEAM", n >= 26 ? 4 : 1));
+        const int beam = t_beam_override > 0 ? t_beam_override : std::max(1, env_int_regs("QSV_REGS_BEAM", n >= 28 ? 4 : 1));
         // cost of a sequence in 1/100 ms at 30 qubits complex128 (tools/sweep_cost_model.py, fitted to 17 measured
         // sweeps / circuits: a pass 0.96 ms, its tensor-core block 0.85 ms, a 4x4 / 2x2 gate on register bits 1.03 / 0.56 ms)
         auto pass_cost = [&](const PassPick &pk) {

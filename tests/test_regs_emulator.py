@@ -123,7 +123,7 @@ def test_feature_switches(emu, env, monkeypatch):
 @pytest.mark.parametrize("beam", [2, 4, 16])
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 def test_pass_sequence_search(emu, beam, dtype, monkeypatch):
-    """csrc/tile_regs.cu: beam search over pass sequences (QSV_REGS_BEAM; the default from 26 qubits up).  The programs it
+    """csrc/tile_regs.cu: beam search over pass sequences (QSV_REGS_BEAM; the default from 28 qubits up).  The programs it
     builds must give the oracle's state, and must not need more passes than the greedy rule does."""
     passes = {}
     for b in (1, beam):
@@ -147,7 +147,7 @@ def test_pass_sequence_search(emu, beam, dtype, monkeypatch):
 @pytest.mark.parametrize("tries", [3, 8])
 def test_multi_start_sweep_packing(emu, tries, monkeypatch):
     """csrc/tile_kernels.cu: plan_sweeps_regs tries several orders of offering the ready gates to first fit and keeps the
-    cheapest plan under the cost model (QSV_REGS_PACK_TRIES; default from 26 qubits up).  Whatever it picks must give the
+    cheapest plan under the cost model (QSV_REGS_PACK_TRIES; default from 28 qubits up).  Whatever it picks must give the
     oracle's state; on a layered ansatz it must not need more sweeps than program order."""
     sweeps = {}
     for t in (1, tries):
