@@ -258,11 +258,71 @@ def transcribed():
     return {"adjoint": jac, "sparse_pauli": sparse, "probs": probs}
 
 
+def closed_forms():
+    """tests/test_expval.py:38-200 and tests/test_var.py:34-130: 3-wire circuits with the closed-form expectation values and
+    variances the reference asserts (evaluated here at the tests' own parameter grids; tolerance = the tests' default
+    atol 1e-8 loosened to 1e-7 for the formulas' rounding)."""
+    theta_s = np.linspace(0.11, 1, 3)
+    phi_s = np.linspace(0.32, 1, 3)
+    varphi_s = np.linspace(0.02, 1, 3)
+    cos, sin, sqrt = math.cos, math.sin, math.sqrt
+    E, V = "tests/test_expval.py", "tests/test_var.py"
+
+    def op(name, wires, *params):
+        return {"name": name, "wires": list(wires), "params": [float(x) for x in params]}
+
+    def named(name, w):
+        return ["Named", name, [w]]
+
+    out = []
+    for th, ph in zip(theta_s, phi_s):
+        rx = [op("RX", [0], th), op("RX", [1], ph), op("CNOT", [0, 1])]
+        ry = [op("RY", [0], th), op("RY", [1], ph), op("CNOT", [0, 1])]
+        out += [
+            {"cite": E + ":47-60", "ops": rx, "obs": named("Identity", 0), "expval": 1.0},
+            {"cite": E + ":47-60", "ops": rx, "obs": named("Identity", 1), "expval": 1.0},
+            {"cite": E + ":62-74", "ops": rx, "obs": named("PauliZ", 0), "expval": cos(th)},
+            {"cite": E + ":62-74", "ops": rx, "obs": named("PauliZ", 1), "expval": cos(th) * cos(ph)},
+            {"cite": E + ":76-88", "ops": ry, "obs": named("PauliX", 0), "expval": sin(th) * sin(ph)},
+            {"cite": E + ":76-88", "ops": ry, "obs": named("PauliX", 1), "expval": sin(ph)},
+            {"cite": E + ":90-102", "ops": rx, "obs": named("PauliY", 0), "expval": 0.0},
+            {"cite": E + ":90-102", "ops": rx, "obs": named("PauliY", 1), "expval": -cos(th) * sin(ph)},
+            {"cite": E + ":104-124", "ops": ry, "obs": named("Hadamard", 0),
+             "expval": (sin(th) * sin(ph) + cos(th)) / sqrt(2)},
+            {"cite": E + ":104-124", "ops": ry, "obs": named("Hadamard", 1),
+             "expval": (cos(th) * cos(ph) + sin(ph)) / sqrt(2)},
+            {"cite": V + ":44-63", "ops": [op("RX", [0], ph), op("RY", [0], th)], "obs": named("PauliZ", 0),
+             "var": 0.25 * (3 - cos(2 * th) - 2 * cos(th) ** 2 * cos(2 * ph))},
+        ]
+    for th, ph, vp in zip(theta_s, phi_s, varphi_s):
+        c3 = [op("RX", [0], th), op("RX", [1], ph), op("RX", [2], vp), op("CNOT", [0, 1]), op("CNOT", [1, 2])]
+        xy = ["TensorProd", [named("PauliX", 0), named("PauliY", 2)]]
+        ziz = ["TensorProd", [named("PauliZ", 0), named("Identity", 1), named("PauliZ", 2)]]
+        zhy = ["TensorProd", [named("PauliZ", 0), named("Hadamard", 1), named("PauliY", 2)]]
+        out += [
+            {"cite": E + ":129-149", "ops": c3, "obs": xy, "expval": sin(th) * sin(ph) * sin(vp)},
+            {"cite": E + ":151-172", "ops": c3, "obs": ziz, "expval": cos(vp) * cos(ph)},
+            {"cite": E + ":174-195", "ops": c3, "obs": zhy,
+             "expval": -(cos(vp) * sin(ph) + sin(vp) * cos(th)) / sqrt(2)},
+            {"cite": V + ":69-96", "ops": c3, "obs": xy,
+             "var": (8 * sin(th) ** 2 * cos(2 * vp) * sin(ph) ** 2 - cos(2 * (th - ph)) - cos(2 * (th + ph))
+                     + 2 * cos(2 * th) + 2 * cos(2 * ph) + 14) / 16},
+            {"cite": V + ":98-125", "ops": c3, "obs": zhy,
+             "var": (3 + cos(2 * ph) * cos(vp) ** 2 - cos(2 * th) * sin(vp) ** 2
+                     - 2 * cos(th) * sin(ph) * sin(2 * vp)) / 4},
+        ]
+    for case in out:
+        case["n"] = 3
+        case["atol"] = 1e-7
+    return {"closed_forms": out}
+
+
 def main():
     kats = {"_about": "generated by tests/golden/make_golden.py from /root/reference; do not edit"}
     kats["gates_py"] = extract_test_apply()
     kats.update(extract_cpp())
     kats.update(transcribed())
+    kats.update(closed_forms())
     with open(OUT, "w") as f:
         json.dump(kats, f, indent=1)
     print("wrote", OUT, {k: (len(v) if isinstance(v, list) else "-") for k, v in kats.items()})

@@ -211,6 +211,26 @@ def test_measurement_golden_vectors(q, kats, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_closed_form_golden_vectors(q, kats, dtype):
+    """tests/test_expval.py:38-200, tests/test_var.py:34-130 of the reference: closed-form expectation values and variances
+    of named and tensor observables (Identity and Hadamard factors included) on 3-wire circuits."""
+    tol = max(1e-6, TOL[np.dtype(dtype)])
+    for case in kats["closed_forms"]:
+        sv = q.StateVector(case["n"], dtype)
+        for op in case["ops"]:
+            sv.apply(op["name"], op["wires"], op["params"])
+        obs = q.Observable.from_tuple(obs_from_json(case["obs"]))
+        e = sv.expval(obs)
+        if "expval" in case:
+            assert abs(e - case["expval"]) < tol * 10, case["cite"]
+        if "var" in case:
+            o_psi = q.StateVector(case["n"], dtype)
+            o_psi.copy_from(sv)
+            o_psi.apply_observable(obs)
+            assert abs(o_psi.inner_product(o_psi).real - e * e - case["var"]) < tol * 20, case["cite"]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [3, 10, 14])
 def test_expvals_vs_oracle(q, n, dtype):
     rng = np.random.default_rng(300 + n)

@@ -189,3 +189,18 @@ def test_sample_definition():
     assert np.all(s[:, 0] == s[:, 2]) and np.all(s[:, 1] == 0)
     assert 400 < s[:, 0].sum() < 600
     assert np.array_equal(s, orc.sample(st, 1000, seed=7))
+
+
+def test_closed_form_expvals_and_variances(kats):
+    """tests/test_expval.py:38-200, tests/test_var.py:34-130: the closed forms the reference asserts for named and tensor
+    observables on 3-wire circuits (48 cases on the tests' own parameter grids)."""
+    assert len(kats["closed_forms"]) == 48
+    for case in kats["closed_forms"]:
+        psi = orc.apply_ops(orc.basis_state(case["n"]), case["ops"])
+        obs = obs_from_json(case["obs"])
+        e = orc.expval_obs(psi, obs)
+        if "expval" in case:
+            _close(e, case["expval"], case)
+        if "var" in case:
+            o_psi = orc.apply_observable(psi.copy(), obs)
+            _close(np.vdot(o_psi, o_psi).real - e ** 2, case["var"], case)
