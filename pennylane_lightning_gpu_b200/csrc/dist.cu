@@ -16,6 +16,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <functional>
 
@@ -527,6 +528,27 @@ void swap_p2p(State &sv, const std::vector<SwapItem> &items, int gphys, int l) {
 }
 
 }  // namespace
+
+
+// ------------------------------------------------------------------------------------------------
+// Hooks for the CPU emulation of the sharded executor (tests/native/regs_emu.cu): the host-side pieces of
+// dist_apply_ops -- lowering on the whole register, the exchange schedule, and the gate a rank actually runs under a
+// qubit map -- so that the code the GPUs execute is what the test replays on host shards.
+// ------------------------------------------------------------------------------------------------
+LoweredGate dist_hook_lower(int n_total, const Op &op) { return lower_op_total(n_total, op, false); }
+
+std::vector<std::array<int, 3>> dist_hook_plan(const std::vector<LoweredGate> &lowered, std::vector<int> &phys_of,
+                                               std::vector<int> &log_of, int n_local) {
+    std::vector<uint64_t> dense(lowered.size(), 0), diag(lowered.size(), 0);
+    for (size_t i = 0; i < lowered.size(); ++i) gate_bit_masks(lowered[i], dense[i], diag[i]);
+    std::vector<std::array<int, 3>> out;
+    for (const DistStep &st : plan_dist_steps(dense, diag, phys_of, log_of, n_local)) out.push_back({st.kind, st.a, st.b});
+    return out;
+}
+
+LoweredGate dist_hook_localized(const LoweredGate &g, const std::vector<int> &phys_of, int n_local, uint64_t index_hi) {
+    return localize_gate(remap_gate(g, phys_of), n_local, index_hi);
+}
 
 // physical swap of global bit gphys (>= n_local) with local bit l, applied to the register and its companions
 void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {

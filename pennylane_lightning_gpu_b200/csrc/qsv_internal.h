@@ -10,6 +10,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/qsv_b200.h"
@@ -245,6 +246,12 @@ void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
 double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>
 void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
                       const std::vector<int64_t> &trainable, bool apply_operations, double *jac);
+
+// hooks for the CPU emulation of the sharded executor (dist.cu; used by tests/native only)
+LoweredGate dist_hook_lower(int n_total, const Op &op);
+std::vector<std::array<int, 3>> dist_hook_plan(const std::vector<LoweredGate> &lowered, std::vector<int> &phys_of,
+                                               std::vector<int> &log_of, int n_local);
+LoweredGate dist_hook_localized(const LoweredGate &g, const std::vector<int> &phys_of, int n_local, uint64_t index_hi);
 
 // Pauli-word views of observables (circuit.cu)
 bool as_pauli_word(const Obs &o, int n, uint64_t &x, uint64_t &z, int &ny);

@@ -258,6 +258,77 @@ extern "C" int regs_emu_fused_exchange(const void *ops_handle, int n_local, int 
     }
 }
 
+// The sharded executor (csrc/dist.cu: dist_apply_ops) replayed on host shards for all 2^(n_total - n_local) ranks: the
+// library's own lowering, exchange schedule (QSV_DIST_DAG) and per-rank gate localisation (controls / diagonal bits on
+// global qubits resolved against the rank's index bits); only the gate arithmetic (plain reference loops) and the exchange
+// (a host permutation between the two shards of a pair) are the emulator's.  state: 2^n_total interleaved (re, im)
+// doubles in the canonical layout, updated in place; map_io: logical -> physical bit, in (nullptr = identity) and out;
+// n_exchanges: exchanges performed.  `reps` applications in a row share the qubit map, as in bench.py.
+extern "C" int dist_emu_apply_ops(const void *ops_handle, int n_total, int n_local, int reps, double *state, int *n_exchanges) {
+    try {
+        const qsv_ops *ops = reinterpret_cast<const qsv_ops *>(ops_handle);
+        const int g = n_total - n_local, world = 1 << g;
+        const uint64_t NL = 1ull << n_local;
+        std::vector<std::vector<double2>> shard(world, std::vector<double2>(NL));
+        for (int r = 0; r < world; ++r)
+            for (uint64_t i = 0; i < NL; ++i) {
+                const uint64_t k = ((uint64_t)r << n_local) | i;
+                shard[r][i] = make_double2(state[2 * k], state[2 * k + 1]);
+            }
+        std::vector<LoweredGate> lowered;
+        for (const auto &op : ops->ops)
+            if (op.name != "Identity") lowered.push_back(dist_hook_lower(n_total, op));
+        std::vector<int> phys_of(n_total), log_of(n_total);
+        for (int b = 0; b < n_total; ++b) phys_of[b] = log_of[b] = b;
+        int exchanges = 0;
+        for (int rep = 0; rep < reps; ++rep) {
+            std::vector<int> plan_phys = phys_of, plan_log = log_of;
+            const auto steps = dist_hook_plan(lowered, plan_phys, plan_log, n_local);
+            for (const auto &st : steps) {
+                if (st[0] == 0) {
+                    // exchange physical global bit st[1] with local bit st[2]: rank r keeps the amplitudes whose local
+                    // bit equals its value a of the global bit, and swaps the others with rank r ^ (1 << gb)
+                    const int gb = st[1] - n_local, l = st[2];
+                    for (int r = 0; r < world; ++r) {
+                        const int peer = r ^ (1 << gb);
+                        if (peer < r) continue;
+                        // r has a = 0: its elements with bit l = 1 <-> peer's (a = 1) elements with bit l = 0
+                        for (uint64_t i = 0; i < NL; ++i)
+                            if (!(i >> l & 1)) std::swap(shard[r][i | (1ull << l)], shard[peer][i]);
+                    }
+                    const int a = log_of[st[1]], b = log_of[st[2]];
+                    log_of[st[1]] = b;
+                    log_of[st[2]] = a;
+                    phys_of[a] = st[2];
+                    phys_of[b] = st[1];
+                    ++exchanges;
+                    continue;
+                }
+                for (int r = 0; r < world; ++r) {
+                    const LoweredGate gl = dist_hook_localized(lowered[st[1]], phys_of, n_local, (uint64_t)r << n_local);
+                    if (gl.kind != LoweredGate::NOP) apply_lowered_host(shard[r], n_local, gl);
+                }
+            }
+            if (phys_of != plan_phys) return 2;
+        }
+        // back to the canonical layout: amplitude with logical index k sits at physical index p(k)
+        const uint64_t N = 1ull << n_total;
+        for (uint64_t k = 0; k < N; ++k) {
+            uint64_t p = 0;
+            for (int b = 0; b < n_total; ++b)
+                if (k >> b & 1) p |= 1ull << phys_of[b];
+            const double2 v = shard[p >> n_local][p & (NL - 1)];
+            state[2 * k] = v.x;
+            state[2 * k + 1] = v.y;
+        }
+        if (n_exchanges) *n_exchanges = exchanges;
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "dist_emu_apply_ops: %s\n", e.what());
+        return 1;
+    }
+}
+
 // Per-sweep structure of the programs the host side builds for a circuit (no state needed): for sweep k,
 // out[8 k ..] = {passes, gates in the program, D2 blocks, D1-type gates, diagonal gates, tensor-core passes, gates folded
 // into pass boundaries, 256 * (distinct dense-target bits of the sweep) + gates of the sweep before normalisation}.  Returns the number of sweeps (lone gates: passes = 0).

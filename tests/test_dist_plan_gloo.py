@@ -314,3 +314,51 @@ def test_reordered_plans_are_legal_for_every_gate_family():
             assert sorted(seen) == list(range(len(ops))) and phys == m_next
             assert np.max(np.abs(got - want)) < 1e-12, (trial, n_total, n_local)
             m = m_next
+
+
+@pytest.mark.parametrize("n_total,n_local", [(8, 7), (9, 7), (10, 7), (9, 4), (7, 2)])
+@pytest.mark.parametrize("dag", ["1", "0"])
+def test_sharded_executor_emulated_on_host_shards(n_total, n_local, dag, monkeypatch):
+    """csrc/dist.cu: dist_apply_ops replayed on host shards for all ranks (tests/native/regs_emu.cu: dist_emu_apply_ops) with
+    the library's own lowering, exchange schedule and per-rank gate localisation -- controls and diagonal gates on global
+    qubits resolved against the rank's bits, two-level gates, 3- and 4-wire gates -- against the oracle's full state, for one
+    application and for three in a row over the persisting qubit map."""
+    import ctypes as C
+    import importlib.util
+
+    from oracle import np_oracle as orc
+    from pennylane_lightning_gpu_b200 import Ops, workloads
+
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    emu = C.CDLL(mod.build())
+    emu.dist_emu_apply_ops.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    monkeypatch.setenv("QSV_DIST_DAG", dag)
+    rng = np.random.default_rng(5 + n_total)
+    ops = workloads.random_gate_circuit(n_total, 50, 40 + n_total)
+    extra = [{"name": "CZ", "wires": [0, n_total - 1], "params": []}, {"name": "RZ", "wires": [0], "params": [0.3]},
+             {"name": "CNOT", "wires": [0, 3], "params": []}, {"name": "CRY", "wires": [4, 0], "params": [1.1]},
+             {"name": "IsingXX", "wires": [0, 1], "params": [0.7]}, {"name": "SWAP", "wires": [0, n_total - 2], "params": []},
+             {"name": "ControlledPhaseShift", "wires": [0, 1], "params": [0.2]}, {"name": "PhaseShift", "wires": [1], "params": [0.4]},
+             {"name": "SingleExcitation", "wires": [1, 5], "params": [0.6]}, {"name": "Hadamard", "wires": [0], "params": []}]
+    if n_local >= 3:
+        extra += [{"name": "Toffoli", "wires": [1, 0, 2], "params": []}, {"name": "MultiRZ", "wires": [0, 2, 5], "params": [0.9]}]
+    if n_local >= 4:
+        extra += [{"name": "DoubleExcitation", "wires": [0, 1, 2, 3], "params": [0.5]}]
+    for i, e in enumerate(extra):
+        ops.insert(3 + 3 * i, e)
+    rec = Ops(ops)
+    psi = rng.normal(size=1 << n_total) + 1j * rng.normal(size=1 << n_total)
+    psi /= np.linalg.norm(psi)
+    want = psi.copy()
+    for reps in (1, 3):
+        buf = np.ascontiguousarray(psi).view(np.float64).copy()
+        n_x = C.c_int(-1)
+        rc = emu.dist_emu_apply_ops(rec._h, n_total, n_local, reps, buf.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n_x))
+        assert rc == 0
+        want = psi.copy()
+        for _ in range(reps):
+            want = orc.apply_ops(want, ops)
+        assert np.max(np.abs(buf.view(np.complex128) - want)) < 1e-12, (reps, n_x.value)
+        assert n_x.value >= 1
