@@ -359,7 +359,8 @@ std::vector<DistStep> plan_dist_steps(const std::vector<uint64_t> &dense, const 
             }
             return best;
         };
-    const int depth = n <= 4096 ? 2 : 1;
+    const char *depth_env = std::getenv("QSV_DIST_PLAN_DEPTH");
+    const int depth = depth_env ? std::max(1, std::min(3, std::atoi(depth_env))) : (n <= 4096 ? 2 : 1);
     while (true) {
         uint64_t gmask = 0;
         for (int q = 0; q < n_total; ++q)
