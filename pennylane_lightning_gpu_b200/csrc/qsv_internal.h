@@ -235,7 +235,8 @@ std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<Lowered
 void regs_sweep_work(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, double *fma_per_amp,
                      int *passes);
 // price of one fused sweep under the cost model of tools/sweep_cost_model.py (ms at 30 qubits complex128; only ratios matter)
-double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L);
+double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,
+                             bool greedy_scheduler);
 bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);
 bool regs_fusable(const LoweredGate &g, int n_local);
 uint64_t regs_need_bits(const LoweredGate &g);

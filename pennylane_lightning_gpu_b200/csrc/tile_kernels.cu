@@ -712,11 +712,22 @@ static std::vector<SweepPlan> plan_sweeps_once(int n_local, const std::vector<Lo
                 }
             } else {
                 // first fit over the ready gates of a look-ahead window, repeated until nothing more fits
-                // order_seed 0: program order; > 0: a fixed pseudo-random order of the window (multi-start, see below)
+                // order_seed 0: program order; 1 / 2: by lowest / highest index bit; > 2: a fixed pseudo-random order of the
+                // window (multi-start, see below)
                 const int stop = std::min(m, first + window);
                 std::vector<int> order;
                 for (int j = first; j < stop; ++j) order.push_back(j);
-                if (order_seed > 0) {
+                if (order_seed == 1 || order_seed == 2) {
+                    // by index bit instead of program order: a layered circuit is then packed along its wires (all layers
+                    // of a group of neighbouring qubits in one sweep, as far as the entangling gates allow)
+                    auto key = [&](int j) {
+                        const LoweredGate &g = gates[seg[j]];
+                        const uint64_t bits = all_bits(g) | regs_need_bits(g);
+                        const int b = bits ? (order_seed == 1 ? __builtin_ctzll(bits) : 63 - __builtin_clzll(bits)) : 0;
+                        return order_seed == 1 ? b : -b;
+                    };
+                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+                } else if (order_seed > 2) {
                     uint32_t r = 2654435761u * (uint32_t)(order_seed + 17 * (int)plan.size());
                     for (int k = (int)order.size() - 1; k > 0; --k) {
                         r = r * 1664525u + 1013904223u;
@@ -752,20 +763,20 @@ static std::vector<SweepPlan> plan_sweeps_once(int n_local, const std::vector<Lo
     return plan;
 }
 
-// Multi-start packing (QSV_REGS_PACK_TRIES; default 4 from 28 qubits up -- where its 2 ms of host time are under a tenth
-// of the circuit's GPU time even when nothing overlaps them -- else 1): first fit depends on the
-// order in which the ready gates are offered.  Program order is close to the best found for random circuits, but on layered
-// circuits (rotations on every wire + an entangling ladder) other orders need fewer sweeps and passes -- the 30-qubit
-// hardware-efficient ansatz: 9 sweeps / 25 passes instead of 11 / 30.  Every candidate is priced with the cost model of
-// tools/sweep_cost_model.py on the programs the pass scheduler builds for it (greedy scheduler, ~0.5 ms of host time per
-// candidate and 200 gates).
+// Multi-start packing (QSV_REGS_PACK_TRIES; default 3 from 28 qubits up -- where its ~3 ms of host time, paid once per
+// gate-list structure thanks to the plan cache, are small against the circuit's GPU time -- else 1): first fit depends on
+// the order in which the ready gates are offered.  Besides program order the gates are offered by lowest and by highest
+// index bit (try 1 and 2; further tries use fixed pseudo-random orders).  Program order is close to the best found for
+// random circuits, but layered circuits (rotations on every wire + an entangling ladder) pack much better along their wires
+// -- the 30-qubit hardware-efficient ansatz: 9 sweeps / 26 passes instead of 11 / 30.  Candidates are priced with the cost
+// model of tools/sweep_cost_model.py on the programs the pass scheduler builds for them.
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag, int max_gates,
                                         int window, int dtype) {
     std::vector<SweepPlan> best = plan_sweeps_once(n_local, gates, L, dag, max_gates, window, 0);
-    const int tries = dag && n_local >= 12 ? std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 28 ? 4 : 1)) : 1;
+    const int tries = dag && n_local >= 12 ? std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 28 ? 3 : 1)) : 1;
     if (tries <= 1) return best;
     std::vector<const LoweredGate *> cur;
-    auto price = [&](const std::vector<SweepPlan> &plan) {
+    auto price = [&](const std::vector<SweepPlan> &plan, bool greedy) {
         double c = 0.0;
         for (const SweepPlan &sw : plan) {
             if (!sw.fused) {
@@ -774,19 +785,25 @@ std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGa
             }
             cur.clear();
             for (int i : sw.gates) cur.push_back(&gates[i]);
-            c += regs_sweep_model_cost(n_local, dtype, cur, sw.need, L);
+            c += regs_sweep_model_cost(n_local, dtype, cur, sw.need, L, greedy);
         }
         return c;
     };
-    double best_cost = price(best);
+    // candidates are priced with the greedy pass scheduler (cheap); the winner then has to beat program order under the
+    // scheduler that will really build the programs (the pass-sequence search), so the result is never worse than it
+    std::vector<SweepPlan> winner;
+    double winner_cost = price(best, true);
+    bool have_winner = false;
     for (int t = 1; t < tries; ++t) {
         std::vector<SweepPlan> cand = plan_sweeps_once(n_local, gates, L, dag, max_gates, window, t);
-        const double c = price(cand);
-        if (c < best_cost - 1e-9) {
-            best_cost = c;
-            best = std::move(cand);
+        const double c = price(cand, true);
+        if (c < winner_cost - 1e-9) {
+            winner_cost = c;
+            winner = std::move(cand);
+            have_winner = true;
         }
     }
+    if (have_winner && price(winner, false) < price(best, false) - 1e-9) best = std::move(winner);
     return best;
 }
 

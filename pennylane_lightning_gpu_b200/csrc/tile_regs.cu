@@ -999,9 +999,10 @@ void build_reg_program(int n, int dtype, uint64_t index_hi, const std::vector<co
     P.prefetch = std::max(0, env_int_regs("QSV_REGS_PREFETCH", 0));
 }
 
-double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L) {
+double regs_sweep_model_cost(int n, int dtype, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,
+                             bool greedy_scheduler) {
     static thread_local RegProgram P;
-    t_beam_override = 1;
+    t_beam_override = greedy_scheduler ? 1 : 0;
     struct Reset {
         ~Reset() { t_beam_override = 0; }
     } reset;
