@@ -227,7 +227,7 @@ struct SweepPlan {
 };
 std::vector<LoweredGate> prepare_gates_regs(const std::vector<LoweredGate> &gates_in);
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag,
-                                        int max_gates, int window, int dtype = QSV_C128);
+                                        int max_gates, int window, int dtype = QSV_C128, int tries = 0);
 // the same through a small cache keyed by the structure of the gate list (kinds and index bits, not matrix entries)
 std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<LoweredGate> &merged, int L, bool dag, int max_gates,
                                           int window, int dtype);

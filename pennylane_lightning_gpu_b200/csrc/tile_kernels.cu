@@ -770,10 +770,17 @@ static std::vector<SweepPlan> plan_sweeps_once(int n_local, const std::vector<Lo
 // random circuits, but layered circuits (rotations on every wire + an entangling ladder) pack much better along their wires
 // -- the 30-qubit hardware-efficient ansatz: 9 sweeps / 26 passes instead of 11 / 30.  Candidates are priced with the cost
 // model of tools/sweep_cost_model.py on the programs the pass scheduler builds for them.
+int regs_pack_tries(int n_local, bool seen_before) {
+    // from 28 qubits up the search pays even for a circuit that is applied once; from 20 qubits up it is run when a gate-list
+    // structure comes back (plan cache), i.e. for the loops -- variational iterations, adjoint sweeps layer by layer,
+    // benchmarks -- that apply one structure many times
+    return std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 28 || (seen_before && n_local >= 20) ? 3 : 1));
+}
+
 std::vector<SweepPlan> plan_sweeps_regs(int n_local, const std::vector<LoweredGate> &gates, int L, bool dag, int max_gates,
-                                        int window, int dtype) {
+                                        int window, int dtype, int tries_in) {
     std::vector<SweepPlan> best = plan_sweeps_once(n_local, gates, L, dag, max_gates, window, 0);
-    const int tries = dag && n_local >= 12 ? std::max(1, env_int("QSV_REGS_PACK_TRIES", n_local >= 28 ? 3 : 1)) : 1;
+    const int tries = dag && n_local >= 12 ? (tries_in > 0 ? tries_in : regs_pack_tries(n_local, false)) : 1;
     if (tries <= 1) return best;
     std::vector<const LoweredGate *> cur;
     auto price = [&](const std::vector<SweepPlan> &plan, bool greedy) {
@@ -824,6 +831,7 @@ bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b) {
 namespace {
 struct PlanCacheEntry {
     uint64_t h1 = 0, h2 = 0;
+    int tries = 1;  // how hard the packing was searched for this plan
     std::vector<SweepPlan> plan;
 };
 std::mutex g_plan_cache_mu;
@@ -860,19 +868,29 @@ std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<Lowered
                        env_int("QSV_REGS_MMA", 2), env_int("QSV_REGS_FOLD", 1), env_int("QSV_REGS_UDIAG", 1),
                        env_int("QSV_REGS_DIAG1", 1)};
     structure_hash(merged, key, (int)(sizeof(key) / sizeof(key[0])), h1, h2);
+    bool seen_before = false;
     {
         std::lock_guard<std::mutex> lock(g_plan_cache_mu);
         for (size_t i = 0; i < g_plan_cache.size(); ++i)
             if (g_plan_cache[i].h1 == h1 && g_plan_cache[i].h2 == h2) {
                 if (i != 0) std::rotate(g_plan_cache.begin(), g_plan_cache.begin() + i, g_plan_cache.begin() + i + 1);
-                return g_plan_cache[0].plan;
+                if (g_plan_cache[0].tries >= regs_pack_tries(n_local, true)) return g_plan_cache[0].plan;
+                seen_before = true;  // a structure that comes back is worth the search it was spared the first time
+                break;
             }
     }
-    std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, dag, max_gates, window, dtype);
+    const int tries = regs_pack_tries(n_local, seen_before);
+    std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, dag, max_gates, window, dtype, tries);
     std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+    for (size_t i = 0; i < g_plan_cache.size(); ++i)
+        if (g_plan_cache[i].h1 == h1 && g_plan_cache[i].h2 == h2) {
+            g_plan_cache.erase(g_plan_cache.begin() + i);
+            break;
+        }
     PlanCacheEntry e;
     e.h1 = h1;
     e.h2 = h2;
+    e.tries = tries;
     e.plan = plan;
     g_plan_cache.insert(g_plan_cache.begin(), std::move(e));
     if (g_plan_cache.size() > 32) g_plan_cache.pop_back();
