@@ -117,6 +117,27 @@ class LightningGPU(_Base):
         self._state_host = None
         self._samples = None
 
+    @classmethod
+    def capabilities(cls):
+        """lightning_gpu.py:485-497."""
+        base = getattr(super(), "capabilities", None)
+        caps = dict(base()) if callable(base) else {}
+        caps.update(model="qubit", supports_inverse_operations=True, supports_analytic_computation=True,
+                    supports_finite_shots=True, returns_state=True)
+        caps.pop("passthru_devices", None)
+        return caps
+
+    @staticmethod
+    def _adjoint_jacobian_processing(jac):
+        """Post-processing of the Jacobian for the new return type system (lightning_gpu.py:754-769): a scalar for one
+        observable and one parameter, a tuple of arrays for one of the two, a tuple of tuples otherwise."""
+        jac = np.squeeze(jac)
+        if jac.ndim == 0:
+            return np.array(jac)
+        if jac.ndim == 1:
+            return tuple(np.array(j) for j in jac)
+        return tuple(tuple(np.array(j_) for j_ in j) for j in jac)
+
     # ---- state ------------------------------------------------------------------------------------
     def reset(self):
         if _Base is not object:
@@ -338,6 +359,17 @@ class LightningGPU(_Base):
         if self._seed is None:
             return self._gpu_state.GenerateSamples(self.num_wires, int(self.shots)).astype(int)
         return self._gpu_state.GenerateSamples(self.num_wires, int(self.shots), int(self._seed)).astype(int)
+
+    def sample(self, observable: Obs, shot_range=None, bin_size=None, counts: bool = False):
+        """Eigenvalue samples of an observable (lightning_gpu.py:812-818): the state is rotated into the observable's
+        eigenbasis, sampled in the computational basis and restored; counts=True returns {eigenvalue: occurrences}."""
+        s = self._sample_observable(observable)
+        if shot_range is not None:
+            s = s[slice(*shot_range)]
+        if counts:
+            vals, n = np.unique(s, return_counts=True)
+            return {float(v): int(c) for v, c in zip(vals, n)}
+        return s if bin_size is None else s.reshape(-1, bin_size)
 
     def _sample_observable(self, observable: Obs) -> np.ndarray:
         """Eigenvalue samples of a Pauli-word observable measured in the computational basis after the

@@ -76,3 +76,15 @@ def test_dense_matrix_of_composite_observables(lg):
         lg.LightningGPU._matrix_of(lg.Obs("Tensor", terms=[lg.Obs("PauliX", [0]), lg.Obs("Hadamard", [0])]))
     with pytest.raises(NotImplementedError):
         lg.LightningGPU._matrix_of(lg.Obs("Tensor", terms=[lg.Obs("Hadamard", [w]) for w in range(11)]))
+
+
+def test_capabilities_and_jacobian_processing(lg):
+    caps = lg.LightningGPU.capabilities()
+    assert caps["model"] == "qubit" and caps["returns_state"] and caps["supports_finite_shots"]
+    assert caps["supports_inverse_operations"] and caps["supports_analytic_computation"] and "passthru_devices" not in caps
+    proc = lg.LightningGPU._adjoint_jacobian_processing
+    assert proc(np.array([[0.5]])).shape == ()                      # one observable, one parameter
+    one_obs = proc(np.array([[0.1, 0.2, 0.3]]))
+    assert isinstance(one_obs, tuple) and len(one_obs) == 3 and float(one_obs[1]) == 0.2
+    many = proc(np.arange(6.0).reshape(2, 3))
+    assert isinstance(many, tuple) and isinstance(many[0], tuple) and float(many[1][2]) == 5.0
