@@ -101,6 +101,10 @@ def test_samples_and_shot_statistics(dev_mod):
     assert abs(dev.expval(lg.Obs("PauliX", [1])) - 1.0) < 1e-12  # |+> on wire 1
     assert abs(dev.var(lg.Obs("PauliZ", [0])) - (1 - orc.expval_named(psi, "PauliZ", [0]) ** 2)) < 0.03
     assert np.max(np.abs(dev.probability([0, 1]) - orc.probs(psi, [0, 1]))) < 0.02
+    ev = dev.sample(lg.Obs("PauliZ", [0]))
+    assert ev.shape == (20000,) and set(np.unique(ev)) <= {-1.0, 1.0}
+    counts = dev.sample(lg.Obs("PauliX", [1]), counts=True)
+    assert counts == {1.0: 20000}  # |+> on wire 1: every shot gives +1
 
 
 @pytest.mark.parametrize("c_dtype,tol", [(np.complex128, 1e-10), (np.complex64, 3e-4)])
