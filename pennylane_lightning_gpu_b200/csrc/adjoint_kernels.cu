@@ -18,171 +18,228 @@ namespace qsv {
 
 namespace {
 
-constexpr int GT_TB = 11;        // tile bits: 2^11 amplitudes of ket in shared memory (32 KiB complex128)
-constexpr int GT_NT = 256;
-constexpr int GT_EPT = (1 << GT_TB) / GT_NT;  // 8 amplitudes per thread
-static_assert(GT_EPT == 8 && GT_NT == 256, "the kernel's index split assumes e = tid + 256 * j with j < 8");
-constexpr int GT_MAX = 32;       // generators per launch
+constexpr int GT_JB = 4;                 // the top GT_JB tile bits distinguish the amplitudes of one thread
+constexpr int GT_EPT = 1 << GT_JB;       // 16 amplitudes per thread
+constexpr int GT_MAX = 48;               // generators per launch
+constexpr int GT_TB_MAX = 13;            // tile bits: 2^12 (256 threads) or 2^13 (512 threads) amplitudes of ket in shared memory
 
 struct GenDesc {
     int kind;            // 0: diagonal table (<= 1 table bit: parity of index & zmask), 1: 2x2 block on one tile bit,
                          // 2: Pauli word (X/Y letters on tile bits, Z letters anywhere)
     int slot;            // complex output slot
     unsigned tbit;       // kind 1: tile-local position of the target bit; kind 2: tile-local flip mask
-    unsigned pad0;       // kind 0: bits 0-2 = parity mask on the thread's three amplitude-index bits (tile bits 8..10), bit 8 =
-                         // a control sits on one of them (generic per-amplitude path)
-    uint64_t ctrl;       // global bits that must be 1
-    uint64_t zmask;      // kind 0 / 2: global bits whose parity selects the phase / the sign
+    unsigned jinfo;      // what the generator sees of the thread's GT_JB amplitude bits j (CTA-uniform, so the per-amplitude
+                         // work is branch-free): bits 0-3 parity mask over j, bits 4-7 control mask over j, bit 8 constant
+                         // parity flip (kind 2: the flipped j bits under the parity mask)
+    uint64_t ctrl;       // global bits that must be 1          } outside the j columns: thread-constant
+    uint64_t zmask;      // kind 0 / 2: global parity-mask bits }
     uint64_t xg;         // kind 2: flip mask on global bits
     double m[8];         // kind 1: row-major complex 2x2; kind 0: phases for even / odd parity; kind 2: i^ny
 };
 
 struct GenProgram {
     int n_gens;
+    int n_first;                // generators [0, n_first) are of kind 1 / 2 (they need bra), the rest are diagonal
     int L;
-    unsigned char hi_bits[16];  // global positions of tile bits L..GT_TB-1
+    int pad;
+    unsigned char hi_bits[16];  // global positions of tile bits L..TB-1
     Holes tile_holes;
     GenDesc g[GT_MAX];
 };
 
-template <typename T>
-__global__ void __launch_bounds__(GT_NT)
+__device__ __forceinline__ void pick_w(const double (&Wr)[GT_EPT], const double (&Wi)[GT_EPT], unsigned idx, double &wr, double &wi) {
+    switch (idx & 15u) {  // CTA-uniform
+    case 0: wr = Wr[0]; wi = Wi[0]; break;
+    case 1: wr = Wr[1]; wi = Wi[1]; break;
+    case 2: wr = Wr[2]; wi = Wi[2]; break;
+    case 3: wr = Wr[3]; wi = Wi[3]; break;
+    case 4: wr = Wr[4]; wi = Wi[4]; break;
+    case 5: wr = Wr[5]; wi = Wi[5]; break;
+    case 6: wr = Wr[6]; wi = Wi[6]; break;
+    case 7: wr = Wr[7]; wi = Wi[7]; break;
+    case 8: wr = Wr[8]; wi = Wi[8]; break;
+    case 9: wr = Wr[9]; wi = Wi[9]; break;
+    case 10: wr = Wr[10]; wi = Wi[10]; break;
+    case 11: wr = Wr[11]; wi = Wi[11]; break;
+    case 12: wr = Wr[12]; wi = Wi[12]; break;
+    case 13: wr = Wr[13]; wi = Wi[13]; break;
+    case 14: wr = Wr[14]; wi = Wi[14]; break;
+    default: wr = Wr[15]; wi = Wi[15]; break;
+    }
+}
+
+// One CTA = one tile of 2^TB amplitudes: ket in shared memory, the matching bra amplitudes in registers (16 per thread:
+// element e = tid + NT * j, j = the top four tile bits).  Everything a generator needs to know about an amplitude splits
+// into a thread-constant part (computed once per generator and thread) and a part that depends on j only, which is
+// CTA-uniform and unrolled -- so the inner loops are one shared-memory read and four FP64 multiply-adds per amplitude.
+template <typename T, int TB>
+__global__ void __launch_bounds__(1 << (TB - GT_JB))
     k_bra_gens_ket(const void *__restrict__ bra, const void *__restrict__ ket, double *out,
                    const __grid_constant__ GenProgram P) {
     using A = typename VecOf<T, 1>::type;
+    constexpr int NT = 1 << (TB - GT_JB), NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     A *s = reinterpret_cast<A *>(smem_raw);
-    __shared__ double s_acc[GT_MAX][2];
+    double(*s_acc)[NW][2] = reinterpret_cast<double(*)[NW][2]>(smem_raw + (sizeof(A) << TB));
     const uint64_t base = expand_index((uint64_t)blockIdx.x, P.tile_holes);
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < 2 * GT_MAX; i += GT_NT) (&s_acc[0][0])[i] = 0.0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    // element e of the tile (local index) lives at global index base | deposit(e)
-    // (e = tid + 256 * j: the thread part of the deposit is computed once, the three j bits are CTA-uniform columns)
+    // element e of the tile (local index) lives at global index base | deposit(e); g0 = the thread part (j bits clear)
+    uint64_t g0 = tid & ((1u << P.L) - 1u);
+    for (int q = P.L; q < TB - GT_JB; ++q) g0 |= (uint64_t)((tid >> q) & 1u) << P.hi_bits[q - P.L];
+    g0 |= base;
+    uint64_t col[GT_JB];
+#pragma unroll
+    for (int q = 0; q < GT_JB; ++q) col[q] = 1ull << P.hi_bits[TB - GT_JB + q - P.L];
+    const bool same = bra == ket;  // expectation values: one read of the vector serves both sides
     A b[GT_EPT];
-    uint64_t gidx[GT_EPT];
-    uint64_t dep_tid = (uint32_t)tid & ((1u << P.L) - 1u);
-    for (int q = P.L; q < GT_TB - 3; ++q) dep_tid |= (uint64_t)(((uint32_t)tid >> q) & 1u) << P.hi_bits[q - P.L];
-    dep_tid |= base;
-    const uint64_t cj0 = 1ull << P.hi_bits[GT_TB - 3 - P.L], cj1 = 1ull << P.hi_bits[GT_TB - 2 - P.L],
-                   cj2 = 1ull << P.hi_bits[GT_TB - 1 - P.L];
 #pragma unroll
     for (int j = 0; j < GT_EPT; ++j) {
-        const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
-        gidx[j] = dep_tid | ((j & 1) ? cj0 : 0ull) | ((j & 2) ? cj1 : 0ull) | ((j & 4) ? cj2 : 0ull);
-        s[e] = reinterpret_cast<const A *>(ket)[gidx[j]];
-        b[j] = reinterpret_cast<const A *>(bra)[gidx[j]];
+        uint64_t gi = g0;
+#pragma unroll
+        for (int q = 0; q < GT_JB; ++q)
+            if ((j >> q) & 1) gi |= col[q];
+        s[tid + (uint32_t)j * NT] = reinterpret_cast<const A *>(ket)[gi];
+        if (!same) b[j] = reinterpret_cast<const A *>(bra)[gi];
     }
     __syncthreads();
-
-    // Diagonal / parity generators: conj(b_i) * p(i) * k_i with t0_i = conj(b_i) * k_i shared by all of them.  The thread's
-    // 8 amplitudes differ in tile bits 8..10 (j = 0..7), everything else of the index is thread-constant, so
-    //   sum_j p(parity_j) t0_j = e_a * (W[0] + W[m]) / 2 + e_b * (W[0] - W[m]) / 2,   W[m] = sum_j (-1)^{popc(j & m)} t0_j
-    // with m = the generator's parity mask restricted to the three j bits and (e_a, e_b) = the two phases ordered by the
-    // thread-constant part of the parity: one Walsh-Hadamard transform per thread, then ~12 FP64 operations per generator
-    // instead of ~8 per generator AND amplitude.
-    double Wr[GT_EPT], Wi[GT_EPT];
+    if (same) {
 #pragma unroll
-    for (int j = 0; j < GT_EPT; ++j) {
-        const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
-        Wr[j] = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
-        Wi[j] = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
+        for (int j = 0; j < GT_EPT; ++j) b[j] = s[tid + (uint32_t)j * NT];
     }
-#pragma unroll
-    for (int h = 1; h < GT_EPT; h <<= 1)
-#pragma unroll
-        for (int j = 0; j < GT_EPT; ++j)
-            if (!(j & h)) {
-                const double ar = Wr[j], ai = Wi[j], br = Wr[j | h], bi = Wi[j | h];
-                Wr[j] = ar + br;
-                Wi[j] = ai + bi;
-                Wr[j | h] = ar - br;
-                Wi[j | h] = ai - bi;
-            }
 
-    for (int k = 0; k < P.n_gens; ++k) {
+    auto reduce_store = [&](int k, double re, double im) {
+        re = warp_sum(re);
+        im = warp_sum(im);
+        if (lane == 0) {
+            s_acc[k][warp][0] = re;
+            s_acc[k][warp][1] = im;
+        }
+    };
+
+    // ---- generators with off-diagonal parts: Pauli words and 2x2 blocks --------------------------------------
+    for (int k = 0; k < P.n_first; ++k) {
         const GenDesc &g = P.g[k];
+        const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
+        const bool t_on = (g0 & g.ctrl) == g.ctrl;
         double re = 0.0, im = 0.0;
-        if (g.kind == 0 && (g.pad0 >> 8) == 0u) {
-            // no control on a j bit: the control test is thread-constant too (gidx[0] has the j bits clear)
-            if ((gidx[0] & g.ctrl) == g.ctrl) {
-                const unsigned m = g.pad0 & 7u;
-                double wr, wi;
-                switch (m) {  // CTA-uniform
-                case 0: wr = Wr[0]; wi = Wi[0]; break;
-                case 1: wr = Wr[1]; wi = Wi[1]; break;
-                case 2: wr = Wr[2]; wi = Wi[2]; break;
-                case 3: wr = Wr[3]; wi = Wi[3]; break;
-                case 4: wr = Wr[4]; wi = Wi[4]; break;
-                case 5: wr = Wr[5]; wi = Wi[5]; break;
-                case 6: wr = Wr[6]; wi = Wi[6]; break;
-                default: wr = Wr[7]; wi = Wi[7]; break;
+        if (g.kind == 2) {
+            // (P ket)_i = i^ny * (-1)^{popc(i' & z)} * ket_i' with i' = i ^ x (only where the control bits are set: generators
+            // |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum
+            const bool t_odd = ((__popcll((g0 ^ g.xg) & g.zmask) ^ (g.jinfo >> 8)) & 1u) != 0u;
+            double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};  // two chains each
+            if (t_on) {
+                if (mj == 0u) {
+#pragma unroll
+                    for (int j = 0; j < GT_EPT; ++j) {
+                        if (((unsigned)j & cjm) != cjm) continue;
+                        const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                        ar[j & 1] += (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
+                        ai[j & 1] += (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < GT_EPT; ++j) {
+                        if (((unsigned)j & cjm) != cjm) continue;
+                        const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                        const double sg = (__popc((unsigned)j & mj) & 1) ? -1.0 : 1.0;  // CTA-uniform
+                        const double bx = sg * (double)b[j].x, by = sg * (double)b[j].y;
+                        ar[j & 1] += bx * (double)x.x + by * (double)x.y;
+                        ai[j & 1] += bx * (double)x.y - by * (double)x.x;
+                    }
                 }
-                const bool odd = __popcll(gidx[0] & g.zmask) & 1;
-                const double ear = odd ? g.m[2] : g.m[0], eai = odd ? g.m[3] : g.m[1];
-                const double ebr = odd ? g.m[0] : g.m[2], ebi = odd ? g.m[1] : g.m[3];
-                const double Ar = 0.5 * (Wr[0] + wr), Ai = 0.5 * (Wi[0] + wi);
-                const double Br = 0.5 * (Wr[0] - wr), Bi = 0.5 * (Wi[0] - wi);
-                re = ear * Ar - eai * Ai + ebr * Br - ebi * Bi;
-                im = ear * Ai + eai * Ar + ebr * Bi + ebi * Br;
             }
-        } else if (g.kind == 0) {
-            const double e0r = g.m[0], e0i = g.m[1], e1r = g.m[2], e1i = g.m[3];
-#pragma unroll
-            for (int j = 0; j < GT_EPT; ++j) {
-                if ((gidx[j] & g.ctrl) != g.ctrl) continue;
-                const bool odd = __popcll(gidx[j] & g.zmask) & 1;
-                const double pr = odd ? e1r : e0r, pi = odd ? e1i : e0i;
-                const A x = s[(uint32_t)tid + (uint32_t)j * GT_NT];
-                const double yr = pr * (double)x.x - pi * (double)x.y, yi = pr * (double)x.y + pi * (double)x.x;
-                re += (double)b[j].x * yr + (double)b[j].y * yi;
-                im += (double)b[j].x * yi - (double)b[j].y * yr;
-            }
-        } else if (g.kind == 2) {
-            // (P ket)_i = i^ny * (-1)^{popc(j & z)} * ket_j with j = i ^ x (optionally only where the control bits are set:
-            // generators |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum
-#pragma unroll
-            for (int j = 0; j < GT_EPT; ++j) {
-                if ((gidx[j] & g.ctrl) != g.ctrl) continue;
-                const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
-                const A x = s[e ^ g.tbit];
-                const bool odd = __popcll((gidx[j] ^ g.xg) & g.zmask) & 1;
-                const double ur = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
-                const double ui = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
-                re += odd ? -ur : ur;
-                im += odd ? -ui : ui;
-            }
-            const double cr = g.m[0], ci = g.m[1], r0 = re;
-            re = cr * r0 - ci * im;
-            im = cr * im + ci * r0;
+            const double r0 = t_odd ? -(ar[0] + ar[1]) : ar[0] + ar[1], i0 = t_odd ? -(ai[0] + ai[1]) : ai[0] + ai[1];
+            re = g.m[0] * r0 - g.m[1] * i0;
+            im = g.m[0] * i0 + g.m[1] * r0;
         } else {
             const uint32_t bit = 1u << g.tbit;
             const double m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
             const double m4 = g.m[4], m5 = g.m[5], m6 = g.m[6], m7 = g.m[7];
+            if (t_on) {
 #pragma unroll
-            for (int j = 0; j < GT_EPT; ++j) {
-                if ((gidx[j] & g.ctrl) != g.ctrl) continue;
-                const uint32_t e = (uint32_t)tid + (uint32_t)j * GT_NT;
-                const A x0 = s[e & ~bit], x1 = s[e | bit];
-                const bool hi = (e & bit) != 0;
-                const double ar = hi ? m4 : m0, ai = hi ? m5 : m1, br = hi ? m6 : m2, bi = hi ? m7 : m3;
-                const double yr = ar * (double)x0.x - ai * (double)x0.y + br * (double)x1.x - bi * (double)x1.y;
-                const double yi = ar * (double)x0.y + ai * (double)x0.x + br * (double)x1.y + bi * (double)x1.x;
-                re += (double)b[j].x * yr + (double)b[j].y * yi;
-                im += (double)b[j].x * yi - (double)b[j].y * yr;
+                for (int j = 0; j < GT_EPT; ++j) {
+                    if (((unsigned)j & cjm) != cjm) continue;
+                    const uint32_t e = tid + (uint32_t)j * NT;
+                    const A x0 = s[e & ~bit], x1 = s[e | bit];
+                    const bool hi = (e & bit) != 0;
+                    const double ar = hi ? m4 : m0, ai = hi ? m5 : m1, br = hi ? m6 : m2, bi = hi ? m7 : m3;
+                    const double yr = ar * (double)x0.x - ai * (double)x0.y + br * (double)x1.x - bi * (double)x1.y;
+                    const double yi = ar * (double)x0.y + ai * (double)x0.x + br * (double)x1.y + bi * (double)x1.x;
+                    re += (double)b[j].x * yr + (double)b[j].y * yi;
+                    im += (double)b[j].x * yi - (double)b[j].y * yr;
+                }
             }
         }
-        re = warp_sum(re);
-        im = warp_sum(im);
-        if (lane == 0) {
-            atomicAdd(&s_acc[k][0], re);
-            atomicAdd(&s_acc[k][1], im);
+        reduce_store(k, re, im);
+    }
+
+    // ---- diagonal / parity generators -------------------------------------------------------------------------
+    // conj(b_i) * p(i) * k_i with t0_i = conj(b_i) * k_i shared by all of them.  The thread's 16 amplitudes differ in the j
+    // bits only, so with W[m] = sum_j (-1)^{popc(j & m)} t0_j (one Walsh-Hadamard transform per thread)
+    //   sum over the j that have the control bits c set of (-1)^{popc(j & m)} t0_j = 2^-|c| sum_{s subset of c} (-1)^|s| W[m ^ s]
+    // and a generator costs a handful of FP64 operations per THREAD instead of ~8 per amplitude.
+    if (P.n_first < P.n_gens) {
+        double Wr[GT_EPT], Wi[GT_EPT];
+#pragma unroll
+        for (int j = 0; j < GT_EPT; ++j) {
+            const A x = s[tid + (uint32_t)j * NT];
+            Wr[j] = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
+            Wi[j] = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
+        }
+#pragma unroll
+        for (int h = 1; h < GT_EPT; h <<= 1)
+#pragma unroll
+            for (int j = 0; j < GT_EPT; ++j)
+                if (!(j & h)) {
+                    const double ar = Wr[j], ai = Wi[j], br = Wr[j | h], bi = Wi[j | h];
+                    Wr[j] = ar + br;
+                    Wi[j] = ai + bi;
+                    Wr[j | h] = ar - br;
+                    Wi[j | h] = ai - bi;
+                }
+        for (int k = P.n_first; k < P.n_gens; ++k) {
+            const GenDesc &g = P.g[k];
+            const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
+            double re = 0.0, im = 0.0;
+            if ((g0 & g.ctrl) == g.ctrl) {
+                // S0 = sum over the controlled j of t0_j, Sm = the same with the parity sign
+                double s0r = 0.0, s0i = 0.0, smr = 0.0, smi = 0.0;
+                unsigned sub = cjm;
+                for (;;) {  // CTA-uniform loop over the subsets of the control mask (one iteration without controls on j bits)
+                    const double sg = (__popc(sub) & 1) ? -1.0 : 1.0;
+                    double wr, wi;
+                    pick_w(Wr, Wi, sub, wr, wi);
+                    s0r += sg * wr;
+                    s0i += sg * wi;
+                    pick_w(Wr, Wi, mj ^ sub, wr, wi);
+                    smr += sg * wr;
+                    smi += sg * wi;
+                    if (sub == 0u) break;
+                    sub = (sub - 1u) & cjm;
+                }
+                const double sc = 0.5 / (double)(1u << __popc(cjm));
+                const double Er = sc * (s0r + smr), Ei = sc * (s0i + smi);  // even parity among the j bits
+                const double Or = sc * (s0r - smr), Oi = sc * (s0i - smi);  // odd
+                const bool odd = __popcll(g0 & g.zmask) & 1;
+                const double ear = odd ? g.m[2] : g.m[0], eai = odd ? g.m[3] : g.m[1];
+                const double ebr = odd ? g.m[0] : g.m[2], ebi = odd ? g.m[1] : g.m[3];
+                re = ear * Er - eai * Ei + ebr * Or - ebi * Oi;
+                im = ear * Ei + eai * Er + ebr * Oi + ebi * Or;
+            }
+            reduce_store(k, re, im);
         }
     }
     __syncthreads();
-    if (tid < P.n_gens) {
-        atomicAdd(out + 2 * (size_t)P.g[tid].slot, s_acc[tid][0]);
-        atomicAdd(out + 2 * (size_t)P.g[tid].slot + 1, s_acc[tid][1]);
+    if ((int)tid < P.n_gens) {
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            re += s_acc[tid][w][0];
+            im += s_acc[tid][w][1];
+        }
+        atomicAdd(out + 2 * (size_t)P.g[tid].slot, re);
+        atomicAdd(out + 2 * (size_t)P.g[tid].slot + 1, im);
     }
 }
 
@@ -203,14 +260,40 @@ bool tile_gen_kind(const LoweredGate &g, int n, int &kind) {
     return false;
 }
 
-template <typename T> void launch_gens_t(State &sv, const void *bra, const void *ket, double *out, const GenProgram &P) {
-    const size_t smem = ((size_t)1 << GT_TB) * sizeof(typename VecOf<T, 1>::type);
-    const unsigned grid = (unsigned)(1ull << (sv.n - GT_TB));
-    k_bra_gens_ket<T><<<grid, GT_NT, smem, sv.stream>>>(bra, ket, out, P);
+template <typename T, int TB>
+void launch_gens_t(State &sv, const void *bra, const void *ket, double *out, const GenProgram &P) {
+    constexpr int NT = 1 << (TB - GT_JB);
+    const size_t smem = ((size_t)1 << TB) * sizeof(typename VecOf<T, 1>::type) + (size_t)GT_MAX * (NT / 32) * 2 * sizeof(double);
+    const unsigned grid = (unsigned)(1ull << (sv.n - TB));
+    static bool configured[64] = {false};  // per device: function attributes belong to the device's context
+    auto kern = k_bra_gens_ket<T, TB>;
+    if (!configured[sv.device & 63]) {
+        QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[sv.device & 63] = true;
+    }
+    kern<<<grid, NT, smem, sv.stream>>>(bra, ket, out, P);
     QSV_CUDA(cudaGetLastError());
 }
 
+int gens_env(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
 }  // namespace
+
+// tile size of the batched generator kernel for an n-qubit vector (0: too small, generators go one by one) and its
+// contiguous low bits: a 2^13 tile with 2 low bits takes 13 single-qubit generators on arbitrary qubits per launch and the
+// 11 others in the next one, so a layer of rotations on 24 qubits needs two reads of (bra, ket)
+int gens_tile_bits(int n) {
+    static const int want = std::max(12, std::min(gens_env("QSV_GENS_TB", 13), GT_TB_MAX));
+    return n >= want ? want : (n >= 12 ? 12 : 0);
+}
+int gens_low_bits(int tb) {
+    static const int l13 = std::max(1, std::min(gens_env("QSV_GENS_L13", 2), 8));
+    static const int l12 = std::max(1, std::min(gens_env("QSV_GENS_L12", 4), 8));
+    return tb == 13 ? l13 : l12;
+}
 
 namespace {
 
@@ -222,59 +305,51 @@ struct GenItem {
     int tgt = -1;  // kind 1
 };
 
-constexpr int GT_L = 4;
-
 void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem> &todo, double *out_dev) {
     const int n = sv.n;
-    const int max_hi = GT_TB - GT_L;
+    const int TB = gens_tile_bits(n), L = gens_low_bits(TB);
+    const int max_hi = TB - L;
+    const uint64_t low = (1ull << L) - 1ull;
     while (!todo.empty()) {
         // one launch: up to GT_MAX items whose non-diagonal bits >= L number at most max_hi (first fit over all)
         GenProgram P;
         memset(&P, 0, sizeof(P));
-        P.L = GT_L;
+        P.L = L;
         uint64_t need = 0;
         std::vector<GenItem> rest, take;
         for (GenItem &it : todo) {
-            if ((int)take.size() < GT_MAX && __builtin_popcountll(need | it.need) <= max_hi) {
-                need |= it.need;
+            if ((int)take.size() < GT_MAX && __builtin_popcountll((need | it.need) & ~low) <= max_hi) {
+                need |= it.need & ~low;
                 take.push_back(it);
             } else {
                 rest.push_back(it);
             }
         }
+        // off-diagonal generators first: they need bra, whose registers the diagonal part then reuses
+        std::stable_sort(take.begin(), take.end(), [](const GenItem &a, const GenItem &b) { return (a.d.kind != 0) > (b.d.kind != 0); });
         std::vector<int> hi;
-        for (int b = GT_L; b < n; ++b)
+        for (int b = L; b < n; ++b)
             if (need >> b & 1) hi.push_back(b);
-        for (int b = GT_L; b < n && (int)hi.size() < max_hi; ++b)
+        for (int b = L; b < n && (int)hi.size() < max_hi; ++b)
             if (!(need >> b & 1)) hi.push_back(b);
         std::sort(hi.begin(), hi.end());
         int pos[64];
         for (int b = 0; b < 64; ++b) pos[b] = -1;
         std::vector<int> tile_bits;
-        for (int b = 0; b < GT_L; ++b) {
+        for (int b = 0; b < L; ++b) {
             pos[b] = b;
             tile_bits.push_back(b);
         }
         for (int j = 0; j < (int)hi.size(); ++j) {
-            pos[hi[j]] = GT_L + j;
+            pos[hi[j]] = L + j;
             P.hi_bits[j] = (unsigned char)hi[j];
             tile_bits.push_back(hi[j]);
         }
         P.tile_holes = make_holes(tile_bits.data(), (int)tile_bits.size(), 0);
-        static_assert(GT_TB - 3 >= GT_L, "the three per-thread amplitude bits are high tile bits");
         for (GenItem &it : take) {
             GenDesc &d = P.g[P.n_gens++];
             d = it.d;
-            if (d.kind == 0) {
-                // tile bits GT_TB-3 .. GT_TB-1 distinguish the 8 amplitudes of a thread (e = tid + 256 * j)
-                unsigned m = 0, cj = 0;
-                for (int q = 0; q < 3; ++q) {
-                    const int gbit = tile_bits[GT_TB - 3 + q];
-                    m |= (unsigned)((d.zmask >> gbit) & 1ull) << q;
-                    cj |= (unsigned)((d.ctrl >> gbit) & 1ull);
-                }
-                d.pad0 = m | (cj << 8);
-            }
+            if (d.kind != 0) P.n_first = P.n_gens;
             if (d.kind == 1) {
                 d.tbit = (unsigned)pos[it.tgt];
             } else if (d.kind == 2) {
@@ -283,12 +358,31 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
                     if (d.xg >> b & 1) xl |= 1u << pos[b];
                 d.tbit = xl;
             }
+            // the thread's GT_JB amplitude bits j are the top tile bits (e = tid + NT * j): what the generator sees of them
+            unsigned mj = 0, cj = 0, xj = 0;
+            for (int q = 0; q < GT_JB; ++q) {
+                const int gbit = tile_bits[TB - GT_JB + q];
+                mj |= (unsigned)((d.zmask >> gbit) & 1ull) << q;
+                cj |= (unsigned)((d.ctrl >> gbit) & 1ull) << q;
+                xj |= (unsigned)((d.xg >> gbit) & 1ull) << q;
+                d.zmask &= ~(1ull << gbit);
+                d.ctrl &= ~(1ull << gbit);
+            }
+            const unsigned flip0 = d.kind == 2 ? (unsigned)(__builtin_popcount(xj & mj) & 1) : 0u;
+            d.jinfo = mj | (cj << 4) | (flip0 << 8);
         }
         sv.stat_launches += 1;
-        if (sv.dtype == QSV_C128)
-            launch_gens_t<double>(sv, bra, ket, out_dev, P);
-        else
-            launch_gens_t<float>(sv, bra, ket, out_dev, P);
+        if (sv.dtype == QSV_C128) {
+            if (TB == 13)
+                launch_gens_t<double, 13>(sv, bra, ket, out_dev, P);
+            else
+                launch_gens_t<double, 12>(sv, bra, ket, out_dev, P);
+        } else {
+            if (TB == 13)
+                launch_gens_t<float, 13>(sv, bra, ket, out_dev, P);
+            else
+                launch_gens_t<float, 12>(sv, bra, ket, out_dev, P);
+        }
         todo.swap(rest);
     }
 }
@@ -306,7 +400,7 @@ void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std:
         const LoweredGate &g = gens[k];
         int kind;
         if (g.kind == LoweredGate::NOP) continue;  // a projector that is zero on this shard
-        if (!(n >= GT_TB && tile_gen_kind(g, n, kind))) {
+        if (!(gens_tile_bits(n) > 0 && tile_gen_kind(g, n, kind))) {
             launch_bra_op_ket(sv, bra, ket, g, out_dev, slots[k]);
             continue;
         }
@@ -317,7 +411,7 @@ void launch_bra_gens_ket(State &sv, const void *bra, const void *ket, const std:
         it.d.ctrl = g.ctrl_mask;
         if (kind == 1) {
             it.tgt = g.tgt_bits[0];
-            if (it.tgt >= GT_L) it.need = 1ull << it.tgt;
+            it.need = 1ull << it.tgt;
             const cplx zero(0.0, 0.0), one(1.0, 0.0), pi_(0.0, 1.0), mi_(0.0, -1.0);
             const bool is_x = g.mat[0] == zero && g.mat[1] == one && g.mat[2] == one && g.mat[3] == zero;
             const bool is_y = g.mat[0] == zero && g.mat[1] == mi_ && g.mat[2] == pi_ && g.mat[3] == zero;
@@ -361,11 +455,12 @@ void launch_bra_paulis_ket(State &sv, const void *bra, const void *ket, int n_te
                            const uint64_t *zmasks, const int *nys, int first_slot, double *out_dev) {
     sv.use();
     const int n = sv.n;
-    const uint64_t low = (1ull << GT_L) - 1ull;
+    const int TB = gens_tile_bits(n);
+    const uint64_t low = (1ull << gens_low_bits(TB)) - 1ull;
     std::vector<GenItem> todo;
     for (int t = 0; t < n_terms; ++t) {
-        const uint64_t need = xmasks[t] & ~low;
-        if (n < GT_TB || __builtin_popcountll(need) > GT_TB - GT_L) {
+        const uint64_t need = xmasks[t];
+        if (TB == 0 || __builtin_popcountll(need & ~low) > TB - gens_low_bits(TB)) {
             launch_bra_pauli_ket(sv, bra, ket, xmasks[t], zmasks[t], nys[t], out_dev, first_slot + t);
             continue;
         }

@@ -403,6 +403,18 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
         };
         size_t pending = 0;
         for (int64_t idx = first_needed; idx < n_ops; ++idx) pending += skipped(ops.ops[idx]) ? 0 : 1;
+        const char *defer_env = std::getenv("QSV_ADJOINT_DEFER");
+        const bool defer_diag = !(defer_env && std::atoi(defer_env) == 0);
+        std::vector<LoweredGate> deferred_gens;  // diagonal generators waiting for the next layer's launch
+        std::vector<int> deferred_slot0;
+        auto launch_gens = [&](const std::vector<LoweredGate> &gens, const std::vector<int> &slot0) {
+            if (gens.empty()) return;
+            std::vector<int> slots(gens.size());
+            for (size_t i = 0; i < n_obs; ++i) {
+                for (size_t k = 0; k < gens.size(); ++k) slots[k] = slot0[k] + (int)(2 * i);
+                launch_bra_gens_ket(sv, vecs[1 + i]->data, lambda.data, gens, slots, red);
+            }
+        };
         while (pending) {
             std::vector<int64_t> ready;
             for (int w = 0; w < sv.n; ++w)
@@ -411,33 +423,10 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
                     ready.push_back(on_wire[w].back());
             QSV_CHECK(!ready.empty(), "internal: adjoint scheduling made no progress");
             std::sort(ready.begin(), ready.end(), std::greater<int64_t>());
-            // generator inner products of the trainable ready ops, all against the current vectors
-            std::vector<LoweredGate> gens;
-            std::vector<int> gen_slot0;
-            for (int64_t idx : ready) {
-                const int64_t tp = tp_of[idx];
-                if (tp < 0) continue;
-                const Op &op = ops.ops[idx];
-                LoweredGenerator g = lower_generator(sv.n, op.name, op.wires);
-                factor[tp] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
-                extra[tp] = g.extra_identity;
-                gens.push_back(std::move(g.op));
-                gen_slot0.push_back((int)(tp * n_obs * 2));
-                if (g.extra_identity != 0.0) {
-                    LoweredGate id;
-                    for (size_t i = 0; i < n_obs; ++i)
-                        launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
-                }
-            }
-            if (!gens.empty()) {
-                std::vector<int> slots(gens.size());
-                for (size_t i = 0; i < n_obs; ++i) {
-                    for (size_t k = 0; k < gens.size(); ++k) slots[k] = gen_slot0[k] + (int)(2 * i);
-                    launch_bra_gens_ket(sv, vecs[1 + i]->data, lambda.data, gens, slots, red);
-                }
-            }
             // undo the ready ops and everything non-trainable that becomes ready behind them, in one fused batch
+            // (collected first: which generators may wait depends on what the batch touches)
             std::vector<LoweredGate> batch;
+            std::vector<int64_t> grown;
             auto take = [&](int64_t idx) {
                 if (ops.ops[idx].name != "Identity") batch.push_back(lower_op(sv, ops.ops[idx], true));
                 retire(idx);
@@ -452,9 +441,51 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
                     const int64_t idx = on_wire[w].back();
                     if (tp_of[idx] >= 0 || !is_ready(idx)) continue;
                     take(idx);
+                    grown.push_back(idx);
                     grew = true;
                 }
             }
+            uint64_t grown_wires = 0;
+            for (int64_t idx : grown)
+                for (int w : ops.ops[idx].wires) grown_wires |= 1ull << w;
+            // generator inner products of the trainable ready ops, all against the current vectors.  A diagonal generator
+            // of a diagonal gate (RZ, PhaseShift, CRZ, IsingZZ, MultiRZ ...) commutes with its own gate and with the
+            // other gates of this batch (disjoint wires) unless a gate that became ready behind it shares a wire: it
+            // may then be evaluated AFTER the batch just as well, i.e. together with the generators of the next
+            // layer -- one read of (bra, lambda) fewer per layer of such gates.
+            std::vector<LoweredGate> gens;
+            std::vector<int> gen_slot0;
+            gens.swap(deferred_gens);
+            gen_slot0.swap(deferred_slot0);
+            for (int64_t idx : ready) {
+                const int64_t tp = tp_of[idx];
+                if (tp < 0) continue;
+                const Op &op = ops.ops[idx];
+                LoweredGenerator g = lower_generator(sv.n, op.name, op.wires);
+                factor[tp] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
+                extra[tp] = g.extra_identity;
+                uint64_t op_wires = 0;
+                for (int w : op.wires) op_wires |= 1ull << w;
+                const bool gen_diag = g.op.kind == LoweredGate::DIAG || g.op.kind == LoweredGate::PARITY;
+                bool gate_diag = false;
+                if (defer_diag && gen_diag && g.extra_identity == 0.0 && (op_wires & grown_wires) == 0) {
+                    const LoweredGate lg = lower_op(sv, op, true);
+                    gate_diag = lg.kind == LoweredGate::DIAG || lg.kind == LoweredGate::PARITY;
+                }
+                if (gate_diag) {
+                    deferred_gens.push_back(std::move(g.op));
+                    deferred_slot0.push_back((int)(tp * n_obs * 2));
+                    continue;
+                }
+                gens.push_back(std::move(g.op));
+                gen_slot0.push_back((int)(tp * n_obs * 2));
+                if (g.extra_identity != 0.0) {
+                    LoweredGate id;
+                    for (size_t i = 0; i < n_obs; ++i)
+                        launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
+                }
+            }
+            launch_gens(gens, gen_slot0);
             // is any trainable op left?  if not, the remaining daggers are not needed
             if (!batch.empty()) apply_gates_tiled(sv, batch, (void *const *)d_table.p, (int)(1 + n_obs));
             bool trainable_left = false;
@@ -462,6 +493,7 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
                 trainable_left = !done[idx] && tp_of[idx] >= 0;
             if (!trainable_left) break;
         }
+        launch_gens(deferred_gens, deferred_slot0);  // against the vectors after the last batch
     } else {
     int64_t tp_pos = (int64_t)n_tp - 1;
     int64_t cur = (int64_t)n_par_ops - 1;

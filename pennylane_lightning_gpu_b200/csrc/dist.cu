@@ -46,7 +46,15 @@ struct DistCtx {
     std::vector<int> log_of;   // physical bit -> logical bit
     cudaStream_t comm_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_xfer[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // exchange timing for the statistics: event pairs recorded on the stream and read LAZILY (qsv_dist_*_swap_stats) --
+    // the host never waits for an exchange on the hot path, so the next batch is queued behind it at once
+    struct TimedSwap {
+        cudaEvent_t t0, t1;
+        uint64_t bytes;
+    };
+    std::vector<TimedSwap> pending;          // recorded, not read yet
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_events;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // the pair of the exchange in flight (taken from free_events)
     void *stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     uint64_t last_bytes = 0, total_bytes = 0;
@@ -499,6 +507,46 @@ std::vector<SwapItem> swap_set(State &sv) {
     return v;
 }
 
+// statistics without a host stall: take an event pair for the exchange about to be queued ...
+void begin_timed_swap(DistCtx &d) {
+    if (d.free_events.empty()) {
+        cudaEvent_t a, b;
+        QSV_CUDA(cudaEventCreate(&a));
+        QSV_CUDA(cudaEventCreate(&b));
+        d.free_events.push_back({a, b});
+    }
+    d.ev_t0 = d.free_events.back().first;
+    d.ev_t1 = d.free_events.back().second;
+    d.free_events.pop_back();
+}
+// ... read every finished (or, with `wait`, every recorded) pair into the totals
+void harvest_swaps(DistCtx &d, bool wait) {
+    size_t k = 0;
+    for (; k < d.pending.size(); ++k) {
+        DistCtx::TimedSwap &t = d.pending[k];
+        if (wait) {
+            QSV_CUDA(cudaEventSynchronize(t.t1));
+        } else if (cudaEventQuery(t.t1) != cudaSuccess) {
+            cudaGetLastError();
+            break;
+        }
+        float ms = 0.f;
+        QSV_CUDA(cudaEventElapsedTime(&ms, t.t0, t.t1));
+        d.last_ms = ms;
+        d.last_bytes = t.bytes;
+        d.total_ms += ms;
+        d.total_bytes += t.bytes;
+        d.n_swaps += 1;
+        d.free_events.push_back({t.t0, t.t1});
+    }
+    d.pending.erase(d.pending.begin(), d.pending.begin() + k);
+}
+void end_timed_swap(DistCtx &d, uint64_t bytes) {
+    d.pending.push_back({d.ev_t0, d.ev_t1, bytes});
+    d.ev_t0 = d.ev_t1 = nullptr;
+    if (d.pending.size() > 64) harvest_swaps(d, d.pending.size() > 1024);
+}
+
 void swap_p2p(State &sv, const std::vector<SwapItem> &items, int gphys, int l) {
     DistCtx &d = *sv.dist;
     const int n_local = sv.n;
@@ -513,6 +561,7 @@ void swap_p2p(State &sv, const std::vector<SwapItem> &items, int gphys, int l) {
     const uint64_t half = pairs / 2;
     const uint64_t first = a == 0 ? 0 : half;
     const uint64_t count = a == 0 ? half : pairs - half;
+    begin_timed_swap(d);
     QSV_CUDA(cudaEventRecord(d.ev_t0, sv.stream));
     handshake(sv, peer);  // the partner has finished everything queued before its own handshake
     if (count > 0) {
@@ -570,14 +619,7 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
         QSV_CHECK(!d.p2p || sv.data == d.main.local, "the shard was re-allocated after qsv_dist_init; peer mappings are stale");
     if (all_mapped) {
         swap_p2p(sv, items, gphys, l);
-        QSV_CUDA(cudaEventSynchronize(d.ev_t1));
-        float ms = 0.f;
-        QSV_CUDA(cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
-        d.last_ms = ms;
-        d.last_bytes = (uint64_t)(sv.length() / 2) * ab * items.size();
-        d.total_ms += ms;
-        d.total_bytes += d.last_bytes;
-        d.n_swaps += 1;
+        end_timed_swap(d, (uint64_t)(sv.length() / 2) * ab * items.size());
         return;
     }
     const uint64_t block_amps = 1ull << l;
@@ -589,6 +631,7 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     QSV_CUDA(cudaEventRecord(d.ev_ready, sv.stream));
     QSV_CUDA(cudaStreamWaitEvent(d.comm_stream, d.ev_ready, 0));
     QSV_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
+    begin_timed_swap(d);
     QSV_CUDA(cudaEventRecord(d.ev_t0, d.comm_stream));
     uint64_t counter = 0;
     for (const SwapItem &it : items) {
@@ -614,15 +657,7 @@ void dist_swap_physical(State &sv, int gphys, int l, size_t chunk_bytes) {
     QSV_CUDA(cudaEventRecord(d.ev_t1, d.comm_stream));
     QSV_CUDA(cudaStreamWaitEvent(sv.stream, d.ev_t1, 0));
     for (int k = 0; k < 2 && (uint64_t)k < counter; ++k) QSV_CUDA(cudaStreamWaitEvent(sv.stream, d.ev_copy[k], 0));
-    // statistics (host sync only here, once per swap: the transfer is tens of milliseconds)
-    QSV_CUDA(cudaEventSynchronize(d.ev_t1));
-    float ms = 0.f;
-    QSV_CUDA(cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
-    d.last_ms = ms;
-    d.last_bytes = (uint64_t)(sv.length() / 2) * ab * items.size();
-    d.total_ms += ms;
-    d.total_bytes += d.last_bytes;
-    d.n_swaps += 1;
+    end_timed_swap(d, (uint64_t)(sv.length() / 2) * ab * items.size());
 }
 
 namespace {
@@ -781,9 +816,17 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     }
     flush(nullptr);
     if (in_shadow) {
-        // an odd number of fused exchanges: bring the register home (one device-to-device copy of the shard)
-        QSV_CUDA(cudaMemcpyAsync(home, d.shadow, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
-        sv.data = home;
+        // an odd number of fused exchanges.  A register that owns its memory simply lives in the other buffer from now on
+        // (the two buffers and their peer mappings trade places; qsv_data_ptr follows); a borrowed buffer (a torch
+        // tensor) has to hold the state when the call returns: one device-to-device copy of the shard.
+        if (sv.owns) {
+            std::swap(d.main, d.shadow_pb);
+            void *other = d.shadow;
+            d.shadow = home;
+            restore_home.p = other;
+        } else {
+            QSV_CUDA(cudaMemcpyAsync(home, d.shadow, sv.bytes(), cudaMemcpyDeviceToDevice, sv.stream));
+        }
     }
     QSV_CHECK(d.phys_of == plan_phys, "internal: the executed exchanges do not match the planned qubit map");
 }
@@ -1473,6 +1516,14 @@ void dist_free(State &sv) {
         if (d->ev_copy[k]) cudaEventDestroy(d->ev_copy[k]);
     }
     if (d->ev_ready) cudaEventDestroy(d->ev_ready);
+    for (auto &t : d->pending) {
+        cudaEventDestroy(t.t0);
+        cudaEventDestroy(t.t1);
+    }
+    for (auto &e : d->free_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     if (d->ev_t0) cudaEventDestroy(d->ev_t0);
     if (d->ev_t1) cudaEventDestroy(d->ev_t1);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
@@ -1631,8 +1682,6 @@ int qsv_dist_init(qsv_state *sv, const void *id128, int rank, int world_size) {
         QSV_CUDA(cudaEventCreateWithFlags(&d->ev_xfer[k], cudaEventDisableTiming));
         QSV_CUDA(cudaEventCreateWithFlags(&d->ev_copy[k], cudaEventDisableTiming));
     }
-    QSV_CUDA(cudaEventCreate(&d->ev_t0));
-    QSV_CUDA(cudaEventCreate(&d->ev_t1));
     QSV_CUDA(cudaMalloc(&d->red_dev, 4096 * sizeof(double)));
     QSV_CUDA(cudaMalloc(&d->hs_dev, 2 * sizeof(int)));
     QSV_CUDA(cudaMemset(d->hs_dev, 0, 2 * sizeof(int)));
@@ -1942,6 +1991,8 @@ int qsv_dist_nccl_version(int *version) {
 int qsv_dist_last_swap_stats(const qsv_state *sv, uint64_t *bytes_sent, float *ms) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    sv->use();
+    harvest_swaps(*sv->dist, true);  // waits for the recorded exchanges; the hot path never does
     if (bytes_sent) *bytes_sent = sv->dist->last_bytes;
     if (ms) *ms = sv->dist->last_ms;
     QSV_API_END
@@ -1961,6 +2012,8 @@ int qsv_dist_total_swap_stats(qsv_state *sv, int *n_swaps, uint64_t *bytes_sent,
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
     DistCtx &d = *sv->dist;
+    sv->use();
+    harvest_swaps(d, true);
     if (n_swaps) *n_swaps = d.n_swaps;
     if (bytes_sent) *bytes_sent = d.total_bytes;
     if (ms) *ms = d.total_ms;

@@ -918,9 +918,8 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
         }
         cur.clear();
         for (int i : sw.gates) cur.push_back(&merged[i]);
-        // the last sweep of the batch carries the exchange when the exchanged bit is not one of its tile bits
-        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1 &&
-                           !regs_tile_contains_bit(sv.n, sw.need, L, fx->local_bit);
+        // the last sweep of the batch carries the exchange (its stores are routed element by element, xchg_target)
+        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1;
         run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs, carry ? fx : nullptr);
         if (carry) fx->done = true;
     }

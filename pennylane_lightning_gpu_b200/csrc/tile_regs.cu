@@ -42,8 +42,9 @@ __device__ unsigned long long g_sm_arrivals[256];
 // Sweep fused with a global<->local index-bit exchange of a sharded register (XCHG = true, csrc/dist.cu): the sweep reads
 // the shard in place but stores out of place -- tiles whose index bit `bit` equals this rank's value of the exchanged
 // global bit go to the same offset of this rank's other buffer, all other tiles to the partner GPU's other buffer (a
-// peer mapping: plain stores over NVLink) at the offset with that bit flipped.  `bit` is never a tile bit, so the choice
-// is per CTA.  The transfer overlaps the arithmetic of the tiles in flight; no separate exchange pass, no staging.
+// peer mapping: plain stores over NVLink) at the offset with that bit flipped.  The choice is made per stored element
+// (xchg_target), so `bit` may also be a tile bit.  The transfer overlaps the arithmetic of the tiles in flight; no
+// separate exchange pass, no staging.
 struct XchgArgs {
     void *out_mine;
     void *out_peer;
@@ -162,19 +163,147 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         // whole kernel just to be reused here
         uint32_t tid_s = tid;
         asm volatile("" : "+r"(tid_s));
-        uint64_t obase_idx = base;
-        A *obase = gbase;
-        if constexpr (XCHG) {
-            const XchgTarget t = xchg_target(base, xa.bit_mask, xa.keep);
-            obase = reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer);
-            obase_idx = t.base;
-        }
-        const uint64_t gt = obase_idx ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
+        const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
         uint64_t gr[RB_MAX];
 #pragma unroll
         for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
+        if constexpr (XCHG) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) obase[slot_offset<RB>(gt, gr, j)] = x[j];
+            for (int j = 0; j < NS; ++j) {
+                const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep);
+                reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer)[t.base] = x[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
+        }
+    }
+}
+
+// ---- generation 3: persistent CTAs, the next tile streams into the idle transposition buffer ----------------
+// The register-tile kernel above loads a tile from HBM into registers, computes, stores: nothing of a CTA overlaps its own
+// HBM latency, and with 128 registers there are only two CTAs per SM to cover for each other (ncu, round 1: 3.4 ms per
+// sweep that the arithmetic does not hide).  Here a CTA is resident for the whole sweep (grid = CTAs that fit the GPU)
+// and walks over tiles blockIdx.x, + gridDim.x, ...  The shared-memory transposition buffer is idle during the LAST
+// pass of a tile (its result goes from registers straight to HBM), so as soon as the last transposition has been read
+// every thread issues the 2^RB asynchronous copies (cp.async, LDGSTS: HBM -> shared memory, no registers) of ITS OWN
+// amplitudes of the CTA's next tile into private slots (element j * NT + tid: conflict-free, and no barrier is needed
+// to read them back).  The HBM latency of tile k+1 runs under the arithmetic of the last pass of tile k and under the
+// stores; gate constants and descriptors are set up once per CTA instead of once per tile.
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ void touch_value(double2 &v) { asm volatile("" : "+d"(v.x), "+d"(v.y)); }
+__device__ __forceinline__ void touch_value(float2 &v) { asm volatile("" : "+f"(v.x), "+f"(v.y)); }
+
+template <typename T, int RB, int MINB, bool XCHG = false>
+__global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
+    k_tile_regs_p(void *single, void *const *table, const __grid_constant__ RegProgram P,
+                  const std::conditional_t<XCHG, XchgArgs, NoXchg> xa, int tiles_log2, uint32_t n_items) {
+    using A = typename Cx<T>::type;
+    constexpr int NS = 1 << RB;
+    constexpr int NT = 1 << (RT_TB - RB);
+    constexpr int NTB = RT_TB - RB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A *s = reinterpret_cast<A *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    T *spool = reinterpret_cast<T *>(smem_raw + (sizeof(A) << RT_TB));
+    for (int i = tid; i < P.pool_used; i += NT) spool[i] = (T)P.pool[i];
+
+    const uint32_t tile_mask = (1u << tiles_log2) - 1u;
+    auto item_base = [&](uint32_t item, A *&gb) -> uint64_t {
+        gb = reinterpret_cast<A *>(table ? table[item >> tiles_log2] : single);
+        return expand_index((uint64_t)(item & tile_mask), P.tile_holes);
+    };
+    auto prefetch = [&](uint32_t item) {
+        A *gb;
+        const uint64_t b = item_base(item, gb);
+        uint32_t tid_p = tid;
+        asm volatile("" : "+r"(tid_p));  // opaque: the per-bit masks are recomputed here, not kept alive across the passes
+        const uint64_t gt = b ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid_p);
+        uint64_t gr[RB_MAX];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) gr[k] = P.gl_load.reg[k];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) cp_async_elem<(int)sizeof(A)>(s + j * NT + tid_p, gb + slot_offset<RB>(gt, gr, j));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint32_t item = blockIdx.x;
+    if (item < n_items) prefetch(item);
+    __syncthreads();  // the constant pool is in place
+    const int last = P.n_passes - 1;
+    for (; item < n_items; item += gridDim.x) {
+        A *gbase;
+        const uint64_t base = item_base(item, gbase);
+        const uint64_t outside = base | P.index_hi;
+        const uint32_t next = item + gridDim.x;
+        A x[NS];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < NS; ++j) x[j] = s[j * NT + tid];
+        if (last == 0 && next < n_items) {
+            // private slots: nobody else reads or writes them; the copies may only be issued once this thread's own reads
+            // of the slots have returned (cp.async is not ordered after earlier loads of the issuing thread)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) touch_value(x[j]);
+            prefetch(next);
+        }
+        for (int pv = 0;; ++pv) {
+            const int p = __shfl_sync(0xffffffffu, pv, 0);
+            const RegPass &ps = P.passes[p];
+            pass_compute<T, RB>(x, P, ps, tid, outside, spool);
+            if (p == last) break;
+            __syncthreads();  // every thread has read the previous layout (pass 0: its prefetched slots)
+            {
+                const uint32_t st = thread_offset<NTB>(ps.st_thr, ps.st_c, tid);
+                uint32_t sr[RB_MAX];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) sr[b] = ps.st_reg[b];
+#pragma unroll
+                for (int j = 0; j < NS; ++j) s[slot_offset<RB>(st, sr, j)] = x[j];
+            }
+            __syncthreads();
+            {
+                const RegPass &pn = P.passes[p + 1];
+                const uint32_t st = thread_offset<NTB>(pn.ld_thr, pn.ld_c, tid);
+                uint32_t sr[RB_MAX];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) sr[b] = pn.ld_reg[b];
+#pragma unroll
+                for (int j = 0; j < NS; ++j) x[j] = s[slot_offset<RB>(st, sr, j)];
+            }
+            if (p + 1 == last && next < n_items) {
+                __syncthreads();  // the buffer is idle from here on
+                prefetch(next);
+            }
+        }
+        // single pass: a folded permutation stores where another thread of this tile loaded; all of its copies have landed
+        // once every thread is past its wait_group
+        if (last == 0) __syncthreads();
+        {
+            uint32_t tid_s = tid;
+            asm volatile("" : "+r"(tid_s));
+            const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid_s);
+            uint64_t gr[RB_MAX];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) gr[b] = P.gl_store.reg[b];
+            if constexpr (XCHG) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep);
+                    reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer)[t.base] = x[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) gbase[slot_offset<RB>(gt, gr, j)] = x[j];
+            }
+        }
     }
 }
 
@@ -253,15 +382,40 @@ uint64_t regs_need_bits(const LoweredGate &g) { return g.kind == LoweredGate::DE
 
 namespace {
 
+int env_int_regs(const char *name, int dflt);
+
 template <typename T, int RB>
 void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vecs, const XchgArgs *xa) {
     // register budget: 16 amplitudes per thread need 2 CTAs of 256 threads (128 registers); 8 amplitudes per thread run as
     // 2 CTAs of 512 threads (64 registers)
     constexpr int MINB = RB == 4 ? (sizeof(T) == 8 ? 2 : 3) : 2;
     const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
-    dim3 grid((unsigned)(1ull << (sv.n - RT_TB)), (unsigned)n_vecs);
+    const int tiles_log2 = sv.n - RT_TB;
+    QSV_CHECK(!xa || (table == nullptr && n_vecs == 1), "internal: a sweep fused with an exchange works on one vector");
+    static const int persist = env_int_regs("QSV_REGS_PERSIST", 1);
+    if (persist) {
+        // generation 3: resident CTAs walking over the tiles, next tile prefetched into the idle transposition buffer
+        const uint64_t n_items = (uint64_t)n_vecs << tiles_log2;
+        static const int ctas_per_sm = env_int_regs("QSV_REGS_PERSIST_CTAS", MINB);
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_items, (uint64_t)NUM_SMS * ctas_per_sm);
+        auto launch = [&](auto kern, bool &configured, auto xarg) {
+            if (!configured) {
+                QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = true;
+            }
+            kern<<<grid, 1 << (RT_TB - RB), smem, sv.stream>>>(table ? nullptr : sv.data, table, P, xarg, tiles_log2,
+                                                                   (uint32_t)n_items);
+            QSV_CUDA(cudaGetLastError());
+        };
+        static bool conf_p[64] = {false}, conf_px[64] = {false};  // per device: function attributes belong to its context
+        if (xa)
+            launch(k_tile_regs_p<T, RB, MINB, true>, conf_px[sv.device & 63], *xa);
+        else
+            launch(k_tile_regs_p<T, RB, MINB, false>, conf_p[sv.device & 63], NoXchg{});
+        return;
+    }
+    dim3 grid((unsigned)(1ull << tiles_log2), (unsigned)n_vecs);
     if (xa) {
-        QSV_CHECK(table == nullptr && n_vecs == 1, "internal: a sweep fused with an exchange works on one vector");
         static bool configured_x[64] = {false};
         auto kern = k_tile_regs<T, RB, MINB, true>;
         if (!configured_x[sv.device & 63]) {
@@ -1047,7 +1201,6 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     XchgArgs xa_store;
     const XchgArgs *xa = nullptr;
     if (fx) {
-        QSV_CHECK(!regs_tile_contains_bit(sv.n, need, L, fx->local_bit), "internal: the exchanged bit is a tile bit");
         xa_store.out_mine = fx->out_mine;
         xa_store.out_peer = fx->out_peer;
         xa_store.bit_mask = 1ull << fx->local_bit;

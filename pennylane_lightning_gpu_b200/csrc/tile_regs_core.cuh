@@ -72,16 +72,18 @@ struct RegProgram {
     int pad1;
 };
 
-// Sweep fused with a global<->local index-bit exchange (k_tile_regs<..., XCHG = true>, csrc/dist.cu): the tile whose base
-// offset has the exchanged bit equal to this rank's value of the global bit (`keep` = bit_mask or 0) stays on this rank, at
-// the same offset of its other buffer; every other tile goes to the partner's other buffer with that bit flipped.
+// Sweep fused with a global<->local index-bit exchange (k_tile_regs<..., XCHG = true>, csrc/dist.cu): an amplitude whose
+// shard offset has the exchanged bit equal to this rank's value of the global bit (`keep` = bit_mask or 0) stays on this
+// rank, at the same offset of its other buffer; every other amplitude goes to the partner's other buffer with that bit
+// flipped.  The rule is applied per stored element, so the exchanged bit may be any bit of the shard: outside the tile
+// (whole tiles go one way), a thread bit or a register bit of the last pass (a tile is split between the two targets).
 struct XchgTarget {
     bool stays;
     uint64_t base;
 };
-__host__ __device__ __forceinline__ XchgTarget xchg_target(uint64_t base, uint64_t bit_mask, uint64_t keep) {
-    const bool stays = (base & bit_mask) == keep;
-    return {stays, stays ? base : base ^ bit_mask};
+__host__ __device__ __forceinline__ XchgTarget xchg_target(uint64_t offset, uint64_t bit_mask, uint64_t keep) {
+    const bool stays = (offset & bit_mask) == keep;
+    return {stays, stays ? offset : offset ^ bit_mask};
 }
 
 template <typename T> __host__ __device__ __forceinline__ const T *const_pool(const RegProgram &P);

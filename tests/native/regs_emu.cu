@@ -115,10 +115,11 @@ void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegPro
                 A(&x)[NS] = *reinterpret_cast<A(*)[NS]>(&xs[(size_t)tid * NS]);
                 pass_compute<T, RB>(x, P, ps, tid, outside, spool.data());
                 if (last && xc.out_mine) {
-                    const XchgTarget t = xchg_target(base, xc.bit_mask, xc.keep);
-                    A *dst = t.stays ? xc.out_mine : xc.out_peer;
-                    const uint64_t gt = t.base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
-                    for (int j = 0; j < NS; ++j) dst[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
+                    const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
+                    for (int j = 0; j < NS; ++j) {
+                        const XchgTarget t = xchg_target(slot_offset<RB>(gt, P.gl_store.reg, j), xc.bit_mask, xc.keep);
+                        (t.stays ? xc.out_mine : xc.out_peer)[t.base] = x[j];
+                    }
                 } else if (last) {
                     const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
                     for (int j = 0; j < NS; ++j) psi[slot_offset<RB>(gt, P.gl_store.reg, j)] = x[j];
@@ -232,7 +233,7 @@ extern "C" int regs_emu_fused_exchange(const void *ops_handle, int n_local, int 
                 cur.clear();
                 for (int i : sw.gates) cur.push_back(&merged[i]);
                 build_reg_program(n_local, QSV_C128, 0, cur, sw.need, L, 4, P);
-                const bool carry = k + 1 == plan.size() && !regs_tile_contains_bit(n_local, sw.need, L, local_bit);
+                const bool carry = k + 1 == plan.size();
                 emulate_program<double, 4>(psi, n_local, P, carry ? xc : EmuXchg<double2>());
                 done = done || carry;
             }

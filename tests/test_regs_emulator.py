@@ -272,4 +272,6 @@ def test_sweep_fused_with_exchange(emu):
             got = out[r].view(np.complex128)
             assert np.max(np.abs(got - expect[r])) < 1e-12, (n_local, local_bit, r, carried.value)
         modes.add(carried.value)
-    assert modes == {0, 1}  # both forms ran: carried by the last sweep, and the copy pass (exchanged bit inside the tile)
+    # the last sweep carries the exchange wherever the exchanged bit sits (outside the tile, thread bit, register bit); the
+    # copy pass is left for batches that end in a lone unfused gate
+    assert 1 in modes and modes <= {0, 1}
