@@ -201,7 +201,14 @@ def run_ours(args):
     tdtype = torch.complex128 if args.dtype == "c128" else torch.complex64
     hbm_peak, peak_src = measured_peaks()
 
-    ops = workloads.random_gate_circuit(n_total, args.gates, 2024)
+    circuit = args.circuit if args.circuit != "auto" else ("config5" if n_local >= 32 else "config2")
+    if circuit == "config5":
+        # BASELINE config 5: 4 layers of [random one-qubit rotation on every wire, CNOTs on a random perfect matching]
+        ops = workloads.random_layer_circuit(n_total, layers=4, seed=99)
+        workload = f"config 5: 4-layer random-layer circuit ({len(ops)} gates), {n_total} qubits"
+    else:
+        ops = workloads.random_gate_circuit(n_total, args.gates, 2024)
+        workload = f"config 2(ii): {args.gates}-gate random 1/2-qubit circuit, {n_total} qubits"
     alg_bytes_total = circuit_bytes(ops, n_total, amp_bytes)  # whole job (all ranks)
 
     # state in torch-owned HBM, initialised on the device: normalised random state, seed 1234
@@ -219,10 +226,19 @@ def run_ours(args):
         dist.all_reduce(nrm2)
     buf.mul_(1.0 / math.sqrt(float(nrm2)))
 
+    parity = None
     if distributed:
         from pennylane_lightning_gpu_b200.distributed import DistributedStateVector
 
-        sv = DistributedStateVector(n_total, cdtype, device=local_rank, external_ptr=buf.data_ptr())
+        # SCALE carries its own check: the same circuit generator on a reduced register (20 local qubits), sharded
+        # engine with the exchange schedule / fused exchanges of this run against the single-GPU engine on every rank
+        parity = dist_self_check(torch, q, DistributedStateVector, dist, args, local_rank, rank, n_glob, cdtype)
+        # Up to 31 local qubits the register owns its shard, so that exchanges fused into sweeps may leave it in either of
+        # its two buffers (no copy back); beyond that there is no room for a second buffer and it borrows torch's.
+        owned = 3 * (amp_bytes << n_local) < (150 << 30)
+        sv = DistributedStateVector(n_total, cdtype, device=local_rank, external_ptr=None if owned else buf.data_ptr())
+        if owned:
+            sv.local.copy_from(q.StateVector(n_local, cdtype, device=local_rank, external_ptr=buf.data_ptr()))
     else:
         sv = q.StateVector(n_local, cdtype, device=local_rank, external_ptr=buf.data_ptr())
     rec = q.Ops(ops)
@@ -307,6 +323,7 @@ def run_ours(args):
 
     detail = {}
     if distributed:
+        detail["parity_check"] = parity
         n_swaps, swap_bytes, swap_ms = sv.swap_stats()
         # per-direction NVLink bandwidth of the global<->local index-bit swaps (device time of the
         # NCCL send/recv stream, this rank) over warm-up + timed steps
@@ -328,6 +345,17 @@ def run_ours(args):
             total_steps = args.steps + max(args.warmup, 3)
             detail["nvlink_swaps"]["out_of_place_exchanges_per_step"] = n_oop / total_steps
             detail["nvlink_swaps"]["carried_by_sweeps_per_step"] = n_carried / total_steps
+        if circuit == "config5":
+            sw = detail["nvlink_swaps"]
+            detail["config5"] = {
+                "n_qubits": n_total, "local_qubits": n_local, "gpus": world, "gates": len(ops), "ms_per_step": ms_per_step,
+                "shard_gib": (amp_bytes << n_local) / 2**30, "exchanges_per_step": sw["n_swaps_per_step"],
+                "gb_sent_per_exchange_per_gpu": sw["gb_sent_per_swap"], "gbs_per_direction": sw["gbs_per_direction"],
+                "frac_of_770_measured_peer_copy": sw["frac_of_770_measured_peer_copy"],
+                "frac_of_900_nominal": (sw["gbs_per_direction"] / 900.0) if sw["gbs_per_direction"] else None,
+                "target": "global-qubit swaps at >= 0.70 of NVLink bandwidth (north_star)",
+                "timing": "CUDA events around handshake + k_peer_swap + handshake on the compute stream, read lazily; this rank",
+            }
         kernel_ms = ms_total - detail["nvlink_swaps"]["swap_ms_per_step"] * args.steps
         if launches > 0 and kernel_ms > 0:
             roofline["ms_per_launch"] = kernel_ms / launches
@@ -384,7 +412,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers ----------------------------------
     e2e = None
-    if args.e2e:
+    if args.e2e and n_local <= 31:  # a pinned host copy of a 33-qubit shard (128 GiB per rank) is not a sensible input
         e2e = end_to_end(torch, q, sv, buf, ops, n_local, cdtype, tdtype, amp_bytes, alg_bytes_total, args,
                          dist if distributed else None)
 
@@ -398,10 +426,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
-            "config": {"workload": f"config 2(ii): {args.gates}-gate random 1/2-qubit circuit, {n_total} qubits, "
-                                   f"{'complex128' if args.dtype == 'c128' else 'complex64'}",
+            "config": {"workload": f"{workload}, {'complex128' if args.dtype == 'c128' else 'complex64'}",
                        "local_qubits": n_local, "global_qubits": n_glob, "fused": bool(args.fuse),
-                       "l2": "state (16 GiB) >> L2 (126 MB): no flush needed",
+                       "l2": f"state ({(amp_bytes << n_local) / 2**30:.0f} GiB per GPU) >> L2 (126 MB): no flush needed",
                        "bytes_rule": "sum over gates of 2*B*N/2^controls (SURVEY.md 8d), no credit for fusion"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "hbm_sweeps": sweeps, "clocks": clk.summary(), "detail": detail,
@@ -415,6 +442,47 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def dist_self_check(torch, q, DistributedStateVector, dist, args, local_rank, rank, n_glob, cdtype, n_check_local=20):
+    """Before anything is timed at N > 1: the bench's circuit generator on n_check_local + log2(N) qubits, applied twice
+    (the second application runs on the qubit map the first one left, as the timed steps do) on a sharded register with
+    this run's settings, compared shard by shard with the single-GPU engine on the same full state (which the GPU parity
+    tests pin to the oracle).  Raises on a mismatch, so an unverified computation is never timed."""
+    n = n_check_local + n_glob
+    tol = 1e-10 if cdtype == np.complex128 else 1e-5
+    ops = workloads.random_gate_circuit(n, args.gates, 2024)
+    rec = q.Ops(ops)
+    rng = np.random.default_rng(4321)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi = (psi / np.linalg.norm(psi)).astype(cdtype)
+    one = q.StateVector(n, cdtype, device=local_rank)
+    one.h2d(psi)
+    sharded = DistributedStateVector(n, cdtype, device=local_rank)
+    lo, hi = rank << n_check_local, (rank + 1) << n_check_local
+    sharded.h2d(psi[lo:hi])
+    worst = 0.0
+    for _ in range(2):
+        one.apply_ops(rec, fuse=bool(args.fuse))
+        sharded.apply_ops(rec, fuse=bool(args.fuse))
+    n_swaps = sharded.swap_stats()[0]
+    try:
+        n_oop, n_carried = sharded.fused_exchange_stats()
+    except Exception:
+        n_oop, n_carried = 0, 0
+    want = one.d2h()[lo:hi]
+    got = sharded.d2h()  # collective (lazy qubit map): every rank calls it
+    worst = float(np.max(np.abs(got - want)))
+    t = torch.tensor([worst], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t)
+    del one, sharded
+    out = {"n_qubits": n, "local_qubits": n_check_local, "gates": 2 * len(ops), "max_abs_err_vs_single_gpu": worst, "tol": tol,
+           "in_place_exchanges": n_swaps, "exchanges_through_second_buffer": n_oop, "carried_by_sweeps": n_carried,
+           "passed": bool(worst <= tol)}
+    if not out["passed"]:
+        raise SystemExit("bench.py: sharded engine differs from the single-GPU engine: " + json.dumps(out))
+    return out
 
 
 def single_gate_sweeps(torch, q, sv, n, amp_bytes, hbm_peak):
@@ -679,6 +747,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--qubits", type=int, default=30, help="local qubits per GPU")
     ap.add_argument("--gates", type=int, default=200)
+    ap.add_argument("--circuit", default="auto", choices=["auto", "config2", "config5"],
+                    help="auto: config 2(ii) random gate circuit; config 5 random-layer circuit from 32 local qubits up")
     ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
     ap.add_argument("--fuse", type=int, default=1)
     ap.add_argument("--sweeps", type=int, default=1)

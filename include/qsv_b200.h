@@ -239,6 +239,14 @@ int qsv_dist_uses_peer_access(const qsv_state *local);
  * half of its tiles straight into the partner's buffer over NVLink) and how many of them a gate sweep carried; they are
  * not part of the swap statistics above, which time the in-place exchanges */
 int qsv_dist_fused_exchange_stats(const qsv_state *local, int *n_out_of_place, int *n_carried_by_sweeps);
+/* Qubit-map policy of a sharded register.  lazy = 0 (default; the reference's contract, StateVectorCudaMPI keeps every
+ * gate's swaps paired, MPI.hpp:2533-2583): every collective entry point returns with the canonical layout, so
+ * qsv_dist_d2h and the Python `state` property are purely LOCAL copies of the shard (StateVectorCudaBase.hpp:104-228)
+ * and a rank-conditional read cannot dead-lock.  lazy = 1: the logical->physical map persists between calls (a
+ * swapped-in qubit stays local until evicted; what bench.py times); qsv_dist_d2h and qsv_dist_canonicalize are then
+ * COLLECTIVE -- every rank must call them.  Collective itself (it restores the canonical layout when switching back). */
+int qsv_dist_set_lazy_map(qsv_state *sv, int lazy);
+
 /* host-only (no GPU, no NCCL): the exchanges qsv_dist_apply_ops would perform.  steps receives triples
  * (kind, a, b): kind 0 = swap physical global bit a with local bit b, kind 1 = apply op number a */
 int qsv_dist_plan(const qsv_ops *ops, int n_total, int n_local, int *steps, int max_steps, int *n_steps,

@@ -90,6 +90,7 @@ SIGNATURES = {
     "qsv_dist_swap_bits": (_I, [_P, _I, _I, C.c_size_t]),
     "qsv_dist_apply_ops": (_I, [_P, _P, _I, C.c_size_t]),
     "qsv_dist_canonicalize": (_I, [_P, C.c_size_t]),
+    "qsv_dist_set_lazy_map": (_I, [_P, _I]),
     "qsv_dist_qubit_map": (_I, [_P, _IP, _I]),
     "qsv_dist_expval_pauli_words": (_I, [_P, _I, C.c_char_p, _IP, _IP, _DP, _DP, _DP]),
     "qsv_dist_allreduce_f64": (_I, [_P, _DP, _I]),

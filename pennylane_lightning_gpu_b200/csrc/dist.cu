@@ -73,6 +73,12 @@ struct DistCtx {
     };
     std::vector<Companion> comp;
     bool skip_main = false;                // adjoint sweep: the register itself stays where it is
+    // Qubit-map policy.  lazy_map = false (default, the reference's contract): every collective entry point leaves the
+    // register in the canonical layout, so DeviceToHost / `state` stay purely local reads of the shard, as in the
+    // reference (StateVectorCudaBase.hpp:104-228), and a rank-conditional read cannot dead-lock.  lazy_map = true
+    // (qsv_dist_set_lazy_map; the throughput setting of bench.py): the map persists between calls -- a swapped-in
+    // qubit stays local until evicted -- and qsv_dist_d2h / qsv_dist_canonicalize become COLLECTIVE.
+    bool lazy_map = false;
     // exchanges fused into sweeps (QSV_DIST_FUSED_SWAP=1): a second shard-sized buffer, peer-mapped like the first;
     // a fused sweep reads the buffer the register lives in and writes this rank's and the partner's other buffer
     void *shadow = nullptr;
@@ -677,9 +683,11 @@ void swap_logical_in(State &sv, int gphys, int l, size_t chunk_bytes) {
 
 namespace {
 
+// on unless QSV_DIST_FUSED_SWAP=0 (parity on 2 B200s: profiles/r2_dist_check_2gpu_fused.log); needs room for a second
+// shard-sized buffer (ensure_shadow), otherwise the exchanges stay in place
 bool fused_swap_enabled() {
     const char *e = std::getenv("QSV_DIST_FUSED_SWAP");
-    return e && std::atoi(e) != 0;
+    return !(e && std::atoi(e) == 0);
 }
 
 // Collective (every rank calls it at the same point of the same plan): allocate and peer-map the second buffer.  Any
@@ -1644,6 +1652,11 @@ using namespace qsv;
         set_last_error("unknown error");                                                           \
         return 1;                                                                                  \
     }
+// end of a collective entry point: back to the canonical layout unless the register was switched to a lazy map
+#define QSV_DIST_SETTLE(sv)                                                                        \
+    do {                                                                                           \
+        if (!(sv)->dist->lazy_map) dist_canonicalize(*(sv), 0);                                    \
+    } while (0)
 
 extern "C" {
 
@@ -1717,6 +1730,7 @@ int qsv_dist_apply_ops(qsv_state *sv, const qsv_ops *ops, int fuse, size_t chunk
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && ops != nullptr, "null argument");
     dist_apply_ops(*sv, *ops, fuse != 0, chunk_bytes);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1725,6 +1739,14 @@ int qsv_dist_canonicalize(qsv_state *sv, size_t chunk_bytes) {
     QSV_CHECK(sv != nullptr, "null state");
     dist_canonicalize(*sv, chunk_bytes);
     QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    QSV_API_END
+}
+
+int qsv_dist_set_lazy_map(qsv_state *sv, int lazy) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    sv->dist->lazy_map = lazy != 0;
+    QSV_DIST_SETTLE(sv);  // collective when it switches a permuted register back to the canonical contract
     QSV_API_END
 }
 
@@ -1769,6 +1791,7 @@ int qsv_dist_expval_pauli_words(qsv_state *sv, int n_terms, const char *letters,
         nys[t] = ny;
     }
     dist_expval_pauli(*sv, n_terms, xs.data(), zs.data(), nys.data(), coeffs, per_term, out, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1801,6 +1824,7 @@ int qsv_dist_expval_named(qsv_state *sv, const char *name, const int *wires, int
     QSV_CHECK(find_gate(name) != nullptr, std::string("Currently unsupported observable: ") + name);
     std::vector<cplx> m = named_gate_matrix(name, std::vector<double>(params, params + n_params), n_wires);
     dist_expval_matrix(*sv, m.data(), std::vector<int>(wires, wires + n_wires), out, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1812,6 +1836,7 @@ int qsv_dist_expval_matrix(qsv_state *sv, const double *matrix, const int *wires
     std::vector<cplx> m(dim * dim);
     for (size_t i = 0; i < dim * dim; ++i) m[i] = cplx(matrix[2 * i], matrix[2 * i + 1]);
     dist_expval_matrix(*sv, m.data(), std::vector<int>(wires, wires + n_wires), out, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1830,6 +1855,7 @@ int qsv_dist_expval_csr(qsv_state *sv, const int64_t *row_offsets, const int64_t
         for (int64_t i = 0; i < nnz; ++i) o.values[i] = cplx(values[2 * i], values[2 * i + 1]);
     }
     *out = dist_obs_expval(*sv, o, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1837,6 +1863,7 @@ int qsv_dist_probs(qsv_state *sv, const int *wires, int n_wires, double *out) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr && wires && out, "null argument");
     dist_probs(*sv, std::vector<int>(wires, wires + n_wires), out);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1845,6 +1872,7 @@ int qsv_dist_sample(qsv_state *sv, const double *uniforms, int64_t shots, uint64
     QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
     QSV_CHECK(shots >= 0 && (shots == 0 || (uniforms && out)), "invalid sampling arguments");
     dist_sample(*sv, uniforms, shots, out, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1852,6 +1880,7 @@ int qsv_dist_obs_expval(const qsv_obs *obs, qsv_state *sv, double *out) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr && obs && out, "null argument");
     *out = dist_obs_expval(*sv, *obs->p, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1859,6 +1888,7 @@ int qsv_dist_obs_apply(const qsv_obs *obs, qsv_state *sv) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr && obs, "null argument");
     dist_obs_apply(*sv, *obs->p, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1875,6 +1905,7 @@ int qsv_dist_adjoint_jacobian(qsv_state *sv, const qsv_ops *ops, qsv_obs *const 
     std::vector<int64_t> tp(trainable, trainable + n_trainable);
     QSV_CHECK(n_trainable == 0 || jac != nullptr, "null Jacobian output");
     dist_adjoint_jacobian(*sv, *ops, o, tp, apply_operations != 0, jac, 0);
+    QSV_DIST_SETTLE(sv);
     QSV_API_END
 }
 
@@ -1900,7 +1931,15 @@ int qsv_dist_d2h(qsv_state *sv, void *host, size_t n_amps) {
     QSV_API_BEGIN
     QSV_CHECK(sv != nullptr && sv->dist != nullptr && host, "null argument");
     QSV_CHECK(n_amps <= sv->length(), "host buffer larger than the local shard");
-    dist_canonicalize(*sv, 0);
+    // A purely local copy (as CopyGpuDataToHost of the reference) whenever the layout is canonical -- always, unless the
+    // register runs with a lazy map (qsv_dist_set_lazy_map), where this call is collective and documented as such.
+    bool canonical = true;
+    for (int b = 0; b < sv->dist->n_total; ++b) canonical = canonical && sv->dist->phys_of[b] == b;
+    if (!canonical) {
+        QSV_CHECK(sv->dist->lazy_map, "internal: non-canonical layout outside lazy-map mode");
+        dist_canonicalize(*sv, 0);
+    }
+    sv->use();
     QSV_CUDA(cudaMemcpyAsync(host, sv->data, n_amps * sv->amp_bytes(), cudaMemcpyDeviceToHost, sv->stream));
     QSV_CUDA(cudaStreamSynchronize(sv->stream));
     QSV_API_END

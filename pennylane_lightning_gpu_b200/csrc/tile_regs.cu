@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
     }
 }
 
-// ---- generation 3: persistent CTAs, the next tile streams into the idle transposition buffer ----------------
+// ---- experiment (QSV_REGS_PERSIST=1, off: measured 10 % SLOWER than the kernel above, profiles/r2_ab_persist.txt) ----
+// persistent CTAs, the next tile streams into the idle transposition buffer
 // The register-tile kernel above loads a tile from HBM into registers, computes, stores: nothing of a CTA overlaps its own
 // HBM latency, and with 128 registers there are only two CTAs per SM to cover for each other (ncu, round 1: 3.4 ms per
 // sweep that the arithmetic does not hide).  Here a CTA is resident for the whole sweep (grid = CTAs that fit the GPU)
@@ -392,7 +393,7 @@ void launch_regs_t(State &sv, const RegProgram &P, void *const *table, int n_vec
     const size_t smem = ((size_t)1 << RT_TB) * sizeof(typename Cx<T>::type) + RT_POOL * sizeof(T);
     const int tiles_log2 = sv.n - RT_TB;
     QSV_CHECK(!xa || (table == nullptr && n_vecs == 1), "internal: a sweep fused with an exchange works on one vector");
-    static const int persist = env_int_regs("QSV_REGS_PERSIST", 1);
+    static const int persist = env_int_regs("QSV_REGS_PERSIST", 0);  // measured slower on B200 (profiles/r2_ab_persist.txt)
     if (persist) {
         // generation 3: resident CTAs walking over the tiles, next tile prefetched into the idle transposition buffer
         const uint64_t n_items = (uint64_t)n_vecs << tiles_log2;

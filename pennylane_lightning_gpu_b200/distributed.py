@@ -39,7 +39,11 @@ class DistributedStateVector:
     (PennyLane wires 0..g-1 are global, as in lightning_gpu.py:317-319 / MPI.hpp:240-246)."""
 
     def __init__(self, n_total: int, dtype=np.complex128, device: int = 0, *, external_ptr: int | None = None,
-                 chunk_bytes: int = 0):
+                 chunk_bytes: int = 0, lazy_map: bool = True):
+        """lazy_map=True (this class's default, the throughput setting): the logical->physical qubit map persists
+        between calls, and `d2h` / `canonicalize` are COLLECTIVE (every rank must call them).  lazy_map=False is the
+        C ABI's own default and what the pybind classes (`LightningGPUMPI_C*`) use: every call returns with the canonical
+        layout and `d2h` is a purely local copy, as in the reference."""
         import torch
         import torch.distributed as dist
 
@@ -66,6 +70,14 @@ class DistributedStateVector:
         raw = bytes(ident.cpu().tolist())
         self._id = (C.c_ubyte * 128).from_buffer_copy(raw)
         _check(lib().qsv_dist_init(self.local._h, self._id, self.rank, self.world))
+        self.lazy_map = bool(lazy_map)
+        if self.lazy_map:
+            _check(lib().qsv_dist_set_lazy_map(self.local._h, 1))
+
+    def set_lazy_map(self, lazy: bool):
+        """Collective: switches the qubit-map policy (see __init__); back to eager restores the canonical layout."""
+        _check(lib().qsv_dist_set_lazy_map(self.local._h, int(bool(lazy))))
+        self.lazy_map = bool(lazy)
 
     # -- gates ----------------------------------------------------------------------------------
     def apply_ops(self, ops: Ops, fuse: bool = True):

@@ -50,6 +50,21 @@ def random_gate_circuit(n: int, n_gates: int = 200, seed: int = 2024):
     return ops
 
 
+def random_layer_circuit(n: int, layers: int = 4, seed: int = 99):
+    """BASELINE config 5: per layer a random one-qubit rotation (RX / RY / RZ, angle uniform in
+    (-pi, pi)) on every wire, then CNOTs on a random perfect matching of the wires (n odd: one wire sits out)."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(layers):
+        for w in range(n):
+            name = ("RX", "RY", "RZ")[int(rng.integers(3))]
+            ops.append({"name": name, "wires": [w], "params": [float(rng.uniform(-math.pi, math.pi))]})
+        perm = [int(x) for x in rng.permutation(n)]
+        for i in range(0, n - 1, 2):
+            ops.append({"name": "CNOT", "wires": [perm[i], perm[i + 1]], "params": []})
+    return ops
+
+
 def gate_bytes(op: dict, n: int, amp_bytes: int) -> int:
     """Algorithmic bytes of one gate sweep: 2 * B * N / 2^c, c = number of
     control wires, explicit or implicit (CNOT, CZ, Toffoli, CR*, ...)."""

@@ -62,7 +62,7 @@ def measurements_and_adjoint(rank, local_rank, world, g):
     failures = []
     n = g + 8
     rng = np.random.default_rng(77)
-    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 5e-5)):
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 1e-5)):
         ops = workloads.random_gate_circuit(n, 40, seed=5 + n)
         ops += [{"name": "Hadamard", "wires": [0], "params": []}, {"name": "CNOT", "wires": [0, n - 1], "params": []},
                 {"name": "RY", "wires": [1], "params": [0.37]}]
@@ -78,9 +78,10 @@ def measurements_and_adjoint(rank, local_rank, world, g):
         sv.set_state_vector(idx, psi0.astype(dtype))
         sv.apply_ops(q.Ops(ops), fuse=True)
 
-        def check(what, got, ref, scale=10.0):
+        def check(what, got, ref):
+            # north_star's tolerance, relative to the size of the quantity when that exceeds 1 (Hamiltonian sums)
             err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
-            if not err <= tol * scale:
+            if not err <= tol * max(1.0, float(np.max(np.abs(np.asarray(ref))))):
                 failures.append(f"{np.dtype(dtype).name} {what}: err {err:.2e}")
             if rank == 0:
                 print(f"[dist_check] {np.dtype(dtype).name} {what}: err={err:.2e}", flush=True)
@@ -91,16 +92,16 @@ def measurements_and_adjoint(rank, local_rank, world, g):
         h2 = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
         check("expval_named RX(0)", sv.expval_named("RX", [0], [0.4]), orc.expval_matrix(want, orc.gate_matrix("RX", [0.4]), [0]))
         check("expval_matrix 1q", sv.expval_matrix(h1, [0]), orc.expval_matrix(want, h1, [0]))
-        check("expval_matrix 2q", sv.expval_matrix(h2, [n - 1, 0]), orc.expval_matrix(want, h2, [n - 1, 0]), 40.0)
+        check("expval_matrix 2q", sv.expval_matrix(h2, [n - 1, 0]), orc.expval_matrix(want, h2, [n - 1, 0]))
         zoo = _obs_zoo(np.random.default_rng(3), n)
         for i, t in enumerate(zoo):
-            check(f"obs[{i}] expval", sv.expval(q.Observable.from_tuple(t)), orc.expval_obs(want, t), 40.0)
+            check(f"obs[{i}] expval", sv.expval(q.Observable.from_tuple(t)), orc.expval_obs(want, t))
         # sparse Hamiltonian: row blocks + gathers from the other shards
         m, (w2, ws2, c2) = workloads.molecular_style_sparse_hamiltonian(n, n_terms=40, n_flip_masks=6, seed=3)
         ref_sparse = orc.expval_csr(want, m.indptr, m.indices, m.data)
-        check("expval_csr", sv.expval_csr(m.indptr, m.indices, m.data), ref_sparse, 40.0)
-        check("expval sparse obs", sv.expval(q.Observable.sparse(m.indptr, m.indices, m.data)), ref_sparse, 40.0)
-        check("pauli words vs csr", sv.expval_pauli_words(w2, ws2, c2), ref_sparse, 40.0)
+        check("expval_csr", sv.expval_csr(m.indptr, m.indices, m.data), ref_sparse)
+        check("expval sparse obs", sv.expval(q.Observable.sparse(m.indptr, m.indices, m.data)), ref_sparse)
+        check("pauli words vs csr", sv.expval_pauli_words(w2, ws2, c2), ref_sparse)
         # sampling: same definition as the single-GPU sampler over the whole register
         shots = 2000
         u = np.random.default_rng(1234).random(shots)
@@ -119,14 +120,14 @@ def measurements_and_adjoint(rank, local_rank, world, g):
             a.canonicalize()
             shard = a.local_state().astype(np.complex128)
             ref_shard = orc.apply_observable(want, zoo[i])[rank << (n - g):(rank + 1) << (n - g)]
-            check(f"obs[{i}] apply", shard, ref_shard, 100.0)
+            check(f"obs[{i}] apply", shard, ref_shard)
             a.close()
         spo = DistributedStateVector(n, dtype, device=local_rank)
         spo.set_state_vector(idx, want.astype(dtype))
         spo.apply_observable(q.Observable.sparse(m.indptr, m.indices, m.data))
         spo.canonicalize()
         ref_shard = orc.csr_matvec(m.indptr, m.indices, m.data, want)[rank << (n - g):(rank + 1) << (n - g)]
-        check("sparse apply", spo.local_state().astype(np.complex128), ref_shard, 400.0)
+        check("sparse apply", spo.local_state().astype(np.complex128), ref_shard)
         spo.close()
         sv.close()
 
@@ -154,14 +155,14 @@ def measurements_and_adjoint(rank, local_rank, world, g):
         a.apply_ops(rec, fuse=False)
         before = a.norm2()
         jac = a.adjoint_jacobian(rec, [q.Observable.from_tuple(t) for t in obs_t], list(range(n_par)))
-        check("adjoint jacobian (all params)", jac, jref, 400.0)
+        check("adjoint jacobian (all params)", jac, jref)
         tp = [0, 3, 7, n_par - 1]
         jac2 = a.adjoint_jacobian(rec, [q.Observable.from_tuple(obs_t[3])], tp)
-        check("adjoint jacobian (subset)", jac2[0], jref[3][tp], 400.0)
+        check("adjoint jacobian (subset)", jac2[0], jref[3][tp])
         # the register itself is untouched by the adjoint sweep
         a.canonicalize()
-        check("state after adjoint", a.local_state().astype(np.complex128), psi_a[rank << (n - g):(rank + 1) << (n - g)], 40.0)
-        if abs(before - 1) > tol * 100:
+        check("state after adjoint", a.local_state().astype(np.complex128), psi_a[rank << (n - g):(rank + 1) << (n - g)])
+        if abs(before - 1) > tol:
             failures.append("norm before adjoint")
         a.close()
     return failures
@@ -181,7 +182,7 @@ def pybind_twins(rank, local_rank, world, g):
     rng = np.random.default_rng(21)
     psi0 = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
     psi0 /= np.linalg.norm(psi0)
-    for bits, dtype, tol in (("128", np.complex128, 1e-10), ("64", np.complex64, 5e-5)):
+    for bits, dtype, tol in (("128", np.complex128, 1e-10), ("64", np.complex64, 1e-5)):
         sv = getattr(m, "LightningGPUMPI_C" + bits)(mgr, m.DevTag(local_rank), 0, g, n - g)
         if (sv.numLocalQubits(), sv.numGlobalQubits(), sv.dataLength()) != (n - g, g, 1 << (n - g)):
             failures.append("MPI state-vector sizes")
@@ -199,9 +200,9 @@ def pybind_twins(rank, local_rank, world, g):
         sv.apply("QubitUnitary", [0], False, [], mat.ravel().astype(dtype))
         want = orc.apply_op(want, "QubitUnitary", [0], [], matrix=mat)
 
-        def check(what, got, ref, scale=20.0):
+        def check(what, got, ref):
             err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
-            if not err <= tol * scale:
+            if not err <= tol * max(1.0, float(np.max(np.abs(np.asarray(ref))))):
                 failures.append(f"pybind C{bits} {what}: err {err:.2e}")
             if rank == 0:
                 print(f"[dist_check] pybind C{bits} {what}: err={err:.2e}", flush=True)
@@ -223,7 +224,7 @@ def pybind_twins(rank, local_rank, world, g):
             got = sv.ExpectationValue(sp.indptr.astype(idt), sp.indices.astype(idt), sp.data.astype(dtype))
         else:
             got = sv.ExpectationValue(np.array([0, 1, 2], dtype=idt), np.array([0, 1], dtype=idt), np.ones(2, dtype=dtype))
-        check("sparse expval (rank-0 matrix)", got, orc.expval_csr(want, sp.indptr, sp.indices, sp.data), 100.0)
+        check("sparse expval (rank-0 matrix)", got, orc.expval_csr(want, sp.indptr, sp.indices, sp.data))
         # adjoint Jacobian through the MPI twins
         names = ["RX", "CNOT", "RY", "RZ", "CRX"]
         params = [np.array([0.3]), np.array([]), np.array([-0.7]), np.array([1.1]), np.array([0.5])]
@@ -242,8 +243,8 @@ def pybind_twins(rank, local_rank, world, g):
         obs_t = [("Named", "PauliZ", [0]), ("Hamiltonian", [0.4, -0.8], [("Named", "PauliX", [0]), ("TensorProd", [("Named", "PauliZ", [0]), ("Named", "PauliY", [n - 1])])])]
         fin = orc.apply_ops(orc.basis_state(n), aops)
         jref = orc.adjoint_jacobian(fin, aops, obs_t, [0, 1, 2, 3])
-        check("adjoint_jacobian", adj.adjoint_jacobian(sv2, obs, rec, [0, 1, 2, 3]), jref, 100.0)
-        check("adjoint_jacobian_serial", adj.adjoint_jacobian_serial(sv2, obs, rec, [0, 1, 2, 3]), jref, 100.0)
+        check("adjoint_jacobian", adj.adjoint_jacobian(sv2, obs, rec, [0, 1, 2, 3]), jref)
+        check("adjoint_jacobian_serial", adj.adjoint_jacobian_serial(sv2, obs, rec, [0, 1, 2, 3]), jref)
         del sv, sv2
     return failures
 
@@ -267,7 +268,7 @@ def device_mirror(rank, world, g):
         want = orc.apply_op(want, o.name, list(o.wires), list(o.parameters))
     sh = 1 << (n - g)
 
-    def check(what, got, ref, tol=1e-9):
+    def check(what, got, ref, tol=1e-10):
         err = float(np.max(np.abs(np.asarray(got) - np.asarray(ref))))
         if not err <= tol:
             failures.append(f"device {what}: err {err:.2e}")
@@ -296,13 +297,84 @@ def device_mirror(rank, world, g):
     return failures
 
 
+def rank_conditional_read(rank, local_rank, world, g):
+    """The reference's DeviceToHost is a purely local copy (StateVectorCudaBase.hpp:104-228), so `if rank == 0:
+    print(dev.state)` is legal there.  With the C ABI's default qubit-map policy (eager: every call returns with the
+    canonical layout) the same holds here: only rank 0 reads, after gates on global qubits, and nothing dead-locks."""
+    failures = []
+    n = g + 9
+    ops = circuit(n, seed=31, n_gates=40)
+    want = orc.apply_ops(orc.basis_state(n), ops)
+    sv = DistributedStateVector(n, np.complex128, device=local_rank, lazy_map=False)
+    sv.apply_ops(q.Ops(ops), fuse=True)
+    if sv.qubit_map() != list(range(n)):
+        failures.append("eager policy left a permuted qubit map")
+    if rank == 0:
+        shard = sv.d2h()  # rank 0 only
+        err = float(np.max(np.abs(shard - want[: 1 << (n - g)])))
+        print(f"[dist_check] rank-0-only read after global gates: err={err:.2e}", flush=True)
+        if err > 1e-10:
+            failures.append(f"rank-0-only read: err {err:.2e}")
+    z = sv.expval_named("PauliX", [0]).real  # a measurement on a global qubit, then again a one-sided read
+    if abs(z - orc.expval_named(want, "PauliX", [0])) > 1e-10:
+        failures.append("expval after eager apply")
+    if rank == world - 1:
+        shard = sv.d2h()
+        if float(np.max(np.abs(shard - want[rank << (n - g):]))) > 1e-10:
+            failures.append("last-rank-only read")
+    sv.close()
+    return failures
+
+
+def config5_generator_at_28_qubits(rank, local_rank, world, g):
+    """BASELINE config 5's circuit generator (4 layers of a random one-qubit rotation on every wire and CNOTs on
+    a random perfect matching, default_rng(99)) at n = 28 on all GPUs of the box vs ONE GPU vs the CPU restatement
+    (oracle/lq_port.c, itself pinned to the NumPy oracle and the reference's golden vectors).  Pattern:
+    src/tests/mpi/Test_StateVectorCudaMPI_Param.cpp:59-125 (sharded against single device)."""
+    failures = []
+    n = int(os.environ.get("DIST_CHECK_BIG_N", "28"))
+    ops = workloads.random_layer_circuit(n, layers=4, seed=99)
+    rec = q.Ops(ops)
+    one = q.StateVector(n, np.complex128, device=local_rank)
+    one.set_basis_state(0)
+    one.apply_ops(rec, fuse=True)
+    sharded = DistributedStateVector(n, np.complex128, device=local_rank)
+    sharded.apply_ops(rec, fuse=True)
+    n_swaps = sharded.swap_stats()[0]
+    n_oop, n_carried = sharded.fused_exchange_stats()
+    sh = 1 << (n - g)
+    got = sharded.d2h()
+    ref = one.d2h()
+    err = float(np.max(np.abs(got - ref[rank * sh:(rank + 1) * sh])))
+    t = torch.tensor([err], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = float(t)
+    if err > 1e-10:
+        failures.append(f"config-5 generator n={n}: {world} GPUs vs 1 GPU err {err:.2e}")
+    err_cpu = -1.0
+    if rank == 0:
+        from oracle import lq_port as lq
+
+        lq.set_num_threads(os.cpu_count() or 1)
+        st = lq.LQState(n)
+        st.apply_ops(ops)
+        err_cpu = float(np.max(np.abs(st.sv - ref)))
+        if err_cpu > 1e-10:
+            failures.append(f"config-5 generator n={n}: 1 GPU vs CPU restatement err {err_cpu:.2e}")
+        print(f"[dist_check] config-5 generator n={n} ({len(ops)} gates): {world} GPUs vs 1 GPU err={err:.2e}, 1 GPU vs "
+              f"lq_port err={err_cpu:.2e}, exchanges in place={n_swaps} through second buffer={n_oop} carried={n_carried}", flush=True)
+    del one
+    sharded.close()
+    return failures
+
+
 def fused_exchange_check(rank, local_rank, world, g):
     """QSV_DIST_FUSED_SWAP=1 (off by default): exchanges through the second buffer, carried by the sweep before them where
     the exchanged bit is not one of its tile bits.  20 local qubits so that sweeps can carry them; 13 so that the
     copy-pass form runs too; repeated application (odd and even numbers of exchanges, register back home each time)."""
     failures = []
     os.environ["QSV_DIST_FUSED_SWAP"] = "1"
-    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 5e-5)):
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 1e-5)):
         for n_local in (13, 20):
             n_total = n_local + g
             ops = circuit(n_total, seed=100 + n_total)
@@ -345,16 +417,19 @@ def main():
             print("DIST_CHECK", "PASS" if int(ok) == 1 else "FAIL", failures, flush=True)
         dist.destroy_process_group()
         sys.exit(0 if int(ok) == 1 else 1)
-    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 2e-5)):
+    for dtype, tol in ((np.complex128, 1e-10), (np.complex64, 1e-5)):
         for n_total in (g + 6, g + 13):
             n_local = n_total - g
             ops = circuit(n_total, seed=n_total)
             want = orc.apply_ops(orc.basis_state(n_total), ops)
             want2 = orc.apply_ops(want, ops)
             # exchange schedule over the dependency DAG (default) and in program order (QSV_DIST_DAG=0, read per call)
-            for fuse, chunk, dag in ((False, 0, "1"), (True, 0, "1"), (False, 1 << 12, "1"), (True, 1 << 12, "1"),
-                                     (True, 0, "0"), (False, 1 << 12, "0")):
+            # ... and with exchanges fused into sweeps through a second buffer (default) or in place (QSV_DIST_FUSED_SWAP=0)
+            for fuse, chunk, dag, fx in ((False, 0, "1", "1"), (True, 0, "1", "1"), (False, 1 << 12, "1", "1"),
+                                         (True, 1 << 12, "1", "0"), (True, 0, "0", "1"), (False, 1 << 12, "0", "0"),
+                                         (True, 0, "1", "0")):
                 os.environ["QSV_DIST_DAG"] = dag
+                os.environ["QSV_DIST_FUSED_SWAP"] = fx
                 sv = DistributedStateVector(n_total, dtype, device=local_rank, chunk_bytes=chunk)
                 sv.apply_ops(q.Ops(ops), fuse=fuse)
                 n_swaps, nbytes, ms = sv.swap_stats()
@@ -372,8 +447,8 @@ def main():
                 dist.all_gather(parts, shard)
                 full = np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
                 err = float(np.max(np.abs(full - want)))
-                tag = f"dtype={np.dtype(dtype).name} n={n_total} fuse={fuse} chunk={chunk} dag={dag}"
-                if err > tol * 10 or abs(ev - ev_want) > tol * 100 or abs(nrm - 1) > tol * 100:
+                tag = f"dtype={np.dtype(dtype).name} n={n_total} fuse={fuse} chunk={chunk} dag={dag} fused_exchange={fx}"
+                if err > tol or abs(ev - ev_want) > tol * max(1.0, abs(ev_want)) or abs(nrm - 1) > tol:
                     failures.append(f"{tag}: state err {err:.2e}, expval {ev} vs {ev_want}, norm {nrm}")
                 if rank == 0:
                     print(f"[dist_check] {tag}: err={err:.2e} expval_err={abs(ev - ev_want):.2e} swaps={n_swaps}", flush=True)
@@ -389,12 +464,16 @@ def main():
                     dist.all_gather(parts, shard)
                     full = np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
                     err = float(np.max(np.abs(full - third)))
-                    if err > tol * 30:
+                    if err > tol:
                         failures.append(f"{tag} repeated: state err {err:.2e}")
                     if rank == 0:
                         print(f"[dist_check] {tag} repeated: err={err:.2e}", flush=True)
                 sv.close()
             os.environ.pop("QSV_DIST_DAG", None)
+            os.environ.pop("QSV_DIST_FUSED_SWAP", None)
+    failures += rank_conditional_read(rank, local_rank, world, g)
+    if os.environ.get("DIST_CHECK_N28", "1") == "1":
+        failures += config5_generator_at_28_qubits(rank, local_rank, world, g)
     failures += measurements_and_adjoint(rank, local_rank, world, g)
     failures += pybind_twins(rank, local_rank, world, g)
     failures += device_mirror(rank, world, g)
