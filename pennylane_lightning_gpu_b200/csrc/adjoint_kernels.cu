@@ -25,23 +25,26 @@ constexpr int GT_TB_MAX = 13;            // tile bits: 2^12 (256 threads) or 2^1
 
 struct GenDesc {
     int kind;            // 0: diagonal table (<= 1 table bit: parity of index & zmask), 1: 2x2 block on one tile bit,
-                         // 2: Pauli word (X/Y letters on tile bits, Z letters anywhere)
+                         // 2: Pauli word (X/Y letters on tile bits, Z letters anywhere),
+                         // 3: "Z sum": kind 0 without controls whose parity mask has at most one bit (RZ, PhaseShift ...)
     int slot;            // complex output slot
-    unsigned tbit;       // kind 1: tile-local position of the target bit; kind 2: tile-local flip mask
+    unsigned tbit;       // kind 1: tile-local position of the target bit; kind 2: tile-local flip mask;
+                         // kind 3: tile-local position of the parity bit, ZS_OUTSIDE (sign from xg & base) or ZS_NONE
     unsigned jinfo;      // what the generator sees of the thread's GT_JB amplitude bits j (CTA-uniform, so the per-amplitude
                          // work is branch-free): bits 0-3 parity mask over j, bits 4-7 control mask over j, bit 8 constant
                          // parity flip (kind 2: the flipped j bits under the parity mask)
     uint64_t ctrl;       // global bits that must be 1          } outside the j columns: thread-constant
     uint64_t zmask;      // kind 0 / 2: global parity-mask bits }
-    uint64_t xg;         // kind 2: flip mask on global bits
-    double m[8];         // kind 1: row-major complex 2x2; kind 0: phases for even / odd parity; kind 2: i^ny
+    uint64_t xg;         // kind 2: flip mask on global bits; kind 3: the parity bit as a global mask
+    double m[8];         // kind 1: row-major complex 2x2; kind 0 / 3: phases for even / odd parity; kind 2: i^ny
 };
+constexpr unsigned ZS_OUTSIDE = 255u, ZS_NONE = 254u;
 
 struct GenProgram {
     int n_gens;
-    int n_first;                // generators [0, n_first) are of kind 1 / 2 (they need bra), the rest are diagonal
+    int n_first;                // generators [0, n_first) are of kind 1 / 2 (they need bra),
+    int n_diag;                 // [n_first, n_diag) generic diagonal ones (kind 0), [n_diag, n_gens) Z sums (kind 3)
     int L;
-    int pad;
     unsigned char hi_bits[16];  // global positions of tile bits L..TB-1
     Holes tile_holes;
     GenDesc g[GT_MAX];
@@ -68,21 +71,44 @@ __device__ __forceinline__ void pick_w(const double (&Wr)[GT_EPT], const double 
     }
 }
 
+// Sums 8 values over the 32 lanes of a warp through a per-warp scratch area (32 x 9 doubles, padded): 8 stores, 8 loads,
+// 7 adds and two shuffle levels instead of 8 x 5 shuffle levels.  Afterwards lane 4 * i (and its three neighbours) holds
+// the warp total of v[i].
+constexpr int RED_PAD = 9;
+__device__ __forceinline__ double warp_reduce8(const double (&v)[8], double *scratch, uint32_t lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) scratch[lane * RED_PAD + i] = v[i];
+    __syncwarp();
+    const uint32_t i = lane >> 2, part = lane & 3u;
+    double a = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a += scratch[(8u * part + t) * RED_PAD + i];
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    __syncwarp();
+    return a;
+}
+
 // One CTA = one tile of 2^TB amplitudes: ket in shared memory, the matching bra amplitudes in registers (16 per thread:
 // element e = tid + NT * j, j = the top four tile bits).  Everything a generator needs to know about an amplitude splits
 // into a thread-constant part (computed once per generator and thread) and a part that depends on j only, which is
 // CTA-uniform and unrolled -- so the inner loops are one shared-memory read and four FP64 multiply-adds per amplitude.
+// Cross-lane sums are taken four generators at a time (warp_reduce8).
 template <typename T, int TB>
 __global__ void __launch_bounds__(1 << (TB - GT_JB))
     k_bra_gens_ket(const void *__restrict__ bra, const void *__restrict__ ket, double *out,
                    const __grid_constant__ GenProgram P) {
     using A = typename VecOf<T, 1>::type;
     constexpr int NT = 1 << (TB - GT_JB), NW = NT / 32;
+    constexpr int NZ = 1 + 5 + GT_JB;  // per-warp Z-sum table: total, sign by lane bit 0..4, sign by j bit 0..3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     A *s = reinterpret_cast<A *>(smem_raw);
     double(*s_acc)[NW][2] = reinterpret_cast<double(*)[NW][2]>(smem_raw + (sizeof(A) << TB));
+    double *s_red = reinterpret_cast<double *>(s_acc + GT_MAX);           // NW x 32 x RED_PAD
+    double(*s_z)[NZ][2] = reinterpret_cast<double(*)[NZ][2]>(s_red + NW * 32 * RED_PAD);  // NW x NZ x 2
     const uint64_t base = expand_index((uint64_t)blockIdx.x, P.tile_holes);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    double *scratch = s_red + warp * (32 * RED_PAD);
 
     // element e of the tile (local index) lives at global index base | deposit(e); g0 = the thread part (j bits clear)
     uint64_t g0 = tid & ((1u << P.L) - 1u);
@@ -108,138 +134,259 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
         for (int j = 0; j < GT_EPT; ++j) b[j] = s[tid + (uint32_t)j * NT];
     }
 
-    auto reduce_store = [&](int k, double re, double im) {
-        re = warp_sum(re);
-        im = warp_sum(im);
-        if (lane == 0) {
-            s_acc[k][warp][0] = re;
-            s_acc[k][warp][1] = im;
-        }
+    // results of up to four generators wait in v[] for one batched cross-lane sum
+    double v[8];
+    auto flush_group = [&](int k0, int count) {
+        const double a = warp_reduce8(v, scratch, lane);
+        const int i = (int)(lane >> 2);
+        if ((lane & 3u) == 0u && (i >> 1) < count) s_acc[k0 + (i >> 1)][warp][i & 1] = a;
+    };
+    auto put = [&](int q, double re, double im) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+            if (q == qq) {
+                v[2 * qq] = re;
+                v[2 * qq + 1] = im;
+            }
     };
 
     // ---- generators with off-diagonal parts: Pauli words and 2x2 blocks --------------------------------------
-    for (int k = 0; k < P.n_first; ++k) {
-        const GenDesc &g = P.g[k];
-        const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
-        const bool t_on = (g0 & g.ctrl) == g.ctrl;
-        double re = 0.0, im = 0.0;
-        if (g.kind == 2) {
-            // (P ket)_i = i^ny * (-1)^{popc(i' & z)} * ket_i' with i' = i ^ x (only where the control bits are set: generators
-            // |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum
-            const bool t_odd = ((__popcll((g0 ^ g.xg) & g.zmask) ^ (g.jinfo >> 8)) & 1u) != 0u;
-            double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};  // two chains each
-            if (t_on) {
-                if (mj == 0u) {
+    for (int k0 = 0; k0 < P.n_first; k0 += 4) {
+        const int count = min(4, P.n_first - k0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.0;
+        for (int q = 0; q < count; ++q) {
+            const GenDesc &g = P.g[k0 + q];
+            const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
+            const bool t_on = (g0 & g.ctrl) == g.ctrl;
+            double re = 0.0, im = 0.0;
+            if (g.kind == 2) {
+                // (P ket)_i = i^ny * (-1)^{popc(i' & z)} * ket_i' with i' = i ^ x (only where the control bits are set:
+                // generators |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum
+                const bool t_odd = ((__popcll((g0 ^ g.xg) & g.zmask) ^ (g.jinfo >> 8)) & 1u) != 0u;
+                double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};  // four independent chains of multiply-adds
+                if (t_on) {
+                    if (mj == 0u) {
+#pragma unroll
+                        for (int j = 0; j < GT_EPT; ++j) {
+                            if (((unsigned)j & cjm) != cjm) continue;
+                            const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                            ar[j & 1] = fma((double)b[j].x, (double)x.x, ar[j & 1]);
+                            ar[j & 1] = fma((double)b[j].y, (double)x.y, ar[j & 1]);
+                            ai[j & 1] = fma((double)b[j].x, (double)x.y, ai[j & 1]);
+                            ai[j & 1] = fma(-(double)b[j].y, (double)x.x, ai[j & 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < GT_EPT; ++j) {
+                            if (((unsigned)j & cjm) != cjm) continue;
+                            const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                            const double sg = (__popc((unsigned)j & mj) & 1) ? -1.0 : 1.0;  // CTA-uniform
+                            const double bx = sg * (double)b[j].x, by = sg * (double)b[j].y;
+                            ar[j & 1] = fma(bx, (double)x.x, ar[j & 1]);
+                            ar[j & 1] = fma(by, (double)x.y, ar[j & 1]);
+                            ai[j & 1] = fma(bx, (double)x.y, ai[j & 1]);
+                            ai[j & 1] = fma(-by, (double)x.x, ai[j & 1]);
+                        }
+                    }
+                }
+                const double r0 = t_odd ? -(ar[0] + ar[1]) : ar[0] + ar[1], i0 = t_odd ? -(ai[0] + ai[1]) : ai[0] + ai[1];
+                re = g.m[0] * r0 - g.m[1] * i0;
+                im = g.m[0] * i0 + g.m[1] * r0;
+            } else {
+                const uint32_t bit = 1u << g.tbit;
+                const double m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
+                const double m4 = g.m[4], m5 = g.m[5], m6 = g.m[6], m7 = g.m[7];
+                if (t_on) {
 #pragma unroll
                     for (int j = 0; j < GT_EPT; ++j) {
                         if (((unsigned)j & cjm) != cjm) continue;
-                        const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
-                        ar[j & 1] += (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
-                        ai[j & 1] += (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < GT_EPT; ++j) {
-                        if (((unsigned)j & cjm) != cjm) continue;
-                        const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
-                        const double sg = (__popc((unsigned)j & mj) & 1) ? -1.0 : 1.0;  // CTA-uniform
-                        const double bx = sg * (double)b[j].x, by = sg * (double)b[j].y;
-                        ar[j & 1] += bx * (double)x.x + by * (double)x.y;
-                        ai[j & 1] += bx * (double)x.y - by * (double)x.x;
+                        const uint32_t e = tid + (uint32_t)j * NT;
+                        const A x0 = s[e & ~bit], x1 = s[e | bit];
+                        const bool hi = (e & bit) != 0;
+                        const double ar = hi ? m4 : m0, ai = hi ? m5 : m1, br = hi ? m6 : m2, bi = hi ? m7 : m3;
+                        const double yr = ar * (double)x0.x - ai * (double)x0.y + br * (double)x1.x - bi * (double)x1.y;
+                        const double yi = ar * (double)x0.y + ai * (double)x0.x + br * (double)x1.y + bi * (double)x1.x;
+                        re += (double)b[j].x * yr + (double)b[j].y * yi;
+                        im += (double)b[j].x * yi - (double)b[j].y * yr;
                     }
                 }
             }
-            const double r0 = t_odd ? -(ar[0] + ar[1]) : ar[0] + ar[1], i0 = t_odd ? -(ai[0] + ai[1]) : ai[0] + ai[1];
-            re = g.m[0] * r0 - g.m[1] * i0;
-            im = g.m[0] * i0 + g.m[1] * r0;
-        } else {
-            const uint32_t bit = 1u << g.tbit;
-            const double m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
-            const double m4 = g.m[4], m5 = g.m[5], m6 = g.m[6], m7 = g.m[7];
-            if (t_on) {
-#pragma unroll
-                for (int j = 0; j < GT_EPT; ++j) {
-                    if (((unsigned)j & cjm) != cjm) continue;
-                    const uint32_t e = tid + (uint32_t)j * NT;
-                    const A x0 = s[e & ~bit], x1 = s[e | bit];
-                    const bool hi = (e & bit) != 0;
-                    const double ar = hi ? m4 : m0, ai = hi ? m5 : m1, br = hi ? m6 : m2, bi = hi ? m7 : m3;
-                    const double yr = ar * (double)x0.x - ai * (double)x0.y + br * (double)x1.x - bi * (double)x1.y;
-                    const double yi = ar * (double)x0.y + ai * (double)x0.x + br * (double)x1.y + bi * (double)x1.x;
-                    re += (double)b[j].x * yr + (double)b[j].y * yi;
-                    im += (double)b[j].x * yi - (double)b[j].y * yr;
-                }
-            }
+            put(q, re, im);
         }
-        reduce_store(k, re, im);
+        flush_group(k0, count);
     }
 
     // ---- diagonal / parity generators -------------------------------------------------------------------------
-    // conj(b_i) * p(i) * k_i with t0_i = conj(b_i) * k_i shared by all of them.  The thread's 16 amplitudes differ in the j
-    // bits only, so with W[m] = sum_j (-1)^{popc(j & m)} t0_j (one Walsh-Hadamard transform per thread)
-    //   sum over the j that have the control bits c set of (-1)^{popc(j & m)} t0_j = 2^-|c| sum_{s subset of c} (-1)^|s| W[m ^ s]
-    // and a generator costs a handful of FP64 operations per THREAD instead of ~8 per amplitude.
+    // conj(b_i) * p(i) * k_i with t0_i = conj(b_i) * k_i shared by all of them; the thread's 16 amplitudes differ in the j
+    // bits only.
     if (P.n_first < P.n_gens) {
         double Wr[GT_EPT], Wi[GT_EPT];
 #pragma unroll
         for (int j = 0; j < GT_EPT; ++j) {
             const A x = s[tid + (uint32_t)j * NT];
-            Wr[j] = (double)b[j].x * (double)x.x + (double)b[j].y * (double)x.y;
-            Wi[j] = (double)b[j].x * (double)x.y - (double)b[j].y * (double)x.x;
+            Wr[j] = fma((double)b[j].x, (double)x.x, (double)b[j].y * (double)x.y);
+            Wi[j] = fma((double)b[j].x, (double)x.y, -((double)b[j].y * (double)x.x));
         }
+        if (P.n_diag < P.n_gens) {
+            // Z sums: every generator of the form  e_even * [bit = 0] + e_odd * [bit = 1]  (RZ, PhaseShift, Z-type
+            // observables) needs only M = sum_i t0_i and Z = sum_i (-1)^{bit(i)} t0_i.  One pass yields Z for EVERY bit of
+            // the index at once: the four j bits by a pruned Walsh-Hadamard transform in registers, the five lane bits by a
+            // butterfly over the warp, the warp bits and the bits outside the tile as signs in the final sum below.
+            double zr[8], zi_[8];  // zr/zi_[q] = sum_j (-1)^{j_q} t0_j for q < 4; index 4: plain sum
+            {
+                double sr[GT_EPT], si[GT_EPT];
 #pragma unroll
-        for (int h = 1; h < GT_EPT; h <<= 1)
+                for (int j = 0; j < GT_EPT; ++j) {
+                    sr[j] = Wr[j];
+                    si[j] = Wi[j];
+                }
 #pragma unroll
-            for (int j = 0; j < GT_EPT; ++j)
-                if (!(j & h)) {
-                    const double ar = Wr[j], ai = Wi[j], br = Wr[j | h], bi = Wi[j | h];
-                    Wr[j] = ar + br;
-                    Wi[j] = ai + bi;
-                    Wr[j | h] = ar - br;
-                    Wi[j | h] = ai - bi;
+                for (int q = 0; q < GT_JB; ++q) {
+                    const int half = GT_EPT >> (q + 1);  // values left after this level
+                    double dr = 0.0, di = 0.0;
+#pragma unroll
+                    for (int t = 0; t < half; ++t) {
+                        dr += sr[2 * t] - sr[2 * t + 1];
+                        di += si[2 * t] - si[2 * t + 1];
+                        sr[t] = sr[2 * t] + sr[2 * t + 1];
+                        si[t] = si[2 * t] + si[2 * t + 1];
+                    }
+                    zr[q] = dr;
+                    zi_[q] = di;
                 }
-        for (int k = P.n_first; k < P.n_gens; ++k) {
-            const GenDesc &g = P.g[k];
-            const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
-            double re = 0.0, im = 0.0;
-            if ((g0 & g.ctrl) == g.ctrl) {
-                // S0 = sum over the controlled j of t0_j, Sm = the same with the parity sign
-                double s0r = 0.0, s0i = 0.0, smr = 0.0, smi = 0.0;
-                unsigned sub = cjm;
-                for (;;) {  // CTA-uniform loop over the subsets of the control mask (one iteration without controls on j bits)
-                    const double sg = (__popc(sub) & 1) ? -1.0 : 1.0;
-                    double wr, wi;
-                    pick_w(Wr, Wi, sub, wr, wi);
-                    s0r += sg * wr;
-                    s0i += sg * wi;
-                    pick_w(Wr, Wi, mj ^ sub, wr, wi);
-                    smr += sg * wr;
-                    smi += sg * wi;
-                    if (sub == 0u) break;
-                    sub = (sub - 1u) & cjm;
-                }
-                const double sc = 0.5 / (double)(1u << __popc(cjm));
-                const double Er = sc * (s0r + smr), Ei = sc * (s0i + smi);  // even parity among the j bits
-                const double Or = sc * (s0r - smr), Oi = sc * (s0i - smi);  // odd
-                const bool odd = __popcll(g0 & g.zmask) & 1;
-                const double ear = odd ? g.m[2] : g.m[0], eai = odd ? g.m[3] : g.m[1];
-                const double ebr = odd ? g.m[0] : g.m[2], ebi = odd ? g.m[1] : g.m[3];
-                re = ear * Er - eai * Ei + ebr * Or - ebi * Oi;
-                im = ear * Ei + eai * Er + ebr * Oi + ebi * Or;
+                zr[4] = sr[0];
+                zi_[4] = si[0];
             }
-            reduce_store(k, re, im);
+            // j-bit sums over the lanes (8 values at once)
+            {
+                double w8[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w8[2 * q] = zr[q];
+                    w8[2 * q + 1] = zi_[q];
+                }
+                const double a = warp_reduce8(w8, scratch, lane);
+                if ((lane & 3u) == 0u) s_z[warp][6 + (lane >> 3)][(lane >> 2) & 1u] = a;
+            }
+            // lane bits: Walsh-Hadamard butterfly of the plain per-thread sum over the 32 lanes
+            double hr = zr[4], hi = zi_[4];
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                const double orr = __shfl_xor_sync(0xffffffffu, hr, m), oi = __shfl_xor_sync(0xffffffffu, hi, m);
+                const double sg = (lane & m) ? -1.0 : 1.0;
+                hr = fma(sg, hr, orr);
+                hi = fma(sg, hi, oi);
+            }
+            // lane 0: total; lane 2^q: sign by lane bit q
+            if (lane == 0u) {
+                s_z[warp][0][0] = hr;
+                s_z[warp][0][1] = hi;
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (lane == (1u << q)) {
+                    s_z[warp][1 + q][0] = hr;
+                    s_z[warp][1 + q][1] = hi;
+                }
+        }
+        if (P.n_first < P.n_diag) {
+            // generic diagonal generators (several parity bits, controls): with W[m] = sum_j (-1)^{popc(j & m)} t0_j
+            //   sum over the j that have the control bits c set of (-1)^{popc(j & m)} t0_j = 2^-|c| sum_{s subset of c} (-1)^|s| W[m ^ s]
+#pragma unroll
+            for (int h = 1; h < GT_EPT; h <<= 1)
+#pragma unroll
+                for (int j = 0; j < GT_EPT; ++j)
+                    if (!(j & h)) {
+                        const double ar = Wr[j], ai = Wi[j], br = Wr[j | h], bi = Wi[j | h];
+                        Wr[j] = ar + br;
+                        Wi[j] = ai + bi;
+                        Wr[j | h] = ar - br;
+                        Wi[j | h] = ai - bi;
+                    }
+            for (int k0 = P.n_first; k0 < P.n_diag; k0 += 4) {
+                const int count = min(4, P.n_diag - k0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.0;
+                for (int q = 0; q < count; ++q) {
+                    const GenDesc &g = P.g[k0 + q];
+                    const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
+                    double re = 0.0, im = 0.0;
+                    if ((g0 & g.ctrl) == g.ctrl) {
+                        // S0 = sum over the controlled j of t0_j, Sm = the same with the parity sign
+                        double s0r = 0.0, s0i = 0.0, smr = 0.0, smi = 0.0;
+                        unsigned sub = cjm;
+                        for (;;) {  // CTA-uniform loop over the subsets of the control mask (one iteration without controls on j)
+                            const double sg = (__popc(sub) & 1) ? -1.0 : 1.0;
+                            double wr, wi;
+                            pick_w(Wr, Wi, sub, wr, wi);
+                            s0r += sg * wr;
+                            s0i += sg * wi;
+                            pick_w(Wr, Wi, mj ^ sub, wr, wi);
+                            smr += sg * wr;
+                            smi += sg * wi;
+                            if (sub == 0u) break;
+                            sub = (sub - 1u) & cjm;
+                        }
+                        const double sc = 0.5 / (double)(1u << __popc(cjm));
+                        const double Er = sc * (s0r + smr), Ei = sc * (s0i + smi);  // even parity among the j bits
+                        const double Or = sc * (s0r - smr), Oi = sc * (s0i - smi);  // odd
+                        const bool odd = __popcll(g0 & g.zmask) & 1;
+                        const double ear = odd ? g.m[2] : g.m[0], eai = odd ? g.m[3] : g.m[1];
+                        const double ebr = odd ? g.m[0] : g.m[2], ebi = odd ? g.m[1] : g.m[3];
+                        re = ear * Er - eai * Ei + ebr * Or - ebi * Oi;
+                        im = ear * Ei + eai * Er + ebr * Oi + ebi * Or;
+                    }
+                    put(q, re, im);
+                }
+                flush_group(k0, count);
+            }
         }
     }
     __syncthreads();
     if ((int)tid < P.n_gens) {
+        const GenDesc &g = P.g[tid];
         double re = 0.0, im = 0.0;
+        if ((int)tid < P.n_diag) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            re += s_acc[tid][w][0];
-            im += s_acc[tid][w][1];
+            for (int w = 0; w < NW; ++w) {
+                re += s_acc[tid][w][0];
+                im += s_acc[tid][w][1];
+            }
+        } else {
+            // value = e_even * (M + Z) / 2 + e_odd * (M - Z) / 2
+            double Mr = 0.0, Mi = 0.0, Zr = 0.0, Zi = 0.0;
+            const unsigned p = g.tbit;
+            for (int w = 0; w < NW; ++w) {
+                const double mr = s_z[w][0][0], mi = s_z[w][0][1];
+                Mr += mr;
+                Mi += mi;
+                if (p < 5u) {
+                    Zr += s_z[w][1 + p][0];
+                    Zi += s_z[w][1 + p][1];
+                } else if (p < (unsigned)(TB - GT_JB)) {
+                    const double sg = ((unsigned)w >> (p - 5u)) & 1u ? -1.0 : 1.0;
+                    Zr += sg * mr;
+                    Zi += sg * mi;
+                } else if (p < (unsigned)TB) {
+                    Zr += s_z[w][6 + p - (TB - GT_JB)][0];
+                    Zi += s_z[w][6 + p - (TB - GT_JB)][1];
+                }
+            }
+            if (p == ZS_OUTSIDE) {
+                const double sg = (base & g.xg) ? -1.0 : 1.0;
+                Zr = sg * Mr;
+                Zi = sg * Mi;
+            } else if (p == ZS_NONE) {
+                Zr = Mr;
+                Zi = Mi;
+            }
+            const double Er = 0.5 * (Mr + Zr), Ei = 0.5 * (Mi + Zi), Or = 0.5 * (Mr - Zr), Oi = 0.5 * (Mi - Zi);
+            re = g.m[0] * Er - g.m[1] * Ei + g.m[2] * Or - g.m[3] * Oi;
+            im = g.m[0] * Ei + g.m[1] * Er + g.m[2] * Oi + g.m[3] * Or;
         }
-        atomicAdd(out + 2 * (size_t)P.g[tid].slot, re);
-        atomicAdd(out + 2 * (size_t)P.g[tid].slot + 1, im);
+        atomicAdd(out + 2 * (size_t)g.slot, re);
+        atomicAdd(out + 2 * (size_t)g.slot + 1, im);
     }
 }
 
@@ -263,7 +410,9 @@ bool tile_gen_kind(const LoweredGate &g, int n, int &kind) {
 template <typename T, int TB>
 void launch_gens_t(State &sv, const void *bra, const void *ket, double *out, const GenProgram &P) {
     constexpr int NT = 1 << (TB - GT_JB);
-    const size_t smem = ((size_t)1 << TB) * sizeof(typename VecOf<T, 1>::type) + (size_t)GT_MAX * (NT / 32) * 2 * sizeof(double);
+    constexpr int NW = NT / 32;
+    const size_t smem = ((size_t)1 << TB) * sizeof(typename VecOf<T, 1>::type) +
+                        ((size_t)GT_MAX * NW * 2 + (size_t)NW * 32 * RED_PAD + (size_t)NW * (1 + 5 + GT_JB) * 2) * sizeof(double);
     const unsigned grid = (unsigned)(1ull << (sv.n - TB));
     static bool configured[64] = {false};  // per device: function attributes belong to the device's context
     auto kern = k_bra_gens_ket<T, TB>;
@@ -325,8 +474,12 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
                 rest.push_back(it);
             }
         }
-        // off-diagonal generators first: they need bra, whose registers the diagonal part then reuses
-        std::stable_sort(take.begin(), take.end(), [](const GenItem &a, const GenItem &b) { return (a.d.kind != 0) > (b.d.kind != 0); });
+        // Z sums: diagonal generators without controls whose parity mask has at most one bit
+        for (GenItem &it : take)
+            if (it.d.kind == 0 && it.d.ctrl == 0 && __builtin_popcountll(it.d.zmask) <= 1) it.d.kind = 3;
+        // off-diagonal generators first (they need bra, whose registers the diagonal part then reuses), Z sums last
+        auto rank_of = [](const GenItem &a) { return a.d.kind == 3 ? 2 : (a.d.kind == 0 ? 1 : 0); };
+        std::stable_sort(take.begin(), take.end(), [&](const GenItem &a, const GenItem &b) { return rank_of(a) < rank_of(b); });
         std::vector<int> hi;
         for (int b = L; b < n; ++b)
             if (need >> b & 1) hi.push_back(b);
@@ -349,7 +502,17 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
         for (GenItem &it : take) {
             GenDesc &d = P.g[P.n_gens++];
             d = it.d;
-            if (d.kind != 0) P.n_first = P.n_gens;
+            if (d.kind == 1 || d.kind == 2) P.n_first = P.n_gens;
+            if (d.kind != 3) P.n_diag = P.n_gens;
+            if (d.kind == 3) {
+                d.xg = d.zmask;
+                d.tbit = d.zmask == 0 ? ZS_NONE : ZS_OUTSIDE;
+                for (int b = 0; b < n; ++b)
+                    if ((d.zmask >> b & 1) && pos[b] >= 0) d.tbit = (unsigned)pos[b];
+                d.zmask = 0;
+                d.jinfo = 0;
+                continue;
+            }
             if (d.kind == 1) {
                 d.tbit = (unsigned)pos[it.tgt];
             } else if (d.kind == 2) {

@@ -210,9 +210,7 @@ int qsv_h2d(qsv_state *sv, const void *host, size_t n_amps) {
     need(sv, "state");
     need(host, "host buffer");
     QSV_CHECK(n_amps <= sv->length(), "host buffer larger than the state vector");
-    sv->use();
-    QSV_CUDA(cudaMemcpyAsync(sv->data, host, n_amps * sv->amp_bytes(), cudaMemcpyHostToDevice, sv->stream));
-    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    copy_state_host(*sv, sv->data, const_cast<void *>(host), n_amps * sv->amp_bytes(), true);
     QSV_API_END
 }
 
@@ -221,9 +219,7 @@ int qsv_d2h(qsv_state *sv, void *host, size_t n_amps) {
     need(sv, "state");
     need(host, "host buffer");
     QSV_CHECK(n_amps <= sv->length(), "host buffer larger than the state vector");
-    sv->use();
-    QSV_CUDA(cudaMemcpyAsync(host, sv->data, n_amps * sv->amp_bytes(), cudaMemcpyDeviceToHost, sv->stream));
-    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    copy_state_host(*sv, sv->data, host, n_amps * sv->amp_bytes(), false);
     QSV_API_END
 }
 

@@ -1922,8 +1922,7 @@ int qsv_dist_h2d(qsv_state *sv, const void *host, size_t n_amps) {
     sv->use();
     DistCtx &d = *sv->dist;
     for (int b = 0; b < d.n_total; ++b) d.phys_of[b] = d.log_of[b] = b;
-    QSV_CUDA(cudaMemcpyAsync(sv->data, host, n_amps * sv->amp_bytes(), cudaMemcpyHostToDevice, sv->stream));
-    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    copy_state_host(*sv, sv->data, const_cast<void *>(host), n_amps * sv->amp_bytes(), true);
     QSV_API_END
 }
 
@@ -1939,9 +1938,7 @@ int qsv_dist_d2h(qsv_state *sv, void *host, size_t n_amps) {
         QSV_CHECK(sv->dist->lazy_map, "internal: non-canonical layout outside lazy-map mode");
         dist_canonicalize(*sv, 0);
     }
-    sv->use();
-    QSV_CUDA(cudaMemcpyAsync(host, sv->data, n_amps * sv->amp_bytes(), cudaMemcpyDeviceToHost, sv->stream));
-    QSV_CUDA(cudaStreamSynchronize(sv->stream));
+    copy_state_host(*sv, sv->data, host, n_amps * sv->amp_bytes(), false);
     QSV_API_END
 }
 

@@ -151,6 +151,9 @@ struct Obs {
     mutable int dev_cache_device = -1;
 };
 
+// Whole-state host <-> device copy (state_io.cu): pageable host memory goes through multi-threaded pinned staging
+void copy_state_host(State &sv, void *dev, void *host, size_t bytes, bool to_device);
+
 // Per-device cache of released workspace blocks (state.cu): state-sized temporaries without cudaMalloc / cudaFree per call.
 void *ws_acquire(int device, size_t bytes, cudaStream_t stream);
 void ws_release(int device, void *p, size_t bytes, cudaStream_t stream);

@@ -358,7 +358,12 @@ class LightningGPU(_Base):
     def generate_samples(self) -> np.ndarray:
         if self._seed is None:
             return self._gpu_state.GenerateSamples(self.num_wires, int(self.shots)).astype(int)
-        return self._gpu_state.GenerateSamples(self.num_wires, int(self.shots), int(self._seed)).astype(int)
+        # one stream of sub-seeds per device, seeded once: every call (every observable, every execution) draws fresh
+        # uniforms, and the whole sequence is reproducible for a given `seed`
+        if getattr(self, "_seed_stream", None) is None:
+            self._seed_stream = np.random.default_rng(int(self._seed))
+        sub_seed = int(self._seed_stream.integers(0, 2**63 - 1))
+        return self._gpu_state.GenerateSamples(self.num_wires, int(self.shots), sub_seed).astype(int)
 
     def sample(self, observable: Obs, shot_range=None, bin_size=None, counts: bool = False):
         """Eigenvalue samples of an observable (lightning_gpu.py:812-818): the state is rotated into the observable's
@@ -435,6 +440,12 @@ class LightningGPU(_Base):
         names, params, wires, invs, mats = self._serialize_ops(operations)
         n_par = sum(1 for p in params if len(p))
         tp = list(range(n_par)) if trainable_params is None else sorted(trainable_params)
+        # the reverse sweep walks the parameters in ascending order; columns are handed back in the caller's order
+        order = None
+        if trainable_params is not None and list(trainable_params) != tp:
+            if len(set(tp)) != len(tp):
+                raise ValueError("trainable_params must not contain duplicates")
+            order = [tp.index(int(t)) for t in trainable_params]
         if not tp:
             return np.zeros((len(observables), 0), dtype=self.R_DTYPE)
         adj = getattr(_ops, ("AdjointJacobianGPUMPI_C" if self._mpi else "AdjointJacobianGPU_C") + self._bits)()
@@ -444,14 +455,19 @@ class LightningGPU(_Base):
             fn = adj.adjoint_jacobian_serial if self._batch_obs else adj.adjoint_jacobian
         else:
             fn = adj.adjoint_jacobian_batched if self._batch_obs else adj.adjoint_jacobian
-        return np.asarray(fn(self._gpu_state, obs, rec, tp))
+        jac = np.asarray(fn(self._gpu_state, obs, rec, tp))
+        return jac if order is None else jac[:, order]
 
     @staticmethod
     def _check_adjdiff_supported_operations(operations):
-        """lightning_gpu.py:622-636: operations with more than one parameter other than Rot cannot be differentiated."""
+        """lightning_gpu.py:622-636: operations with more than one parameter other than Rot cannot be differentiated;
+        an inverse Rot is not expanded by the serializer, so it is rejected here instead of in the C++ layer."""
         for op in operations:
             if len(getattr(op, "parameters", ())) > 1 and op.name != "Rot" and op.name not in _STATE_PREPS:
                 raise ValueError(f'The {op.name} operation is not supported using the "adjoint" differentiation method')
+            if op.name == "Rot" and getattr(op, "inverse", False):
+                raise ValueError('The inverse of Rot is not supported using the "adjoint" differentiation method; '
+                                 "write it as RZ(-omega) RY(-theta) RZ(-phi)")
 
     def vjp(self, operations, observables, dy, trainable_params=None, **kw) -> np.ndarray:
         """Vector-Jacobian product dy^T J (lightning_gpu.py:771-810).  As in the reference the observables are combined
@@ -459,11 +475,14 @@ class LightningGPU(_Base):
         if np.iscomplexobj(dy):
             raise ValueError("The vjp method only works with a real-valued dy when the tape is returning an expectation value")
         dy = np.asarray(dy, dtype=self.R_DTYPE).reshape(-1)
-        if np.allclose(dy, 0):
-            n = len(trainable_params) if trainable_params is not None else 0
-            return np.zeros(n, dtype=self.R_DTYPE)
         if len(dy) != len(observables):
             raise ValueError("Number of observables in the tape must be the same as the length of dy in the vjp method")
+        if np.allclose(dy, 0):
+            if trainable_params is not None:
+                n = len(trainable_params)
+            else:  # all parameters of the tape, counted the way the serializer does (Rot = 3)
+                n = sum(1 for p in self._serialize_ops(list(operations))[1] if len(p))
+            return np.zeros(n, dtype=self.R_DTYPE)
         coeffs, terms = [], []
         for w, o in zip(dy, observables):
             if o.name == "Hamiltonian":
