@@ -301,6 +301,139 @@ double observable_expval(State &sv, const Obs &o) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Layered reverse sweep of the adjoint method (shared by the single-GPU path below and the sharded register, dist.cu)
+// ------------------------------------------------------------------------------------------------
+// Gates on disjoint wires commute, and so do their generators.  An op is READY when every later op that shares a wire
+// with it has already been undone; all ready ops are pairwise disjoint, so the generator inner products of the
+// trainable ones can all be taken against the current (bra, lambda) -- one batched launch per observable -- and their
+// U^dagger, followed by every non-trainable op that becomes ready behind them (e.g. a whole CNOT ladder), go into one
+// fused multi-gate sweep over lambda and all bras.  Reference: one op at a time, algorithms/AdjointDiffGPU.hpp:562-592.
+void layered_reverse_sweep(const Ops &ops, const std::vector<int64_t> &trainable, std::vector<double> &factor,
+                           std::vector<double> &extra, const ReverseSweepHooks &hk) {
+    const size_t n_tp = trainable.size(), n_obs = hk.n_obs;
+    const int64_t n_ops = (int64_t)ops.ops.size();
+    std::vector<int64_t> tp_of(n_ops, -1);
+    int64_t first_needed = n_ops;
+    {
+        int64_t cur = 0;
+        size_t t = 0;
+        for (int64_t idx = 0; idx < n_ops; ++idx) {
+            if (ops.ops[idx].params.empty()) continue;
+            while (t < n_tp && trainable[t] < cur) ++t;
+            if (t < n_tp && trainable[t] == cur) {
+                tp_of[idx] = (int64_t)t;
+                first_needed = std::min(first_needed, idx);
+            }
+            ++cur;
+        }
+    }
+    auto skipped = [&](const Op &op) {
+        return op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState";
+    };
+    // per wire: the ops that touch it, in program order; an op is ready when it is the last pending op on every one
+    // of its wires
+    std::vector<std::vector<int64_t>> on_wire(hk.n_wires);
+    for (int64_t idx = first_needed; idx < n_ops; ++idx) {
+        if (skipped(ops.ops[idx])) continue;
+        for (int w : ops.ops[idx].wires) {
+            QSV_CHECK(w >= 0 && w < hk.n_wires, "wire out of range");
+            on_wire[w].push_back(idx);
+        }
+    }
+    std::vector<char> done(n_ops, 0);
+    auto is_ready = [&](int64_t idx) {
+        for (int w : ops.ops[idx].wires)
+            if (on_wire[w].empty() || on_wire[w].back() != idx) return false;
+        return true;
+    };
+    auto retire = [&](int64_t idx) {
+        done[idx] = 1;
+        for (int w : ops.ops[idx].wires) on_wire[w].pop_back();
+    };
+    size_t pending = 0;
+    for (int64_t idx = first_needed; idx < n_ops; ++idx) pending += skipped(ops.ops[idx]) ? 0 : 1;
+    const char *defer_env = std::getenv("QSV_ADJOINT_DEFER");
+    const bool defer_diag = !(defer_env && std::atoi(defer_env) == 0);
+    std::vector<LoweredGate> deferred_gens;  // diagonal generators waiting for the next layer's launch
+    std::vector<int> deferred_slot0;
+    while (pending) {
+        std::vector<int64_t> ready;
+        for (int w = 0; w < hk.n_wires; ++w)
+            if (!on_wire[w].empty() && is_ready(on_wire[w].back()) &&
+                std::find(ready.begin(), ready.end(), on_wire[w].back()) == ready.end())
+                ready.push_back(on_wire[w].back());
+        QSV_CHECK(!ready.empty(), "internal: adjoint scheduling made no progress");
+        std::sort(ready.begin(), ready.end(), std::greater<int64_t>());
+        // undo the ready ops and everything non-trainable that becomes ready behind them, in one fused batch
+        // (collected first: which generators may wait depends on what the batch touches)
+        std::vector<LoweredGate> batch;
+        std::vector<int64_t> grown;
+        auto take = [&](int64_t idx) {
+            if (ops.ops[idx].name != "Identity") batch.push_back(hk.dagger(ops.ops[idx]));
+            retire(idx);
+            --pending;
+        };
+        for (int64_t idx : ready) take(idx);
+        bool grew = true;
+        while (grew && pending) {
+            grew = false;
+            for (int w = 0; w < hk.n_wires; ++w) {
+                if (on_wire[w].empty()) continue;
+                const int64_t idx = on_wire[w].back();
+                if (tp_of[idx] >= 0 || !is_ready(idx)) continue;
+                take(idx);
+                grown.push_back(idx);
+                grew = true;
+            }
+        }
+        uint64_t grown_wires = 0;
+        for (int64_t idx : grown)
+            for (int w : ops.ops[idx].wires) grown_wires |= 1ull << w;
+        // generator inner products of the trainable ready ops, all against the current vectors.  A diagonal generator
+        // of a diagonal gate (RZ, PhaseShift, CRZ, IsingZZ, MultiRZ ...) commutes with its own gate and with the other
+        // gates of this batch (disjoint wires) unless a gate that became ready behind it shares a wire: it may then be
+        // evaluated AFTER the batch just as well, i.e. together with the generators of the next layer -- one read of
+        // (bra, lambda) fewer per layer of such gates.
+        std::vector<LoweredGate> gens;
+        std::vector<int> gen_slot0;
+        gens.swap(deferred_gens);
+        gen_slot0.swap(deferred_slot0);
+        for (int64_t idx : ready) {
+            const int64_t tp = tp_of[idx];
+            if (tp < 0) continue;
+            const Op &op = ops.ops[idx];
+            LoweredGenerator g = hk.generator(op);
+            factor[tp] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
+            extra[tp] = g.extra_identity;
+            uint64_t op_wires = 0;
+            for (int w : op.wires) op_wires |= 1ull << w;
+            const bool gen_diag = g.op.kind == LoweredGate::DIAG || g.op.kind == LoweredGate::PARITY;
+            bool gate_diag = false;
+            if (defer_diag && gen_diag && g.extra_identity == 0.0 && (op_wires & grown_wires) == 0) {
+                const LoweredGate lg = hk.dagger(op);
+                gate_diag = lg.kind == LoweredGate::DIAG || lg.kind == LoweredGate::PARITY;
+            }
+            if (gate_diag) {
+                deferred_gens.push_back(std::move(g.op));
+                deferred_slot0.push_back((int)(tp * n_obs * 2));
+                continue;
+            }
+            gens.push_back(std::move(g.op));
+            gen_slot0.push_back((int)(tp * n_obs * 2));
+            if (g.extra_identity != 0.0) hk.identity_inner_product(tp);
+        }
+        if (!gens.empty()) hk.inner_products(gens, gen_slot0);
+        if (!batch.empty()) hk.apply(batch);
+        // is any trainable op left?  if not, the remaining daggers are not needed
+        bool trainable_left = false;
+        for (int64_t idx = first_needed; idx < n_ops && !trainable_left; ++idx)
+            trainable_left = !done[idx] && tp_of[idx] >= 0;
+        if (!trainable_left) break;
+    }
+    if (!deferred_gens.empty()) hk.inner_products(deferred_gens, deferred_slot0);  // against the vectors after the last batch
+}
+
+// ------------------------------------------------------------------------------------------------
 // Adjoint Jacobian
 // ------------------------------------------------------------------------------------------------
 void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> &obs,
@@ -356,144 +489,28 @@ void adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Obs *> 
     for (const auto &op : ops.ops) n_par_ops += op.params.empty() ? 0 : 1;
     const char *batch_env = std::getenv("QSV_ADJOINT_BATCH");
     if (!(batch_env && std::atoi(batch_env) == 0)) {
-        // ---- layered reverse sweep ---------------------------------------------------------------
-        // Gates on disjoint wires commute, and so do their generators.  An op is READY when every later op that
-        // shares a wire with it has already been undone; all ready ops are pairwise disjoint, so the generator
-        // inner products of the trainable ones can all be taken against the current (bra, lambda) -- one batched
-        // launch per observable -- and their U^dagger, followed by every non-trainable op that becomes ready
-        // behind them (e.g. a whole CNOT ladder), go into one fused multi-gate sweep over lambda and all bras.
-        const int64_t n_ops = (int64_t)ops.ops.size();
-        std::vector<int64_t> tp_of(n_ops, -1);
-        int64_t first_needed = n_ops;
-        {
-            int64_t cur = 0;
-            size_t t = 0;
-            for (int64_t idx = 0; idx < n_ops; ++idx) {
-                if (ops.ops[idx].params.empty()) continue;
-                while (t < n_tp && trainable[t] < cur) ++t;
-                if (t < n_tp && trainable[t] == cur) {
-                    tp_of[idx] = (int64_t)t;
-                    first_needed = std::min(first_needed, idx);
-                }
-                ++cur;
-            }
-        }
-        auto skipped = [&](const Op &op) {
-            return op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState";
-        };
-        // per wire: the ops that touch it, in program order; an op is ready when it is the last pending op on
-        // every one of its wires
-        std::vector<std::vector<int64_t>> on_wire(sv.n);
-        for (int64_t idx = first_needed; idx < n_ops; ++idx) {
-            if (skipped(ops.ops[idx])) continue;
-            for (int w : ops.ops[idx].wires) {
-                QSV_CHECK(w >= 0 && w < sv.n, "wire out of range");
-                on_wire[w].push_back(idx);
-            }
-        }
-        std::vector<char> done(n_ops, 0);
-        auto is_ready = [&](int64_t idx) {
-            for (int w : ops.ops[idx].wires)
-                if (on_wire[w].empty() || on_wire[w].back() != idx) return false;
-            return true;
-        };
-        auto retire = [&](int64_t idx) {
-            done[idx] = 1;
-            for (int w : ops.ops[idx].wires) on_wire[w].pop_back();
-        };
-        size_t pending = 0;
-        for (int64_t idx = first_needed; idx < n_ops; ++idx) pending += skipped(ops.ops[idx]) ? 0 : 1;
-        const char *defer_env = std::getenv("QSV_ADJOINT_DEFER");
-        const bool defer_diag = !(defer_env && std::atoi(defer_env) == 0);
-        std::vector<LoweredGate> deferred_gens;  // diagonal generators waiting for the next layer's launch
-        std::vector<int> deferred_slot0;
-        auto launch_gens = [&](const std::vector<LoweredGate> &gens, const std::vector<int> &slot0) {
-            if (gens.empty()) return;
+        // ---- layered reverse sweep (layered_reverse_sweep below; shared with the sharded register, dist.cu) ----
+        ReverseSweepHooks hk;
+        hk.n_wires = sv.n;
+        hk.n_obs = n_obs;
+        hk.generator = [&](const Op &op) { return lower_generator(sv.n, op.name, op.wires); };
+        hk.dagger = [&](const Op &op) { return lower_op(sv, op, true); };
+        hk.inner_products = [&](const std::vector<LoweredGate> &gens, const std::vector<int> &slot0) {
             std::vector<int> slots(gens.size());
             for (size_t i = 0; i < n_obs; ++i) {
                 for (size_t k = 0; k < gens.size(); ++k) slots[k] = slot0[k] + (int)(2 * i);
                 launch_bra_gens_ket(sv, vecs[1 + i]->data, lambda.data, gens, slots, red);
             }
         };
-        while (pending) {
-            std::vector<int64_t> ready;
-            for (int w = 0; w < sv.n; ++w)
-                if (!on_wire[w].empty() && is_ready(on_wire[w].back()) &&
-                    std::find(ready.begin(), ready.end(), on_wire[w].back()) == ready.end())
-                    ready.push_back(on_wire[w].back());
-            QSV_CHECK(!ready.empty(), "internal: adjoint scheduling made no progress");
-            std::sort(ready.begin(), ready.end(), std::greater<int64_t>());
-            // undo the ready ops and everything non-trainable that becomes ready behind them, in one fused batch
-            // (collected first: which generators may wait depends on what the batch touches)
-            std::vector<LoweredGate> batch;
-            std::vector<int64_t> grown;
-            auto take = [&](int64_t idx) {
-                if (ops.ops[idx].name != "Identity") batch.push_back(lower_op(sv, ops.ops[idx], true));
-                retire(idx);
-                --pending;
-            };
-            for (int64_t idx : ready) take(idx);
-            bool grew = true;
-            while (grew && pending) {
-                grew = false;
-                for (int w = 0; w < sv.n; ++w) {
-                    if (on_wire[w].empty()) continue;
-                    const int64_t idx = on_wire[w].back();
-                    if (tp_of[idx] >= 0 || !is_ready(idx)) continue;
-                    take(idx);
-                    grown.push_back(idx);
-                    grew = true;
-                }
-            }
-            uint64_t grown_wires = 0;
-            for (int64_t idx : grown)
-                for (int w : ops.ops[idx].wires) grown_wires |= 1ull << w;
-            // generator inner products of the trainable ready ops, all against the current vectors.  A diagonal generator
-            // of a diagonal gate (RZ, PhaseShift, CRZ, IsingZZ, MultiRZ ...) commutes with its own gate and with the
-            // other gates of this batch (disjoint wires) unless a gate that became ready behind it shares a wire: it
-            // may then be evaluated AFTER the batch just as well, i.e. together with the generators of the next
-            // layer -- one read of (bra, lambda) fewer per layer of such gates.
-            std::vector<LoweredGate> gens;
-            std::vector<int> gen_slot0;
-            gens.swap(deferred_gens);
-            gen_slot0.swap(deferred_slot0);
-            for (int64_t idx : ready) {
-                const int64_t tp = tp_of[idx];
-                if (tp < 0) continue;
-                const Op &op = ops.ops[idx];
-                LoweredGenerator g = lower_generator(sv.n, op.name, op.wires);
-                factor[tp] = -2.0 * g.scale * (op.inverse ? -1.0 : 1.0);
-                extra[tp] = g.extra_identity;
-                uint64_t op_wires = 0;
-                for (int w : op.wires) op_wires |= 1ull << w;
-                const bool gen_diag = g.op.kind == LoweredGate::DIAG || g.op.kind == LoweredGate::PARITY;
-                bool gate_diag = false;
-                if (defer_diag && gen_diag && g.extra_identity == 0.0 && (op_wires & grown_wires) == 0) {
-                    const LoweredGate lg = lower_op(sv, op, true);
-                    gate_diag = lg.kind == LoweredGate::DIAG || lg.kind == LoweredGate::PARITY;
-                }
-                if (gate_diag) {
-                    deferred_gens.push_back(std::move(g.op));
-                    deferred_slot0.push_back((int)(tp * n_obs * 2));
-                    continue;
-                }
-                gens.push_back(std::move(g.op));
-                gen_slot0.push_back((int)(tp * n_obs * 2));
-                if (g.extra_identity != 0.0) {
-                    LoweredGate id;
-                    for (size_t i = 0; i < n_obs; ++i)
-                        launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
-                }
-            }
-            launch_gens(gens, gen_slot0);
-            // is any trainable op left?  if not, the remaining daggers are not needed
-            if (!batch.empty()) apply_gates_tiled(sv, batch, (void *const *)d_table.p, (int)(1 + n_obs));
-            bool trainable_left = false;
-            for (int64_t idx = first_needed; idx < n_ops && !trainable_left; ++idx)
-                trainable_left = !done[idx] && tp_of[idx] >= 0;
-            if (!trainable_left) break;
-        }
-        launch_gens(deferred_gens, deferred_slot0);  // against the vectors after the last batch
+        hk.identity_inner_product = [&](int64_t tp) {
+            LoweredGate id;
+            for (size_t i = 0; i < n_obs; ++i)
+                launch_bra_op_ket(sv, vecs[1 + i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
+        };
+        hk.apply = [&](const std::vector<LoweredGate> &batch) {
+            apply_gates_tiled(sv, batch, (void *const *)d_table.p, (int)(1 + n_obs));
+        };
+        layered_reverse_sweep(ops, trainable, factor, extra, hk);
     } else {
     int64_t tp_pos = (int64_t)n_tp - 1;
     int64_t cur = (int64_t)n_par_ops - 1;

@@ -716,19 +716,17 @@ bool ensure_shadow(State &sv) {
 
 }  // namespace
 
-void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
-    sv.use();
-    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+namespace {
+void *const *pointer_table(State &sv, const std::vector<void *> &vecs);
+}
+
+// Gates on LOGICAL bits of the whole register, applied to the register itself (vecs == nullptr) or to a set of its
+// companions (lambda and the bras of the adjoint method): exchanges scheduled over the dependency DAG, everything between
+// two exchanges through the fused tile executor (or gate by gate when fuse is false).
+void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool fuse, size_t chunk_bytes,
+                      const std::vector<void *> *vecs) {
     DistCtx &d = *sv.dist;
-    const int n_local = sv.n, n_total = d.n_total;
-    sv.stat_launches = 0;
-    sv.stat_sweeps = 0;
-    std::vector<LoweredGate> lowered;
-    lowered.reserve(ops.ops.size());
-    for (const auto &op : ops.ops) {
-        if (op.name == "Identity") continue;
-        lowered.push_back(lower_op_total(n_total, op, false));
-    }
+    const int n_local = sv.n;
     std::vector<uint64_t> dense(lowered.size(), 0), diag(lowered.size(), 0);
     for (size_t i = 0; i < lowered.size(); ++i) gate_bit_masks(lowered[i], dense[i], diag[i]);
     for (uint64_t m : dense)
@@ -740,7 +738,14 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     std::vector<LoweredGate> batch;
     auto flush = [&](FusedExchange *fx) {
         if (batch.empty()) return;
-        if (fuse) {
+        if (vecs) {
+            void *const *table = pointer_table(sv, *vecs);
+            if (fuse) {
+                apply_gates_tiled(sv, batch, table, (int)vecs->size(), nullptr);
+            } else {
+                for (const auto &g : batch) launch_gate_multi(sv, g, table, (int)vecs->size());
+            }
+        } else if (fuse) {
             apply_gates_tiled(sv, batch, nullptr, 1, fx);
         } else {
             for (const auto &g : batch) launch_gate(sv, g);
@@ -751,8 +756,8 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
     // alternates between its own buffer and the second one; `home` is restored when the call ends.
     size_t n_exchanges = 0;
     for (const DistStep &st : steps) n_exchanges += st.kind == 0 ? 1 : 0;
-    const bool try_fused = fuse && fused_swap_enabled() && n_exchanges > 0 && d.comp.empty() && !d.skip_main &&
-                           sv.data == d.main.local && ensure_shadow(sv);
+    const bool try_fused = fuse && vecs == nullptr && fused_swap_enabled() && n_exchanges > 0 && d.comp.empty() &&
+                           !d.skip_main && sv.data == d.main.local && ensure_shadow(sv);
     void *const home = sv.data;
     struct Home {  // the register's pointer is back in place whatever happens below
         State &sv;
@@ -837,6 +842,21 @@ void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
         }
     }
     QSV_CHECK(d.phys_of == plan_phys, "internal: the executed exchanges do not match the planned qubit map");
+}
+
+void dist_apply_ops(State &sv, const Ops &ops, bool fuse, size_t chunk_bytes) {
+    sv.use();
+    QSV_CHECK(sv.dist != nullptr, "state vector is not part of a distributed register");
+    const int n_total = sv.dist->n_total;
+    sv.stat_launches = 0;
+    sv.stat_sweeps = 0;
+    std::vector<LoweredGate> lowered;
+    lowered.reserve(ops.ops.size());
+    for (const auto &op : ops.ops) {
+        if (op.name == "Identity") continue;
+        lowered.push_back(lower_op_total(n_total, op, false));
+    }
+    dist_run_lowered(sv, lowered, fuse, chunk_bytes, nullptr);
 }
 
 void dist_allreduce(State &sv, double *host, int count) {
@@ -1473,10 +1493,66 @@ void dist_adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Ob
     double *red = sv.reduction_buffer(2 * n_slots);
     reduction_zero(sv, red, 2 * n_slots);
     std::vector<double> factor(n_tp, 0.0), extra(n_tp, 0.0);
+    const char *batch_env = std::getenv("QSV_ADJOINT_BATCH");
+    if (!(batch_env && std::atoi(batch_env) == 0)) {
+        // The layered reverse sweep of the single-GPU path (circuit.cu: layered_reverse_sweep) on the sharded vectors: the
+        // generators of a whole layer are evaluated by the batched tile kernel once their dense target qubits are local,
+        // and every batch of U^dagger goes through the exchange scheduler and the fused tile executor over lambda and
+        // all bras at once.  The reference undoes one gate at a time with two swaps each
+        // (algorithms/AdjointDiffGPUMPI.hpp:248-334).
+        ReverseSweepHooks hk;
+        hk.n_wires = n_total;
+        hk.n_obs = n_obs;
+        hk.generator = [&](const Op &op) { return lower_generator(n_total, op.name, op.wires); };
+        hk.dagger = [&](const Op &op) { return lower_op_total(n_total, op, true); };
+        hk.inner_products = [&](const std::vector<LoweredGate> &gens, const std::vector<int> &slot0) {
+            uint64_t need = 0;
+            for (const LoweredGate &g : gens)
+                if (g.kind == LoweredGate::DENSE) need |= touched_mask(g);
+            // the ready operations act on disjoint wires; should they need more qubits than a shard holds, go in groups
+            std::vector<size_t> todo(gens.size());
+            for (size_t k = 0; k < gens.size(); ++k) todo[k] = k;
+            while (!todo.empty()) {
+                uint64_t group_need = 0;
+                std::vector<size_t> group, rest;
+                for (size_t k : todo) {
+                    const uint64_t t = gens[k].kind == LoweredGate::DENSE ? touched_mask(gens[k]) : 0;
+                    if (__builtin_popcountll(group_need | t) <= sv.n - 1 || group.empty()) {
+                        group_need |= t;
+                        group.push_back(k);
+                    } else {
+                        rest.push_back(k);
+                    }
+                }
+                if (group_need) dist_localize(sv, group_need, chunk_bytes);
+                std::vector<LoweredGate> local;
+                std::vector<int> base_slot;
+                for (size_t k : group) {
+                    LoweredGate gl = localize_gate(remap_gate(gens[k], d.phys_of), sv.n, sv.index_hi);
+                    if (gl.kind == LoweredGate::NOP) continue;  // a projector that is zero on this rank
+                    local.push_back(std::move(gl));
+                    base_slot.push_back(slot0[k]);
+                }
+                std::vector<int> slots(local.size());
+                for (size_t i = 0; i < n_obs && !local.empty(); ++i) {
+                    for (size_t k = 0; k < local.size(); ++k) slots[k] = base_slot[k] + (int)(2 * i);
+                    launch_bra_gens_ket(sv, bras[i]->data, lambda.data, local, slots, red);
+                }
+                todo.swap(rest);
+            }
+            (void)need;
+        };
+        hk.identity_inner_product = [&](int64_t tp) {
+            LoweredGate id;
+            for (size_t i = 0; i < n_obs; ++i)
+                launch_bra_op_ket(sv, bras[i]->data, lambda.data, id, red, (int)((tp * n_obs + i) * 2 + 1));
+        };
+        hk.apply = [&](const std::vector<LoweredGate> &batch) { dist_run_lowered(sv, batch, true, chunk_bytes, &all_vecs); };
+        layered_reverse_sweep(ops, trainable, factor, extra, hk);
+    } else {
     size_t n_par_ops = 0;
     for (const auto &op : ops.ops) n_par_ops += op.params.empty() ? 0 : 1;
-    int64_t tp_pos = (int64_t)n_tp - 1;
-    int64_t cur = (int64_t)n_par_ops - 1;
+    int64_t tp_pos = (int64_t)n_tp - 1;    int64_t cur = (int64_t)n_par_ops - 1;
     for (int64_t idx = (int64_t)ops.ops.size() - 1; idx >= 0; --idx) {
         const Op &op = ops.ops[idx];
         if (op.name == "QubitStateVector" || op.name == "StatePrep" || op.name == "BasisState") continue;
@@ -1500,6 +1576,7 @@ void dist_adjoint_jacobian(State &sv, const Ops &ops, const std::vector<const Ob
             --cur;
         }
         if (op.name != "Identity") dist_apply_gate(sv, lower_op_total(n_total, op, true), all_vecs, chunk_bytes);
+    }
     }
     std::vector<double> h(2 * n_slots);
     reduction_read(sv, red, h.data(), 2 * n_slots);

@@ -7,6 +7,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -150,6 +151,23 @@ struct Obs {
     mutable std::shared_ptr<void> dev_cache;
     mutable int dev_cache_device = -1;
 };
+
+// Layered reverse sweep of the adjoint method (circuit.cu), parameterised over how generators are evaluated and gates
+// applied: single-GPU vectors (circuit.cu) or a sharded register with its companions (dist.cu).  Gates and generators
+// are in the hooks' own qubit numbering (local index bits / logical bits of the whole register).
+struct ReverseSweepHooks {
+    int n_wires = 0;
+    size_t n_obs = 0;
+    std::function<LoweredGenerator(const Op &)> generator;
+    std::function<LoweredGate(const Op &)> dagger;
+    // <bra_i| gens[k] |lambda> accumulated into complex slot slot0[k] + 2 * i for every observable i
+    std::function<void(const std::vector<LoweredGate> &gens, const std::vector<int> &slot0)> inner_products;
+    // <bra_i|lambda> into the identity slot of trainable parameter tp (slot (tp * n_obs + i) * 2 + 1)
+    std::function<void(int64_t tp)> identity_inner_product;
+    std::function<void(const std::vector<LoweredGate> &batch)> apply;  // to lambda and every bra
+};
+void layered_reverse_sweep(const Ops &ops, const std::vector<int64_t> &trainable, std::vector<double> &factor,
+                           std::vector<double> &extra, const ReverseSweepHooks &hooks);
 
 // Whole-state host <-> device copy (state_io.cu): pageable host memory goes through multi-threaded pinned staging
 void copy_state_host(State &sv, void *dev, void *host, size_t bytes, bool to_device);

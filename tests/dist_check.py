@@ -368,6 +368,50 @@ def config5_generator_at_28_qubits(rank, local_rank, world, g):
     return failures
 
 
+def config3_adjoint_sharded(rank, local_rank, world, g):
+    """BASELINE config 3 (hardware-efficient ansatz, 4 layers, 100-term Pauli Hamiltonian) at 26 qubits on the sharded
+    register: the layered reverse sweep with the batched generator kernel and fused U^dagger sweeps over lambda and the
+    bra (AdjointDiffGPUMPI.hpp:248-334 undoes one gate at a time) against the single-GPU engine on the same circuit."""
+    import time
+
+    failures = []
+    n = int(os.environ.get("DIST_CHECK_CONFIG3_N", "26"))
+    ops, n_par = workloads.hardware_efficient_ansatz(n, layers=4, seed=11)
+    words, wires, coeffs = workloads.random_pauli_hamiltonian(n, 100, seed=5)
+    ham = q.Observable.from_tuple(workloads.hamiltonian_tuple(words, wires, coeffs))
+    rec = q.Ops(ops)
+    one = q.StateVector(n, np.complex128, device=local_rank)
+    one.apply_ops(rec, fuse=True)
+    want = one.adjoint_jacobian(rec, [ham], list(range(n_par)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    want = one.adjoint_jacobian(rec, [ham], list(range(n_par)))
+    torch.cuda.synchronize()
+    t_one = time.perf_counter() - t0
+    e_one = one.expval(ham)
+    del one
+    sv = DistributedStateVector(n, np.complex128, device=local_rank)
+    sv.apply_ops(rec, fuse=True)
+    e = sv.expval(ham)
+    jac = sv.adjoint_jacobian(rec, [ham], list(range(n_par)))
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    jac = sv.adjoint_jacobian(rec, [ham], list(range(n_par)))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_sh = time.perf_counter() - t0
+    scale = max(1.0, float(np.sum(np.abs(coeffs))))  # a gradient of a sum of 100 weighted terms
+    err = float(np.max(np.abs(jac - want)))
+    if err > 1e-10 * scale or abs(e - e_one) > 1e-10 * scale:
+        failures.append(f"config-3 adjoint n={n}: Jacobian err {err:.2e}, expval err {abs(e - e_one):.2e}")
+    if rank == 0:
+        print(f"[dist_check] config-3 adjoint n={n} ({n_par} parameters, 100 terms): {world} GPUs {t_sh * 1e3:.1f} ms vs 1 GPU "
+              f"{t_one * 1e3:.1f} ms, Jacobian err={err:.2e} expval err={abs(e - e_one):.2e}", flush=True)
+    sv.close()
+    return failures
+
+
 def fused_exchange_check(rank, local_rank, world, g):
     """QSV_DIST_FUSED_SWAP=1 (off by default): exchanges through the second buffer, carried by the sweep before them where
     the exchanged bit is not one of its tile bits.  20 local qubits so that sweeps can carry them; 13 so that the
@@ -475,6 +519,8 @@ def main():
     if os.environ.get("DIST_CHECK_N28", "1") == "1":
         failures += config5_generator_at_28_qubits(rank, local_rank, world, g)
     failures += measurements_and_adjoint(rank, local_rank, world, g)
+    if os.environ.get("DIST_CHECK_CONFIG3", "1") == "1":
+        failures += config3_adjoint_sharded(rank, local_rank, world, g)
     failures += pybind_twins(rank, local_rank, world, g)
     failures += device_mirror(rank, world, g)
     ok = torch.tensor([0 if failures else 1], device="cuda")
