@@ -134,27 +134,27 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
         for (int j = 0; j < GT_EPT; ++j) b[j] = s[tid + (uint32_t)j * NT];
     }
 
-    // results of up to four generators wait in v[] for one batched cross-lane sum
-    double v[8];
-    auto flush_group = [&](int k0, int count) {
-        const double a = warp_reduce8(v, scratch, lane);
-        const int i = (int)(lane >> 2);
-        if ((lane & 3u) == 0u && (i >> 1) < count) s_acc[k0 + (i >> 1)][warp][i & 1] = a;
-    };
+    // the per-thread results of up to four generators wait in the warp's scratch area for one batched cross-lane sum
+    // (straight to shared memory: holding them in registers costs 16 registers this kernel does not have)
     auto put = [&](int q, double re, double im) {
+        scratch[lane * RED_PAD + 2 * q] = re;
+        scratch[lane * RED_PAD + 2 * q + 1] = im;
+    };
+    auto flush_group = [&](int k0, int count) {
+        __syncwarp();
+        const uint32_t i = lane >> 2, part = lane & 3u;
+        double a = 0.0;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq)
-            if (q == qq) {
-                v[2 * qq] = re;
-                v[2 * qq + 1] = im;
-            }
+        for (int t = 0; t < 8; ++t) a += scratch[(8u * part + t) * RED_PAD + i];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (part == 0u && (int)(i >> 1) < count) s_acc[k0 + (i >> 1)][warp][i & 1u] = a;
+        __syncwarp();
     };
 
     // ---- generators with off-diagonal parts: Pauli words and 2x2 blocks --------------------------------------
     for (int k0 = 0; k0 < P.n_first; k0 += 4) {
         const int count = min(4, P.n_first - k0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0;
         for (int q = 0; q < count; ++q) {
             const GenDesc &g = P.g[k0 + q];
             const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;
@@ -162,15 +162,18 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
             double re = 0.0, im = 0.0;
             if (g.kind == 2) {
                 // (P ket)_i = i^ny * (-1)^{popc(i' & z)} * ket_i' with i' = i ^ x (only where the control bits are set:
-                // generators |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum
+                // generators |1><1| (x) X / Y of controlled rotations); the constant i^ny is applied after the sum.
+                // partner element = (tid ^ low part of the flip mask) + NT * (j ^ its j part): one thread-level XOR per
+                // generator, the j part is CTA-uniform arithmetic
                 const bool t_odd = ((__popcll((g0 ^ g.xg) & g.zmask) ^ (g.jinfo >> 8)) & 1u) != 0u;
+                const A *sp = s + (tid ^ (g.tbit & (uint32_t)(NT - 1)));
+                const uint32_t jx = g.tbit >> (TB - GT_JB);
                 double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};  // four independent chains of multiply-adds
                 if (t_on) {
-                    if (mj == 0u) {
+                    if ((mj | cjm) == 0u) {
 #pragma unroll
                         for (int j = 0; j < GT_EPT; ++j) {
-                            if (((unsigned)j & cjm) != cjm) continue;
-                            const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                            const A x = sp[((uint32_t)j ^ jx) * NT];
                             ar[j & 1] = fma((double)b[j].x, (double)x.x, ar[j & 1]);
                             ar[j & 1] = fma((double)b[j].y, (double)x.y, ar[j & 1]);
                             ai[j & 1] = fma((double)b[j].x, (double)x.y, ai[j & 1]);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
 #pragma unroll
                         for (int j = 0; j < GT_EPT; ++j) {
                             if (((unsigned)j & cjm) != cjm) continue;
-                            const A x = s[(tid + (uint32_t)j * NT) ^ g.tbit];
+                            const A x = sp[((uint32_t)j ^ jx) * NT];
                             const double sg = (__popc((unsigned)j & mj) & 1) ? -1.0 : 1.0;  // CTA-uniform
                             const double bx = sg * (double)b[j].x, by = sg * (double)b[j].y;
                             ar[j & 1] = fma(bx, (double)x.x, ar[j & 1]);
@@ -306,8 +309,6 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
                     }
             for (int k0 = P.n_first; k0 < P.n_diag; k0 += 4) {
                 const int count = min(4, P.n_diag - k0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.0;
                 for (int q = 0; q < count; ++q) {
                     const GenDesc &g = P.g[k0 + q];
                     const unsigned mj = g.jinfo & 15u, cjm = (g.jinfo >> 4) & 15u;

@@ -76,7 +76,8 @@ class LightningGPU(_Base):
     _CPP_BINARY_AVAILABLE = True
 
     def __init__(self, wires, *, mpi: bool = False, mpi_buf_size: int = 0, sync: bool = False,
-                 c_dtype=np.complex128, shots=None, batch_obs: Union[bool, int] = False, seed: int | None = None):
+                 c_dtype=np.complex128, shots=None, batch_obs: Union[bool, int] = False, seed: int | None = None,
+                 fuse_ops: bool = True):
         if c_dtype is np.complex64 or np.dtype(c_dtype) == np.complex64:
             self.use_csingle, self.R_DTYPE, self.C_DTYPE, bits = True, np.float32, np.complex64, "64"
         elif c_dtype is np.complex128 or np.dtype(c_dtype) == np.complex128:
@@ -94,6 +95,7 @@ class LightningGPU(_Base):
             self.shots = shots
         self._bits = bits
         self._sync = sync
+        self._fuse_ops = bool(fuse_ops)
         self._batch_obs = batch_obs
         self._seed = seed
         self._dp = _ops.DevPool()
@@ -190,20 +192,33 @@ class LightningGPU(_Base):
 
     # ---- gates ------------------------------------------------------------------------------------
     def apply_cq(self, operations):
-        """One call into the binary per operation, dispatched by name (lightning_gpu.py:519-555).  The
-        `inverse` flag is taken per operation (reference defect Q1 -- a sticky flag -- is not reproduced)."""
+        """The reference makes one call into the binary per operation, dispatched by name (lightning_gpu.py:519-555).  Here
+        the whole list goes down in ONE call -- the vector form of `apply` (the reference's own batched overload,
+        StateVectorCudaManaged.hpp:279-315, extended by per-operation matrices) -- so that consecutive gates are fused
+        into shared HBM sweeps.  `fuse_ops=False` on the device restores the per-operation calls.  The `inverse` flag is
+        taken per operation (reference defect Q1 -- a sticky flag -- is not reproduced)."""
+        names, wires, invs, params, mats = [], [], [], [], []
         for o in operations:
             name = o.name
             if name in _STATE_PREPS or name == "Identity":
                 continue
             inv = bool(getattr(o, "inverse", False))
-            wires = list(o.wires)
+            w = list(o.wires)
             method = getattr(self._gpu_state, name, None)
-            if method is not None and getattr(o, "matrix", None) is None:
-                method(wires, inv, [float(p) for p in o.parameters])
-            else:
-                mat = np.asarray(o.matrix, dtype=self.C_DTYPE).reshape(-1)
-                self._gpu_state.apply(name, wires, inv, [], mat)
+            named = method is not None and getattr(o, "matrix", None) is None
+            if not self._fuse_ops:
+                if named:
+                    method(w, inv, [float(p) for p in o.parameters])
+                else:
+                    self._gpu_state.apply(name, w, inv, [], np.asarray(o.matrix, dtype=self.C_DTYPE).reshape(-1))
+                continue
+            names.append(name)
+            wires.append(w)
+            invs.append(inv)
+            params.append([float(p) for p in o.parameters] if named else [])
+            mats.append([] if named else np.asarray(o.matrix, dtype=self.C_DTYPE).reshape(-1))
+        if names:
+            self._gpu_state.apply(names, wires, invs, params, mats)
 
     def apply(self, operations, **kwargs):
         ops = list(operations)

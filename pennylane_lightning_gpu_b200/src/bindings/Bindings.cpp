@@ -92,6 +92,11 @@ template <class PrecisionT> void register_precision(py::module_ &m) {
         .def("apply",
              py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
                                const std::vector<bool> &, const std::vector<std::vector<PrecisionT>> &>(&SV::applyOperation))
+        .def("apply",
+             py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
+                               const std::vector<bool> &, const std::vector<std::vector<PrecisionT>> &,
+                               const std::vector<std::vector<std::complex<PrecisionT>>> &>(&SV::applyOperation),
+             "Whole list of operations as one recorded circuit (fused sweeps); matrices for operations without a kernel")
         .def("apply", py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
                                         const std::vector<bool> &>(&SV::applyOperation))
         .def("apply", py::overload_cast<const std::string &, const std::vector<std::size_t> &, bool,
@@ -319,6 +324,11 @@ template <class PrecisionT> void register_precision_mpi(py::module_ &m) {
         .def("apply",
              py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
                                const std::vector<bool> &, const std::vector<std::vector<PrecisionT>> &>(&SV::applyOperation))
+        .def("apply",
+             py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
+                               const std::vector<bool> &, const std::vector<std::vector<PrecisionT>> &,
+                               const std::vector<std::vector<std::complex<PrecisionT>>> &>(&SV::applyOperation),
+             "Whole list of operations as one recorded circuit (fused sweeps); matrices for operations without a kernel")
         .def("apply", py::overload_cast<const std::vector<std::string> &, const std::vector<std::vector<std::size_t>> &,
                                         const std::vector<bool> &>(&SV::applyOperation))
         .def("apply", py::overload_cast<const std::string &, const std::vector<std::size_t> &, bool,

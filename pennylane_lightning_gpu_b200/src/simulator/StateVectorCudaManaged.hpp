@@ -115,17 +115,37 @@ template <class PrecisionT> class StateVectorCudaManaged {
                             const std::vector<ComplexT> &gate_matrix = {}) {
         applyOperation(opName, wires, adjoint, params, gate_matrix);
     }
+    // The vector overloads (Managed.hpp:279-315 in the reference: a loop over the single-gate form) hand the whole list to
+    // the fused executor as ONE recorded circuit: consecutive gates share HBM sweeps.  The five-argument form adds the
+    // matrices of operations without a named kernel, like create_ops_list (bindings/Bindings.cpp:806-840).
+    void applyOperation(const std::vector<std::string> &ops, const std::vector<std::vector<std::size_t>> &wires,
+                        const std::vector<bool> &adjoints, const std::vector<std::vector<PrecisionT>> &params,
+                        const std::vector<std::vector<ComplexT>> &matrices) {
+        PL_ABORT_IF(ops.size() != wires.size() || ops.size() != adjoints.size() || ops.size() != params.size() ||
+                        (!matrices.empty() && matrices.size() != ops.size()),
+                    "Invalid arguments: number of operations, wires, inverses and parameters must all be equal");
+        qsv_ops *rec = nullptr;
+        Util::check(qsv_ops_create(&rec));
+        int st = 0;
+        for (std::size_t i = 0; i < ops.size() && st == 0; ++i) {
+            const std::vector<int> w(wires[i].begin(), wires[i].end());
+            const std::vector<double> p(params[i].begin(), params[i].end());
+            std::vector<double> m;
+            if (!matrices.empty() && !matrices[i].empty()) m = to_doubles(matrices[i]);
+            st = qsv_ops_append(rec, ops[i].c_str(), w.data(), static_cast<int>(w.size()), p.data(), static_cast<int>(p.size()),
+                                adjoints[i], m.empty() ? nullptr : m.data(), m.empty() ? 0 : (std::size_t{1} << w.size()));
+        }
+        if (st == 0) st = qsv_apply_ops(sv_, rec, 1);
+        qsv_ops_destroy(rec);
+        Util::check(st);
+    }
     void applyOperation(const std::vector<std::string> &ops, const std::vector<std::vector<std::size_t>> &wires,
                         const std::vector<bool> &adjoints, const std::vector<std::vector<PrecisionT>> &params) {
-        PL_ABORT_IF(ops.size() != wires.size() || ops.size() != adjoints.size() || ops.size() != params.size(),
-                    "Invalid arguments: number of operations, wires, inverses and parameters must all be equal");
-        for (std::size_t i = 0; i < ops.size(); ++i) applyOperation(ops[i], wires[i], adjoints[i], params[i]);
+        applyOperation(ops, wires, adjoints, params, {});
     }
     void applyOperation(const std::vector<std::string> &ops, const std::vector<std::vector<std::size_t>> &wires,
                         const std::vector<bool> &adjoints) {
-        PL_ABORT_IF(ops.size() != wires.size() || ops.size() != adjoints.size(),
-                    "Invalid arguments: number of operations, wires and inverses must all be equal");
-        for (std::size_t i = 0; i < ops.size(); ++i) applyOperation(ops[i], wires[i], adjoints[i], {});
+        applyOperation(ops, wires, adjoints, std::vector<std::vector<PrecisionT>>(ops.size()), {});
     }
     // matrix given explicitly (the reference's applyDeviceMatrixGate / applyHostMatrixGate pair)
     void applyMatrix(const std::vector<ComplexT> &matrix, const std::vector<std::size_t> &ctrls,

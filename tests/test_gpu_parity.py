@@ -34,18 +34,18 @@ def gpu_state(q, psi, dtype):
     return sv
 
 
-def assert_close(a, b, dtype, scale=1.0, what=""):
+def assert_close(a, b, dtype, what=""):
     """north_star's tolerance (1e-10 complex128, 1e-5 complex64), relative to the size of the quantity when that exceeds
-    1 (un-normalised vectors, Hamiltonian sums).  `scale` widens the bound for complex64 ONLY (single-precision sums of
-    many terms); complex128 is never widened.  QSV_TEST_MARGINS=<file> logs every (error, bound) pair."""
+    1 (un-normalised vectors, Hamiltonian sums); nothing is widened beyond that (measured on B200, round 2: worst error
+    1.1e-15 in complex128 and 1.5e-7 in complex64 over 2414 comparisons).  QSV_TEST_MARGINS=<file> logs every pair."""
     a, b = np.asarray(a), np.asarray(b)
     ref = float(np.max(np.abs(b))) if b.size else 0.0
-    tol = TOL[np.dtype(dtype)] * max(1.0, ref) * (scale if np.dtype(dtype) == np.complex64 else 1.0)
+    tol = TOL[np.dtype(dtype)] * max(1.0, ref)
     err = float(np.max(np.abs(a - b))) if b.size else 0.0
     log = os.environ.get("QSV_TEST_MARGINS")
     if log:
         with open(log, "a") as f:
-            f.write(f"{np.dtype(dtype).name} err={err:.3e} bound={tol:.1e} strict={TOL[np.dtype(dtype)] * max(1.0, ref):.1e} {what}\n")
+            f.write(f"{np.dtype(dtype).name} err={err:.3e} bound={tol:.1e} strict={tol:.1e} {what}\n")
     assert err <= tol, f"{what}: max abs err {err:.3e} > {tol:.1e}"
 
 
@@ -222,7 +222,7 @@ def test_random_circuit_unfused_and_fused(q, dtype):
     for fuse in (False, True):
         sv = gpu_state(q, psi, dtype)
         sv.apply_ops(rec, fuse=fuse)
-        assert_close(sv.d2h(), want, dtype, scale=10, what=f"fuse={fuse}")
+        assert_close(sv.d2h(), want, dtype, what=f"fuse={fuse}")
         launches, sweeps = sv.last_apply_stats()
         assert launches >= 1 and sweeps >= 1
         if not fuse:
@@ -286,7 +286,7 @@ def test_expvals_vs_oracle(q, n, dtype):
         wires = _rand_wires(rng, n, k)
         a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
         got = sv.expval_matrix(a, wires)  # deliberately non-Hermitian: the reference returns a complex
-        assert_close(got, orc.expval_matrix(psi, a, wires), dtype, scale=1 << k, what=f"dense k={k}")
+        assert_close(got, orc.expval_matrix(psi, a, wires), dtype, what=f"dense k={k}")
     words, wires, coeffs = [], [], []
     for _ in range(12):
         k = int(rng.integers(1, min(n, 5) + 1))
@@ -301,7 +301,7 @@ def test_expvals_vs_oracle(q, n, dtype):
     coeffs.append(-1.5)
     tot, terms = sv.expval_pauli_words(words, wires, coeffs, return_terms=True)
     state_cast = psi.astype(dtype)
-    assert_close(tot, orc.expval_pauli_words(state_cast, words, wires, coeffs), dtype, scale=20)
+    assert_close(tot, orc.expval_pauli_words(state_cast, words, wires, coeffs), dtype)
     for t, (w, ws) in enumerate(zip(words, wires)):
         want = np.vdot(psi, orc.pauli_word_matrix_free(psi, w, ws)).real
         assert_close(terms[t], want, dtype, what=f"word {w}{ws}")
@@ -334,11 +334,11 @@ def test_csr_expval_and_apply(q, per_row, dtype):
     psi = random_state(n, 4)
     sv = gpu_state(q, psi, dtype)
     want = orc.expval_csr(psi, m.indptr, m.indices, m.data)
-    assert_close(sv.expval_csr(m.indptr, m.indices, m.data), want, dtype, scale=100)
+    assert_close(sv.expval_csr(m.indptr, m.indices, m.data), want, dtype)
     obs = q.Observable.sparse(m.indptr, m.indices, m.data)
-    assert_close(sv.expval(obs), want, dtype, scale=100)
+    assert_close(sv.expval(obs), want, dtype)
     sv.apply_observable(obs)
-    assert_close(sv.d2h(), m @ psi, dtype, scale=100)
+    assert_close(sv.d2h(), m @ psi, dtype)
     # empty rows
     import scipy.sparse as sp
 
@@ -356,7 +356,7 @@ def test_probs(q, kats, dtype):
     for wires in ([0], [n - 1], [3, 7], [0, 1, 2], [2, 5, 11, 12], list(range(n)), list(range(1, n)),
                   [12, 0, 6], list(range(12))):
         got = sv.probs(wires)
-        assert_close(got, orc.probs_custatevec_order(psi.astype(dtype), wires), dtype, scale=tol_scale,
+        assert_close(got, orc.probs_custatevec_order(psi.astype(dtype), wires), dtype,
                      what=f"probs{wires}")
         assert abs(got.sum() - 1.0) < 1e-5
     k = kats["probs"]
@@ -422,10 +422,10 @@ def test_observables_apply_and_expval(q, dtype):
     for o in _obs_zoo(rng, n):
         obs = q.Observable.from_tuple(o)
         sv = gpu_state(q, psi, dtype)
-        assert_close(sv.expval(obs), orc.expval_obs(psi, o), dtype, scale=20, what=f"expval {o[0]}")
+        assert_close(sv.expval(obs), orc.expval_obs(psi, o), dtype, what=f"expval {o[0]}")
         assert_close(sv.d2h(), psi, dtype, what="expval must not modify the state")
         sv.apply_observable(obs)
-        assert_close(sv.d2h(), orc.apply_observable(psi, o), dtype, scale=20, what=f"apply {o[0]}")
+        assert_close(sv.d2h(), orc.apply_observable(psi, o), dtype, what=f"apply {o[0]}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -487,11 +487,11 @@ def test_adjoint_all_parametric_gates_vs_oracle(q, dtype):
         want = orc.adjoint_jacobian(final, ops, obs, trainable)
         sv = gpu_state(q, final, dtype)
         jac = sv.adjoint_jacobian(rec, gobs, trainable)
-        assert_close(jac, want, dtype, scale=50, what=f"trainable={trainable}")
+        assert_close(jac, want, dtype, what=f"trainable={trainable}")
         # apply_operations = True starts from the initial state
         sv0 = gpu_state(q, psi0, dtype)
         jac0 = sv0.adjoint_jacobian(rec, gobs, trainable, apply_operations=True)
-        assert_close(jac0, want, dtype, scale=50)
+        assert_close(jac0, want, dtype)
         assert_close(sv0.d2h(), psi0, dtype, what="adjoint must not modify the input state")
     sv = gpu_state(q, final, dtype)
     with pytest.raises(q.QsvError, match="No trainable parameters provided"):
@@ -637,7 +637,7 @@ def test_register_tile_kernel_stress(q, n, low, rb, dtype, monkeypatch):
     want = orc.apply_ops(psi, ops)
     sv = gpu_state(q, psi, dtype)
     sv.apply_ops(q.Ops(ops), fuse=True)
-    assert_close(sv.d2h(), want, dtype, scale=20, what=f"n={n} low={low}")
+    assert_close(sv.d2h(), want, dtype, what=f"n={n} low={low}")
     launches, _ = sv.last_apply_stats()
     assert launches < len(ops)
 
@@ -669,7 +669,7 @@ def test_register_tile_feature_switches(q, env, dtype, monkeypatch):
     want = orc.apply_ops(psi, ops)
     sv = gpu_state(q, psi, dtype)
     sv.apply_ops(q.Ops(ops), fuse=True)
-    assert_close(sv.d2h(), want, dtype, scale=20, what=f"env={env}")
+    assert_close(sv.d2h(), want, dtype, what=f"env={env}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -705,7 +705,7 @@ def test_gate_kernel_launch_shapes(q, env, dtype, monkeypatch):
     want = orc.apply_ops(psi, ops)
     sv = gpu_state(q, psi, dtype)
     sv.apply_ops(q.Ops(ops), fuse=False)
-    assert_close(sv.d2h(), want, dtype, scale=10, what=f"env={env}")
+    assert_close(sv.d2h(), want, dtype, what=f"env={env}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -729,7 +729,7 @@ def test_fused_pauli_word_expvals(q, n, dtype):
     for t, (w, ws) in enumerate(zip(words, wires)):
         want = np.vdot(psi, orc.pauli_word_matrix_free(psi, w, ws)).real
         assert_close(terms[t], want, dtype, what=f"word {w}{ws}")
-    assert_close(tot, orc.expval_pauli_words(psi.astype(dtype), words, wires, coeffs), dtype, scale=80)
+    assert_close(tot, orc.expval_pauli_words(psi.astype(dtype), words, wires, coeffs), dtype)
     ham = ("Hamiltonian", coeffs, [("TensorProd", [("Named", {"X": "PauliX", "Y": "PauliY", "Z": "PauliZ", "I": "Identity"}[c], [w])
                                                    for c, w in zip(word, ws)]) for word, ws in zip(words, wires)])
-    assert_close(sv.expval(q.Observable.from_tuple(ham)), orc.expval_pauli_words(psi, words, wires, coeffs), dtype, scale=80)
+    assert_close(sv.expval(q.Observable.from_tuple(ham)), orc.expval_pauli_words(psi, words, wires, coeffs), dtype)
