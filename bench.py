@@ -185,6 +185,8 @@ def run_ours(args):
     distributed = world > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    clk_all = ClockSampler(local_rank)  # the whole process, beside the sampler of the timed region below
+    clk_all.__enter__()
     if distributed:
         import torch.distributed as dist
 
@@ -296,9 +298,15 @@ def run_ours(args):
                 "kernel": fused_kernel if fused else "k_apply_dense / k_apply_diag (one sweep per gate)",
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "gates_per_launch": len(ops) * args.steps / max(launches, 1)}
+    roofline["frac_note"] = ("`frac` follows SURVEY.md 8d literally (algorithmic bytes of every gate a launch applies, no credit for "
+                             "fusion), so for fused sweeps it is a speed-up over one-sweep-per-gate, NOT a fraction of a roof; "
+                             "`frac_physical` = DRAM bytes actually moved per launch / time / measured HBM peak and "
+                             "`frac_compute` = executed FP multiply-adds / time / FP pipe peak are the roofline fractions")
+    roofline["frac_physical"] = roofline["frac"]
     if fused:
         roofline["hbm_actual_gbs"] = sweep_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
+        roofline["frac_physical"] = roofline["hbm_actual_frac"]
         roofline["note"] = (f"a fused sweep applies ~{len(ops) * args.steps / max(launches, 1):.0f} gates per read+write of the "
                             "state, so it is bound by FP64 issue (64 DFMA/clk/SM) and instruction overhead rather than by HBM: "
                             "see DESIGN.md 4.2; detail.unfused_gate_by_gate and detail.single_gate_sweeps are the HBM-bound "
@@ -361,9 +369,11 @@ def run_ours(args):
             roofline["ms_per_launch"] = kernel_ms / launches
             roofline["achieved"] = bytes_per_launch / (roofline["ms_per_launch"] * 1e-3) / 1e9
             roofline["frac"] = roofline["achieved"] / hbm_peak
+            roofline["frac_physical"] = roofline["frac"]
             if fused:
                 roofline["hbm_actual_gbs"] = sweep_bytes / (roofline["ms_per_launch"] * 1e-3) / 1e9
                 roofline["hbm_actual_frac"] = roofline["hbm_actual_gbs"] / hbm_peak
+                roofline["frac_physical"] = roofline["hbm_actual_frac"]
             roofline["exchange_note"] = "exchange time (NCCL stream) subtracted from the region before dividing by launches"
     # ---- the same circuit gate by gate (one HBM sweep per gate) and in complex64 ----------------
     if args.sweeps and not distributed and args.fuse:
@@ -407,6 +417,7 @@ def run_ours(args):
         detail["config1_sel20"] = config1_sel20(torch, q, args)
     if args.config4 and not distributed:
         detail["sparse_config4"] = sparse_config4(torch, q, args)
+        detail["state_io"] = state_io(torch, q)
     if args.adjoint and not distributed:
         sv = q.StateVector(n_local, cdtype, device=local_rank, external_ptr=buf.data_ptr())
 
@@ -433,10 +444,14 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "hbm_sweeps": sweeps, "clocks": clk.summary(), "detail": detail,
         }
+        clk_all.__exit__()
+        line["clocks"]["region"] = "the timed steps of `value`"
+        line["clocks"]["whole_process"] = clk_all.summary()
         comp = roofline.get("compute")
         if comp and "tflops" in comp and (line["clocks"] or {}).get("sm_mhz"):
             comp["peak_tflops"] = comp.pop("peak_tflops_per_ghz") * line["clocks"]["sm_mhz"] / 1e3
             comp["frac"] = comp["tflops"] / comp["peak_tflops"]
+            roofline["frac_compute"] = comp["frac"]
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
@@ -672,21 +687,54 @@ def sparse_config4(torch, q, args):
     # the same matrix as a SparseHamiltonian observable: its CSR arrays stay device-resident after the first use
     e_obs = sv.expval(obs)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e_obs = sv.expval(obs)
-    torch.cuda.synchronize()
-    t_obs = time.perf_counter() - t0
+    t_obs = None
+    for _ in range(5):
+        t0 = time.perf_counter()
+        e_obs = sv.expval(obs)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_obs = dt if t_obs is None else min(t_obs, dt)
     t0 = time.perf_counter()
     e_pw = sv.expval_pauli_words(words, wires, coeffs)
     torch.cuda.synchronize()
     t_pw = time.perf_counter() - t0
     B, I, N = 16, 8, 1 << n
     alg = m.nnz * (B + I) + (N + 1) * I + 2 * B * N
-    return {"n_qubits": n, "nnz": int(m.nnz), "csr_gb": m.nnz * 24 / 1e9, "host_build_s": build_s,
+    hbm_peak, _ = measured_peaks()
+    return {"n_qubits": n, "nnz": int(m.nnz), "nnz_per_row": m.nnz / N, "csr_gb": m.nnz * 24 / 1e9, "host_build_s": build_s,
             "expval_csr": e_csr, "expval_pauli_words": e_pw, "abs_diff": abs(e_csr - e_pw),
             "csr_call_s_including_h2d": t_csr, "csr_observable_call_s_device_resident": t_obs,
-            "csr_observable_gbs": alg / t_obs / 1e9, "expval_csr_observable": e_obs,
-            "pauli_words_call_s": t_pw, "algorithmic_gb": alg / 1e9}
+            "csr_observable_gbs": alg / t_obs / 1e9, "csr_observable_frac_of_hbm_peak": alg / t_obs / 1e9 / hbm_peak,
+            "expval_csr_observable": e_obs, "pauli_words_call_s": t_pw, "algorithmic_gb": alg / 1e9,
+            "bytes_rule": "nnz * (16 + 8) + (N + 1) * 8 + 2 * 16 * N (SURVEY.md 8d), CSR arrays device-resident, wall time of "
+                          "the call incl. the read-back of the result"}
+
+
+def state_io(torch, q, n=28):
+    """Whole-state host <-> device copies (lightning_gpu.py:345-381 syncH2D / syncD2H): pageable NumPy memory through the
+    multi-threaded pinned staging of csrc/state_io.cu, and pinned memory straight over PCIe."""
+    sv = q.StateVector(n, np.complex128)
+    host = np.empty(1 << n, dtype=np.complex128)
+    host.view(np.float64)[:] = 0.0
+    pinned = torch.empty(1 << n, dtype=torch.complex128).pin_memory().numpy()
+    gb = host.nbytes / 1e9
+
+    def best(fn):
+        fn()
+        out = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out = dt if out is None else min(out, dt)
+        return gb / out
+
+    return {"n_qubits": n, "gb": gb, "host_threads": min(16, max(1, (os.cpu_count() or 2) // 2)),
+            "pageable_h2d_gbs": best(lambda: sv.h2d(host)), "pageable_d2h_gbs": best(lambda: sv.d2h(host)),
+            "pinned_h2d_gbs": best(lambda: sv.h2d(pinned)), "pinned_d2h_gbs": best(lambda: sv.d2h(pinned)),
+            "plain_cudaMemcpy_of_pageable_gbs": "10.5 H2D / 18.3 D2H on this host (profiles/r2_state_io.txt)"}
 
 
 def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, args, dist=None):
@@ -717,11 +765,27 @@ def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, 
         if dist is not None:
             dist.barrier()
 
-    def step():
-        sv.h2d(host_np)                      # HostToDevice of the prepared state (lightning_gpu.py:392-447)
-        rec = q.Ops(ops)                     # host op list -> recorded circuit
-        sv.apply_ops(rec, fuse=bool(args.fuse))
-        return sv.expval(z0)                 # one double back to the host
+    api = "ctypes DistributedStateVector (every rank uploads its own shard)"
+    if dist is None:
+        # the plugin surface: the device class with the reference's call pattern (lightning_gpu.py:392-447 StatePrep ->
+        # syncH2D -> HostToDevice; apply; expval) on top of the pybind11 module, which calls the C ABI
+        from pennylane_lightning_gpu_b200.lightning_gpu import LightningGPU, Obs, Op
+
+        device = LightningGPU(n, c_dtype=cdtype)
+        z0_obs = Obs("PauliZ", [0])
+        api = "LightningGPU device (pennylane_lightning_gpu_b200/lightning_gpu.py) -> lightning_gpu_qubit_ops (pybind11) -> C ABI"
+
+        def step():
+            recs = [Op("StatePrep", list(range(n)), [host_np])]
+            recs += [Op(op["name"], op["wires"], op.get("params", ()), False, op.get("matrix")) for op in ops]
+            device.apply(recs)               # StatePrep = HostToDevice of the 2^n amplitudes, then the circuit
+            return device.expval(z0_obs)     # one double back to the host
+    else:
+        def step():
+            sv.h2d(host_np)                  # HostToDevice of this rank's shard
+            rec = q.Ops(ops)                 # host op list -> recorded circuit
+            sv.apply_ops(rec, fuse=bool(args.fuse))
+            return sv.expval(z0)             # one double back to the host
 
     step()
     k = max(1, min(args.steps, 3))
@@ -736,7 +800,9 @@ def end_to_end(torch, q, sv, buf, ops, n, cdtype, tdtype, amp_bytes, alg_bytes, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t)
     return {"value": alg_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * world,
-            "ms_per_step": dt * 1e3, "result_check": float(val)}
+            "ms_per_step": dt * 1e3, "result_check": float(val), "api": api,
+            "h2d_gbs_if_alone": None, "note": "pinned host state; the 2^n-amplitude upload is PCIe-bound (~55 GB/s measured on "
+            "this host, detail.state_io), the circuit itself is `ms_per_step` of the device-resident line"}
 
 
 def main():
@@ -756,7 +822,7 @@ def main():
     ap.add_argument("--cpu-baseline", dest="cpu_baseline", type=int, default=1)
     ap.add_argument("--adjoint", type=int, default=1, help="also time BASELINE config 3 (24q adjoint Jacobian)")
     ap.add_argument("--adjoint-qubits", dest="adjoint_qubits", type=int, default=24)
-    ap.add_argument("--config4", type=int, default=0, help="also run BASELINE config 4 (22q sparse Hamiltonian)")
+    ap.add_argument("--config4", type=int, default=1, help="also run BASELINE config 4 (22q sparse Hamiltonian)")
     ap.add_argument("--config4-qubits", dest="config4_qubits", type=int, default=22)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -179,6 +179,20 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
                             ai[j & 1] = fma((double)b[j].x, (double)x.y, ai[j & 1]);
                             ai[j & 1] = fma(-(double)b[j].y, (double)x.x, ai[j & 1]);
                         }
+                    } else if (cjm == 0u) {
+                        // the sign depends on the j bits (a Z / Y letter sits on one of them): flip the sign bit of the
+                        // partner amplitude with a CTA-uniform mask instead of multiplying
+#pragma unroll
+                        for (int j = 0; j < GT_EPT; ++j) {
+                            const A x = sp[((uint32_t)j ^ jx) * NT];
+                            const int flip = (__popc((unsigned)j & mj) & 1) << 31;  // CTA-uniform
+                            const double xr = __hiloint2double(__double2hiint((double)x.x) ^ flip, __double2loint((double)x.x));
+                            const double xi = __hiloint2double(__double2hiint((double)x.y) ^ flip, __double2loint((double)x.y));
+                            ar[j & 1] = fma((double)b[j].x, xr, ar[j & 1]);
+                            ar[j & 1] = fma((double)b[j].y, xi, ar[j & 1]);
+                            ai[j & 1] = fma((double)b[j].x, xi, ai[j & 1]);
+                            ai[j & 1] = fma(-(double)b[j].y, xr, ai[j & 1]);
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < GT_EPT; ++j) {
@@ -391,6 +405,78 @@ __global__ void __launch_bounds__(1 << (TB - GT_JB))
     }
 }
 
+// out = sum_t c_t P_t in   (+ out when `accumulate`)   for Pauli words whose X / Y letters all sit on tile bits: the tile of
+// `in` is read once into shared memory, every thread accumulates its 16 output amplitudes in registers over all terms of
+// the launch (one shared-memory read, a sign flip and four FP64 multiply-adds per term and amplitude) and writes them
+// once.  Replaces the per-term gather of k_pauli_sum_apply (one global read per term and amplitude) when a Hamiltonian
+// is applied to a vector -- the bra H|lambda> of the adjoint method (algorithms/ObservablesGPU.hpp:346-362 in the
+// reference: per-term copy + apply + axpy).
+template <typename T, int TB>
+__global__ void __launch_bounds__(1 << (TB - GT_JB))
+    k_pauli_sum_tile(const void *__restrict__ in, void *__restrict__ out, int accumulate, const __grid_constant__ GenProgram P) {
+    using A = typename VecOf<T, 1>::type;
+    constexpr int NT = 1 << (TB - GT_JB);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A *s = reinterpret_cast<A *>(smem_raw);
+    const uint64_t base = expand_index((uint64_t)blockIdx.x, P.tile_holes);
+    const uint32_t tid = threadIdx.x;
+    uint64_t g0 = tid & ((1u << P.L) - 1u);
+    for (int q = P.L; q < TB - GT_JB; ++q) g0 |= (uint64_t)((tid >> q) & 1u) << P.hi_bits[q - P.L];
+    g0 |= base;
+    uint64_t col[GT_JB];
+#pragma unroll
+    for (int q = 0; q < GT_JB; ++q) col[q] = 1ull << P.hi_bits[TB - GT_JB + q - P.L];
+#pragma unroll
+    for (int j = 0; j < GT_EPT; ++j) {
+        uint64_t gi = g0;
+#pragma unroll
+        for (int q = 0; q < GT_JB; ++q)
+            if ((j >> q) & 1) gi |= col[q];
+        s[tid + (uint32_t)j * NT] = reinterpret_cast<const A *>(in)[gi];
+    }
+    __syncthreads();
+    double yr[GT_EPT], yi[GT_EPT];
+#pragma unroll
+    for (int j = 0; j < GT_EPT; ++j) yr[j] = yi[j] = 0.0;
+    for (int k = 0; k < P.n_gens; ++k) {
+        const GenDesc &g = P.g[k];
+        const unsigned mj = g.jinfo & 15u;
+        // sign of amplitude i: (-1)^{popc((i ^ x) & z)} = thread part ^ j part; the j part is CTA-uniform
+        const int t_flip = (int)(((__popcll((g0 ^ g.xg) & g.zmask) ^ (g.jinfo >> 8)) & 1u) << 31);
+        const A *sp = s + (tid ^ (g.tbit & (uint32_t)(NT - 1)));
+        const uint32_t jx = g.tbit >> (TB - GT_JB);
+        const double cr = g.m[0], ci = g.m[1];
+#pragma unroll
+        for (int j = 0; j < GT_EPT; ++j) {
+            const A x = sp[((uint32_t)j ^ jx) * NT];
+            const int flip = t_flip ^ ((__popc((unsigned)j & mj) & 1) << 31);
+            const double xr = __hiloint2double(__double2hiint((double)x.x) ^ flip, __double2loint((double)x.x));
+            const double xi = __hiloint2double(__double2hiint((double)x.y) ^ flip, __double2loint((double)x.y));
+            yr[j] = fma(cr, xr, yr[j]);
+            yr[j] = fma(-ci, xi, yr[j]);
+            yi[j] = fma(cr, xi, yi[j]);
+            yi[j] = fma(ci, xr, yi[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < GT_EPT; ++j) {
+        uint64_t gi = g0;
+#pragma unroll
+        for (int q = 0; q < GT_JB; ++q)
+            if ((j >> q) & 1) gi |= col[q];
+        A *o = reinterpret_cast<A *>(out) + gi;
+        if (accumulate) {
+            const A old = *o;
+            yr[j] += (double)old.x;
+            yi[j] += (double)old.y;
+        }
+        A y;
+        y.x = (T)yr[j];
+        y.y = (T)yi[j];
+        *o = y;
+    }
+}
+
 // which generators the tile kernel takes; everything else goes through launch_bra_op_ket one by one
 bool tile_gen_kind(const LoweredGate &g, int n, int &kind) {
     if (g.kind == LoweredGate::PARITY) {
@@ -455,7 +541,24 @@ struct GenItem {
     int tgt = -1;  // kind 1
 };
 
-void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem> &todo, double *out_dev) {
+template <typename T, int TB>
+void launch_sum_tile_t(State &sv, const void *in, void *out, bool accumulate, const GenProgram &P) {
+    constexpr int NT = 1 << (TB - GT_JB);
+    const size_t smem = ((size_t)1 << TB) * sizeof(typename VecOf<T, 1>::type);
+    const unsigned grid = (unsigned)(1ull << (sv.n - TB));
+    static bool configured[64] = {false};
+    auto kern = k_pauli_sum_tile<T, TB>;
+    if (!configured[sv.device & 63]) {
+        QSV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[sv.device & 63] = true;
+    }
+    kern<<<grid, NT, smem, sv.stream>>>(in, out, accumulate ? 1 : 0, P);
+    QSV_CUDA(cudaGetLastError());
+}
+
+// apply_out != nullptr: the items are Pauli words with coefficients and the launches are k_pauli_sum_tile (out = / +=)
+void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem> &todo, double *out_dev,
+               void *apply_out = nullptr, bool *apply_accumulate = nullptr) {
     const int n = sv.n;
     const int TB = gens_tile_bits(n), L = gens_low_bits(TB);
     const int max_hi = TB - L;
@@ -536,6 +639,22 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
             d.jinfo = mj | (cj << 4) | (flip0 << 8);
         }
         sv.stat_launches += 1;
+        if (apply_out) {
+            if (sv.dtype == QSV_C128) {
+                if (TB == 13)
+                    launch_sum_tile_t<double, 13>(sv, ket, apply_out, *apply_accumulate, P);
+                else
+                    launch_sum_tile_t<double, 12>(sv, ket, apply_out, *apply_accumulate, P);
+            } else {
+                if (TB == 13)
+                    launch_sum_tile_t<float, 13>(sv, ket, apply_out, *apply_accumulate, P);
+                else
+                    launch_sum_tile_t<float, 12>(sv, ket, apply_out, *apply_accumulate, P);
+            }
+            *apply_accumulate = true;
+            todo.swap(rest);
+            continue;
+        }
         if (sv.dtype == QSV_C128) {
             if (TB == 13)
                 launch_gens_t<double, 13>(sv, bra, ket, out_dev, P);
@@ -641,6 +760,34 @@ void launch_bra_paulis_ket(State &sv, const void *bra, const void *ket, int n_te
         todo.push_back(it);
     }
     run_items(sv, bra, ket, todo, out_dev);
+}
+
+// out (+)= sum_t coeffs[t] * P_t in through the tile kernel; returns false when the vector is too small for a tile or a
+// word's X / Y letters do not fit one (the caller then uses the per-term gather kernel)
+bool launch_pauli_sum_apply_tiled(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
+                                  const uint64_t *zmasks, const cplx *coeffs, bool accumulate) {
+    sv.use();
+    const int n = sv.n;
+    const int TB = gens_tile_bits(n);
+    if (TB == 0 || n_terms < 2) return false;
+    const int L = gens_low_bits(TB);
+    const uint64_t low = (1ull << L) - 1ull;
+    std::vector<GenItem> todo;
+    for (int t = 0; t < n_terms; ++t) {
+        if (__builtin_popcountll(xmasks[t] & ~low) > TB - L) return false;
+        GenItem it;
+        memset(&it.d, 0, sizeof(it.d));
+        it.d.kind = 2;
+        it.d.xg = xmasks[t];
+        it.d.zmask = zmasks[t];
+        it.d.m[0] = coeffs[t].real();
+        it.d.m[1] = coeffs[t].imag();
+        it.need = xmasks[t];
+        todo.push_back(it);
+    }
+    bool acc = accumulate;
+    run_items(sv, nullptr, in, todo, nullptr, out, &acc);
+    return true;
 }
 
 }  // namespace qsv

@@ -11,6 +11,7 @@
 // The "bra-op-ket" kernels fuse  mu = G lambda ; <bra|mu>  into one read of bra and lambda, so the
 // adjoint sweep never materialises mu (north_star item (d)).
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "qsv_internal.h"
@@ -563,6 +564,14 @@ void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, c
                             const uint64_t *zmasks, const cplx *coeffs, bool accumulate) {
     sv.use();
     QSV_CHECK(in != out, "internal: pauli-sum apply is out of place");
+    static const bool tiled_ok = [] {
+        const char *v = std::getenv("QSV_PAULI_SUM_TILED");
+        return !(v && std::atoi(v) == 0);
+    }();
+    if (tiled_ok && launch_pauli_sum_apply_tiled(sv, in, out, n_terms, xmasks, zmasks, coeffs, accumulate)) {
+        QSV_CUDA(cudaStreamSynchronize(sv.stream));
+        return;
+    }
     sv.stat_launches += 1;
     const size_t nt = (size_t)n_terms;
     char *scr = (char *)sv.scratch_buffer(nt * (2 * sizeof(uint64_t) + sizeof(double2)));

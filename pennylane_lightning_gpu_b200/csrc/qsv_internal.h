@@ -203,6 +203,8 @@ void launch_bra_paulis_ket(State &sv, const void *bra, const void *ket, int n_te
 void launch_bra_pauli_ket(State &sv, const void *bra, const void *ket, uint64_t xmask, uint64_t zmask,
                           int ny, double *out_dev, int slot);
 // out[i] = sum_t coeff_t (P_t in)[i]   (out-of-place, in != out)
+bool launch_pauli_sum_apply_tiled(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
+                                  const uint64_t *zmasks, const cplx *coeffs, bool accumulate);
 void launch_pauli_sum_apply(State &sv, const void *in, void *out, int n_terms, const uint64_t *xmasks,
                             const uint64_t *zmasks, const cplx *coeffs_with_phase, bool accumulate = false);
 void launch_probs(State &sv, const std::vector<int> &bits_lsb_first, double *out_host);

@@ -233,8 +233,86 @@ __host__ __device__ __forceinline__ void reg_d1(A (&x)[NS], int kind, const T *m
 // Uncontrolled dense gates: no predicates, and the matrix is read from the kernel-parameter constant bank with a
 // CTA-uniform index -- in convergent code the compiler keeps it in UNIFORM registers (LDCU) and feeds DFMA / FFMA from
 // there, so the constants cost neither vector registers nor shared-memory round trips.
+// Every output's LAST multiply-add reads the very input it replaces (new a.x ends with q0x * a.x, ...): all other uses of
+// that input come earlier, so the result can be written over it in place and the unrolled code needs no register moves
+// to bring the amplitudes back to their home registers before the next gate.
 template <typename T, int B, int NS, typename A>
-__host__ __device__ __forceinline__ void reg_d1_plain(A (&x)[NS], int kind, const T *cp) {
+__host__ __device__ __forceinline__ void reg_d1_plain_inplace(A (&x)[NS], int kind, const T *cp) {
+    const T q0x = cp[0], q0y = cp[1], q1x = cp[2], q1y = cp[3], q2x = cp[4], q2y = cp[5], q3x = cp[6], q3y = cp[7];
+    if (kind == RG_D1_REAL) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const int k = j | (1 << B);
+            const T t0 = q1x * x[k].x, t1 = q1x * x[k].y, t2 = q2x * x[j].x, t3 = q2x * x[j].y;
+            x[j].x = q0x * x[j].x + t0;
+            x[j].y = q0x * x[j].y + t1;
+            x[k].x = q3x * x[k].x + t2;
+            x[k].y = q3x * x[k].y + t3;
+        }
+    } else if (kind == RG_D1_RX) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const int k = j | (1 << B);
+            const T t0 = -(q1y * x[k].y), t1 = q1y * x[k].x, t2 = -(q2y * x[j].y), t3 = q2y * x[j].x;
+            x[j].x = q0x * x[j].x + t0;
+            x[j].y = q0x * x[j].y + t1;
+            x[k].x = q3x * x[k].x + t2;
+            x[k].y = q3x * x[k].y + t3;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if ((j >> B) & 1) continue;
+            const int k = j | (1 << B);
+            const T t0 = q1x * x[k].x - q1y * x[k].y - q0y * x[j].y;
+            const T t1 = q1x * x[k].y + q1y * x[k].x + q0y * x[j].x;
+            const T t2 = q2x * x[j].x - q2y * x[j].y - q3y * x[k].y;
+            const T t3 = q2x * x[j].y + q2y * x[j].x + q3y * x[k].x;
+            x[j].x = q0x * x[j].x + t0;
+            x[j].y = q0x * x[j].y + t1;
+            x[k].x = q3x * x[k].x + t2;
+            x[k].y = q3x * x[k].y + t3;
+        }
+    }
+}
+
+template <typename T, int BA, int BB, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d2_plain_inplace(A (&x)[NS], const T *cp) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
+        const int idx[4] = {j, j | (1 << BB), j | (1 << BA), j | (1 << BA) | (1 << BB)};
+        T tr[4], ti[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const T *row = cp + 8 * r;
+            // everything but the real-part-of-the-diagonal term, which goes last and in place
+            T ar = -(row[2 * r + 1] * x[idx[r]].y), ai = row[2 * r + 1] * x[idx[r]].x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c == r) continue;
+                ar = ar + row[2 * c] * x[idx[c]].x - row[2 * c + 1] * x[idx[c]].y;
+                ai = ai + row[2 * c] * x[idx[c]].y + row[2 * c + 1] * x[idx[c]].x;
+            }
+            tr[r] = ar;
+            ti[r] = ai;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const T d = cp[8 * r + 2 * r];
+            x[idx[r]].x = d * x[idx[r]].x + tr[r];
+            x[idx[r]].y = d * x[idx[r]].y + ti[r];
+        }
+    }
+}
+
+// out-of-place forms (every output from fresh copies of the inputs): what the complex64 kernels use -- with 72 registers
+// per thread (3 CTAs per SM) the temporaries of the in-place forms above spill (ptxas: 460 bytes), while the complex128
+// kernels (128 registers) lose two thirds of their register moves with them (static IMAD.MOV 362 -> 135)
+template <typename T, int B, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d1_plain_oop(A (&x)[NS], int kind, const T *cp) {
     const T q0x = cp[0], q0y = cp[1], q1x = cp[2], q1y = cp[3], q2x = cp[4], q2y = cp[5], q3x = cp[6], q3y = cp[7];
     if (kind == RG_D1_REAL) {
 #pragma unroll
@@ -270,7 +348,7 @@ __host__ __device__ __forceinline__ void reg_d1_plain(A (&x)[NS], int kind, cons
 }
 
 template <typename T, int BA, int BB, int NS, typename A>
-__host__ __device__ __forceinline__ void reg_d2_plain(A (&x)[NS], const T *cp) {
+__host__ __device__ __forceinline__ void reg_d2_plain_oop(A (&x)[NS], const T *cp) {
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         if (((j >> BA) & 1) || ((j >> BB) & 1)) continue;
@@ -288,6 +366,31 @@ __host__ __device__ __forceinline__ void reg_d2_plain(A (&x)[NS], const T *cp) {
         x[i2] = y[2];
         x[i3] = y[3];
     }
+}
+
+template <typename T, int B, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d1_plain(A (&x)[NS], int kind, const T *cp) {
+#ifdef QSV_PLAIN_OOP
+    reg_d1_plain_oop<T, B, NS>(x, kind, cp);
+#else
+    if constexpr (sizeof(T) == 8)
+        reg_d1_plain_inplace<T, B, NS>(x, kind, cp);
+    else
+        reg_d1_plain_oop<T, B, NS>(x, kind, cp);
+#endif
+}
+template <typename T, int BA, int BB, int NS, typename A>
+__host__ __device__ __forceinline__ void reg_d2_plain(A (&x)[NS], const T *cp) {
+#ifdef QSV_PLAIN_OOP
+    reg_d2_plain_oop<T, BA, BB, NS>(x, cp);
+#else
+#ifdef QSV_D2_INPLACE
+    if constexpr (sizeof(T) == 8)
+        reg_d2_plain_inplace<T, BA, BB, NS>(x, cp);
+    else
+#endif
+        reg_d2_plain_oop<T, BA, BB, NS>(x, cp);
+#endif
 }
 
 // 4x4 block on register bits BA > BB; matrix index = 2 * bit(BA) + bit(BB)
