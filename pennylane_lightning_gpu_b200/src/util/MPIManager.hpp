@@ -9,9 +9,12 @@
 #include <netdb.h>
 #include <netinet/in.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include <array>
+#include <cstdint>
+#include <algorithm>
 #include <chrono>
 #include <complex>
 #include <cstdlib>
@@ -103,40 +106,93 @@ class MPIManager {
             n -= static_cast<std::size_t>(k);
         }
     }
-    // rank 0 listens on MASTER_ADDR:(QSV_BOOTSTRAP_PORT | MASTER_PORT + 1 + instance) and serves the buffer
+    // Bootstrap of the NCCL unique id over TCP (no MPI): rank 0 listens on the MASTER_ADDR interface, port
+    // QSV_BOOTSTRAP_PORT | MASTER_PORT + 1 (+ instance for further communicators), and serves the buffer to size - 1
+    // DISTINCT ranks.  A client first sends a 16-byte hello {magic, job token, rank, instance}; the token is a hash of
+    // the launcher's job identity (TORCHELASTIC_RUN_ID / SLURM_JOB_ID / QSV_JOB_TOKEN, MASTER_ADDR, MASTER_PORT, world
+    // size), so a stray connection (port scan, health probe) or a rank of another job is dropped and the slot stays
+    // free.  accept and recv time out (QSV_BOOTSTRAP_TIMEOUT_S, default 120 s): a dead rank is an error, not a hang.
+    static std::uint32_t job_token(int size) {
+        std::string key;
+        for (const char *n : {"QSV_JOB_TOKEN", "TORCHELASTIC_RUN_ID", "SLURM_JOB_ID", "MASTER_ADDR", "MASTER_PORT"})
+            if (const char *v = std::getenv(n)) key += std::string(n) + "=" + v + ";";
+        key += "world=" + std::to_string(size);
+        std::uint32_t h = 2166136261u;  // FNV-1a
+        for (unsigned char c : key) h = (h ^ c) * 16777619u;
+        return h;
+    }
+    static void set_timeouts(int fd, int seconds) {
+        timeval tv{};
+        tv.tv_sec = seconds;
+        ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+        ::setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+    }
     void tcp_bcast(unsigned char *buf, std::size_t n) {
-        static int instance = 0;
+        static int instance = 0;  // communicators are created in the same order on every rank (as with MPI_Comm_dup)
+        const int inst = instance++;
         const char *addr = std::getenv("MASTER_ADDR");
         const std::string host = addr ? addr : "127.0.0.1";
-        int port = env_int({"QSV_BOOTSTRAP_PORT"}, env_int({"MASTER_PORT"}, 29400) + 1) + instance++;
-        if (rank_ == 0) {
-            const int srv = ::socket(AF_INET, SOCK_STREAM, 0);
-            PL_ABORT_IF(srv < 0, "bootstrap: cannot create a socket");
-            const int one = 1;
-            ::setsockopt(srv, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-            sockaddr_in sa{};
-            sa.sin_family = AF_INET;
-            sa.sin_addr.s_addr = htonl(INADDR_ANY);
-            sa.sin_port = htons(static_cast<uint16_t>(port));
-            PL_ABORT_IF(::bind(srv, reinterpret_cast<sockaddr *>(&sa), sizeof(sa)) != 0,
-                        "bootstrap: cannot bind port " + std::to_string(port));
-            PL_ABORT_IF(::listen(srv, size_) != 0, "bootstrap: listen failed");
-            for (int r = 1; r < size_; ++r) {
-                const int fd = ::accept(srv, nullptr, nullptr);
-                PL_ABORT_IF(fd < 0, "bootstrap: accept failed");
-                send_all(fd, buf, n);
-                ::close(fd);
-            }
-            ::close(srv);
-            return;
-        }
+        const int port = env_int({"QSV_BOOTSTRAP_PORT"}, env_int({"MASTER_PORT"}, 29400) + 1) + inst;
+        const int timeout_s = std::max(1, env_int({"QSV_BOOTSTRAP_TIMEOUT_S"}, 120));
+        constexpr std::uint32_t MAGIC = 0x51535642u;  // "QSVB"
+        const std::uint32_t token = job_token(size_);
         addrinfo hints{}, *res = nullptr;
         hints.ai_family = AF_INET;
         hints.ai_socktype = SOCK_STREAM;
         PL_ABORT_IF(::getaddrinfo(host.c_str(), std::to_string(port).c_str(), &hints, &res) != 0 || res == nullptr,
                     "bootstrap: cannot resolve " + host);
+        if (rank_ == 0) {
+            const int srv = ::socket(AF_INET, SOCK_STREAM, 0);
+            PL_ABORT_IF(srv < 0, "bootstrap: cannot create a socket");
+            const int one = 1;
+            ::setsockopt(srv, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+            // the MASTER_ADDR interface only (loopback for a single-node torchrun), not INADDR_ANY
+            int rc = ::bind(srv, res->ai_addr, res->ai_addrlen);
+            ::freeaddrinfo(res);
+            PL_ABORT_IF(rc != 0, "bootstrap: cannot bind " + host + ":" + std::to_string(port));
+            PL_ABORT_IF(::listen(srv, size_ + 8) != 0, "bootstrap: listen failed");
+            set_timeouts(srv, timeout_s);  // SO_RCVTIMEO bounds accept()
+            std::vector<bool> served(size_, false);
+            int left = size_ - 1;
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(timeout_s);
+            while (left > 0) {
+                PL_ABORT_IF(std::chrono::steady_clock::now() > deadline,
+                            "bootstrap: " + std::to_string(left) + " rank(s) did not connect within " +
+                                std::to_string(timeout_s) + " s");
+                const int fd = ::accept(srv, nullptr, nullptr);
+                if (fd < 0) continue;  // timeout or interrupted: the deadline check above decides
+                set_timeouts(fd, 5);
+                std::uint32_t hello[4] = {0, 0, 0, 0};
+                std::size_t got = 0;
+                while (got < sizeof(hello)) {
+                    const ssize_t k = ::recv(fd, reinterpret_cast<unsigned char *>(hello) + got, sizeof(hello) - got, 0);
+                    if (k <= 0) break;
+                    got += static_cast<std::size_t>(k);
+                }
+                const bool ok = got == sizeof(hello) && hello[0] == MAGIC && hello[1] == token &&
+                                hello[2] >= 1u && hello[2] < static_cast<std::uint32_t>(size_) &&
+                                hello[3] == static_cast<std::uint32_t>(inst) && !served[hello[2]];
+                if (ok) {
+                    bool sent = true;
+                    const unsigned char *p = buf;
+                    std::size_t todo = n;
+                    while (todo && sent) {
+                        const ssize_t k = ::send(fd, p, todo, MSG_NOSIGNAL);
+                        if (k <= 0) sent = false;
+                        else { p += k; todo -= static_cast<std::size_t>(k); }
+                    }
+                    if (sent) {
+                        served[hello[2]] = true;
+                        --left;
+                    }
+                }
+                ::close(fd);  // an invalid or duplicate peer is simply dropped; its slot stays free
+            }
+            ::close(srv);
+            return;
+        }
         int fd = -1;
-        for (int attempt = 0; attempt < 600; ++attempt) {  // up to ~60 s for rank 0 to come up
+        for (int attempt = 0; attempt < timeout_s * 10; ++attempt) {  // wait for rank 0 to come up
             fd = ::socket(AF_INET, SOCK_STREAM, 0);
             if (fd >= 0 && ::connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
             if (fd >= 0) ::close(fd);
@@ -145,6 +201,9 @@ class MPIManager {
         }
         ::freeaddrinfo(res);
         PL_ABORT_IF(fd < 0, "bootstrap: cannot reach rank 0 at " + host + ":" + std::to_string(port));
+        set_timeouts(fd, timeout_s);
+        const std::uint32_t hello[4] = {MAGIC, token, static_cast<std::uint32_t>(rank_), static_cast<std::uint32_t>(inst)};
+        send_all(fd, reinterpret_cast<const unsigned char *>(hello), sizeof(hello));
         recv_all(fd, buf, n);
         ::close(fd);
     }
