@@ -204,3 +204,26 @@ def test_closed_form_expvals_and_variances(kats):
         if "var" in case:
             o_psi = orc.apply_observable(psi.copy(), obs)
             _close(np.vdot(o_psi, o_psi).real - e ** 2, case["var"], case)
+
+
+def test_cy_and_identity_analytic():
+    """The two named gates for which the reference's tests hold no in/out vector.  CY is pinned by the reference's own
+    matrix (simulator/cuGates_host.hpp:154-163: rows (1,0,0,0), (0,1,0,0), (0,0,0,-i), (0,0,i,0), first wire = control)
+    and by CY = S(t) CNOT S(t)^dagger; Identity is a no-op on any wire (StateVectorCudaManaged.hpp:321-323)."""
+    cy = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, -1j], [0, 0, 1j, 0]], dtype=complex)
+    assert np.array_equal(orc.gate_matrix("CY", [], 2), cy)
+    rng = np.random.default_rng(8)
+    n = 4
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi /= np.linalg.norm(psi)
+    for c, t in ((0, 1), (3, 1), (2, 0)):
+        got = orc.apply_op(psi, "CY", [c, t], [])
+        alt = orc.apply_op(orc.apply_op(orc.apply_op(psi, "S", [t], [], adjoint=True), "CNOT", [c, t], []), "S", [t], [])
+        assert np.max(np.abs(got - alt)) < 1e-15
+        # control = first wire: amplitudes with the control bit clear are untouched
+        keep = ((np.arange(1 << n) >> (n - 1 - c)) & 1) == 0
+        assert np.array_equal(got[keep], psi[keep])
+        assert np.max(np.abs(orc.apply_op(got, "CY", [c, t], [], adjoint=True) - psi)) < 1e-15
+    for w in range(n):
+        assert np.array_equal(orc.apply_op(psi, "Identity", [w], []), psi)
+    assert np.array_equal(orc.gate_matrix("Identity", [], 1), np.eye(2))

@@ -13,8 +13,8 @@ timeout 200 $A >> $OUT 2>&1
 env QSV_PAULI_SUM_TILED=0 timeout 200 $A >> $OUT 2>&1
 env QSV_GENS_TB=12 timeout 200 $A >> $OUT 2>&1
 echo "== default bench (as the driver runs it)" >> $OUT
-/usr/bin/time -v timeout 900 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
-echo "rc=$? $(grep 'Elapsed (wall' gpurun_out/r2_bench_1gpu.err)" >> $OUT
+T0=$(date +%s); timeout 900 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
+echo "rc=$? wall $(( $(date +%s) - T0 )) s" >> $OUT
 python - >> $OUT 2>&1 <<'P'
 import json
 d=json.loads(open("gpurun_out/r2_bench_1gpu.json").read().strip().splitlines()[-1])
