@@ -560,7 +560,14 @@ void launch_sum_tile_t(State &sv, const void *in, void *out, bool accumulate, co
 void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem> &todo, double *out_dev,
                void *apply_out = nullptr, bool *apply_accumulate = nullptr) {
     const int n = sv.n;
-    const int TB = gens_tile_bits(n), L = gens_low_bits(TB);
+    // a handful of generators: the 2^12 tile (two CTAs per SM, one loading while the other computes) beats the 2^13 one,
+    // whose point is to fit more generators into a launch
+    static const int small_tb = gens_env("QSV_GENS_SMALL_TB", 1);
+    bool small = small_tb && todo.size() <= 6 && n >= 12 && gens_tile_bits(n) > 12;
+    for (const GenItem &it : todo)
+        small = small && __builtin_popcountll(it.need & ~((1ull << gens_low_bits(12)) - 1ull)) <= 12 - gens_low_bits(12);
+    const int TB = small ? 12 : gens_tile_bits(n);
+    const int L = gens_low_bits(TB);
     const int max_hi = TB - L;
     const uint64_t low = (1ull << L) - 1ull;
     while (!todo.empty()) {
@@ -578,6 +585,7 @@ void run_items(State &sv, const void *bra, const void *ket, std::vector<GenItem>
                 rest.push_back(it);
             }
         }
+        QSV_CHECK(!take.empty(), "internal: a generator does not fit the tile");
         // Z sums: diagonal generators without controls whose parity mask has at most one bit
         for (GenItem &it : take)
             if (it.d.kind == 0 && it.d.ctrl == 0 && __builtin_popcountll(it.d.zmask) <= 1) it.d.kind = 3;

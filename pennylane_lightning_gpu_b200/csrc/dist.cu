@@ -19,6 +19,7 @@
 #include <array>
 #include <cstdlib>
 #include <functional>
+#include <mutex>
 
 #include "qsv_internal.h"
 
@@ -227,7 +228,8 @@ bool dist_dag_enabled() {
 }
 
 std::vector<DistStep> plan_dist_steps(const std::vector<uint64_t> &dense, const std::vector<uint64_t> &diag,
-                                      std::vector<int> &phys_of, std::vector<int> &log_of, int n_local) {
+                                      std::vector<int> &phys_of, std::vector<int> &log_of, int n_local, int depth_arg = 0,
+                                      int window_arg = 0) {
     const int n_total = (int)phys_of.size();
     const size_t n = dense.size();
     std::vector<DistStep> steps;
@@ -329,7 +331,8 @@ std::vector<DistStep> plan_dist_steps(const std::vector<uint64_t> &dense, const 
         size_t next = 0;
         int q = -1, l = -1;
     };
-    const int window_lo = std::max(0, n_local - 8);  // evict from the top bits: few, large contiguous blocks
+    // evict from the top bits: few, large contiguous blocks
+    const int window_lo = std::max(0, n_local - (window_arg > 0 ? window_arg : 8));
     // best (incoming qubit, evicted local bit) at a stall under the map (phys, log); depth 2 adds the best score of
     // the following stall
     std::function<Choice(const std::vector<int> &, const std::vector<int> &, int)> choose =
@@ -374,7 +377,8 @@ std::vector<DistStep> plan_dist_steps(const std::vector<uint64_t> &dense, const 
             return best;
         };
     const char *depth_env = std::getenv("QSV_DIST_PLAN_DEPTH");
-    const int depth = depth_env ? std::max(1, std::min(3, std::atoi(depth_env))) : (n <= 4096 ? 2 : 1);
+    const int depth = depth_arg > 0 ? depth_arg
+                                    : (depth_env ? std::max(1, std::min(3, std::atoi(depth_env))) : (n <= 4096 ? 2 : 1));
     while (true) {
         uint64_t gmask = 0;
         for (int q = 0; q < n_total; ++q)
@@ -593,12 +597,18 @@ void swap_p2p(State &sv, const std::vector<SwapItem> &items, int gphys, int l) {
 // ------------------------------------------------------------------------------------------------
 LoweredGate dist_hook_lower(int n_total, const Op &op) { return lower_op_total(n_total, op, false); }
 
+std::vector<DistStep> plan_dist_steps_priced(const std::vector<LoweredGate> &lowered, const std::vector<uint64_t> &dense,
+                                             const std::vector<uint64_t> &diag, std::vector<int> &phys_of,
+                                             std::vector<int> &log_of, int n_local, int dtype, bool out_of_place);
+
 std::vector<std::array<int, 3>> dist_hook_plan(const std::vector<LoweredGate> &lowered, std::vector<int> &phys_of,
                                                std::vector<int> &log_of, int n_local) {
     std::vector<uint64_t> dense(lowered.size(), 0), diag(lowered.size(), 0);
     for (size_t i = 0; i < lowered.size(); ++i) gate_bit_masks(lowered[i], dense[i], diag[i]);
     std::vector<std::array<int, 3>> out;
-    for (const DistStep &st : plan_dist_steps(dense, diag, phys_of, log_of, n_local)) out.push_back({st.kind, st.a, st.b});
+    // what dist_run_lowered executes for a fused complex128 circuit with room for the second buffer
+    for (const DistStep &st : plan_dist_steps_priced(lowered, dense, diag, phys_of, log_of, n_local, QSV_C128, true))
+        out.push_back({st.kind, st.a, st.b});
     return out;
 }
 
@@ -720,6 +730,136 @@ namespace {
 void *const *pointer_table(State &sv, const std::vector<void *> &vecs);
 }
 
+// ---- exchange schedules priced with the sweep cost model --------------------------------------------------------------
+// plan_dist_steps minimises the number of exchanges; what a step costs, though, is exchanges PLUS the fused sweeps of the
+// batches between them, and where the exchanges fall decides how well those batches pack.  For registers of 26 local
+// qubits and more (where a sweep is milliseconds) a few schedules -- look-ahead depth 1 / 2 / 3, eviction window 8 / 4 / 12
+// top bits -- are priced with the model of tools/sweep_cost_model.py (regs_sweep_model_cost on the programs the planner
+// builds for every batch, + 6 ms for an exchange a sweep carries, + 13 ms for one that needs its own pass; all at 30 local
+// qubits, the comparison does not depend on the size) and the cheapest is executed.  Rank-independent by construction
+// (global controls are priced as satisfied), so every rank picks the same schedule.  Results are cached by circuit
+// structure and qubit map: a variational loop or a benchmark plans each (circuit, map) once.
+struct DistPlanEntry {
+    uint64_t h1, h2;
+    std::vector<DistStep> steps;
+    std::vector<int> phys, log;
+};
+std::mutex g_dist_plan_mu;
+std::vector<DistPlanEntry> g_dist_plan_cache;
+
+double dist_schedule_cost(const std::vector<LoweredGate> &lowered, const std::vector<DistStep> &steps,
+                          std::vector<int> phys, std::vector<int> log, int n_local, int dtype, bool out_of_place) {
+    const int L = 4;
+    double cost = 0.0;
+    std::vector<LoweredGate> batch;
+    const uint64_t all_hi = ~((1ull << n_local) - 1ull);  // every global control satisfied: the rank with the most work
+    auto close_batch = [&](bool exchange_follows) {
+        bool carried = false;
+        if (!batch.empty()) {
+            const std::vector<LoweredGate> merged = prepare_gates_regs(batch);
+            const std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, true, 48, 512, dtype, 1);
+            std::vector<const LoweredGate *> cur;
+            for (size_t k = 0; k < plan.size(); ++k) {
+                const SweepPlan &sw = plan[k];
+                const bool last = k + 1 == plan.size();
+                const bool tile = sw.fused || (last && exchange_follows && out_of_place && regs_fusable(merged[sw.gates[0]], n_local));
+                if (!tile) {
+                    const LoweredGate &g = merged[sw.gates[0]];
+                    cost += 5.3 / (double)(1u << std::min(6, __builtin_popcountll(g.ctrl_mask)));
+                    continue;
+                }
+                cur.clear();
+                for (int i : sw.gates) cur.push_back(&merged[i]);
+                cost += regs_sweep_model_cost(n_local, dtype, cur, sw.need, L, true);
+                if (last) carried = true;
+            }
+            batch.clear();
+        }
+        if (exchange_follows) cost += out_of_place ? (carried ? 6.0 : 13.0) : 12.6;
+    };
+    for (const DistStep &st : steps) {
+        if (st.kind == 0) {
+            close_batch(true);
+            const int a = log[st.a], b = log[st.b];
+            log[st.a] = b;
+            log[st.b] = a;
+            phys[a] = st.b;
+            phys[b] = st.a;
+            continue;
+        }
+        LoweredGate g = localize_gate(remap_gate(lowered[st.a], phys), n_local, all_hi);
+        if (g.kind != LoweredGate::NOP) batch.push_back(std::move(g));
+    }
+    close_batch(false);
+    return cost;
+}
+
+std::vector<DistStep> plan_dist_steps_priced(const std::vector<LoweredGate> &lowered, const std::vector<uint64_t> &dense,
+                                             const std::vector<uint64_t> &diag, std::vector<int> &phys_of,
+                                             std::vector<int> &log_of, int n_local, int dtype, bool out_of_place) {
+    static const int tries = [] {
+        const char *e = std::getenv("QSV_DIST_PLAN_TRIES");
+        return e ? std::max(1, std::min(6, std::atoi(e))) : 5;
+    }();
+    const char *min_env = std::getenv("QSV_DIST_PLAN_MIN_LOCAL");  // tests lower it to exercise the search on small shards
+    const int min_local = std::max(13, min_env ? std::atoi(min_env) : 26);
+    if (tries <= 1 || n_local < min_local || !dist_dag_enabled() || lowered.size() < 8 || lowered.size() > 4096)
+        return plan_dist_steps(dense, diag, phys_of, log_of, n_local);
+    // cache key: gate structure (kinds, bits) + qubit map
+    uint64_t h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;
+    auto mix = [&](uint64_t v) {
+        h1 = (h1 ^ v) * 1099511628211ull;
+        h2 = (h2 + v) * 0xff51afd7ed558ccdull;
+        h2 ^= h2 >> 29;
+    };
+    mix((uint64_t)n_local);
+    mix((uint64_t)dtype);
+    mix((uint64_t)out_of_place);
+    for (size_t i = 0; i < lowered.size(); ++i) {
+        mix(dense[i]);
+        mix(diag[i]);
+        mix((uint64_t)lowered[i].kind * 131u + (uint64_t)lowered[i].k);
+    }
+    for (int p : phys_of) mix((uint64_t)p);
+    {
+        std::lock_guard<std::mutex> lock(g_dist_plan_mu);
+        for (size_t i = 0; i < g_dist_plan_cache.size(); ++i)
+            if (g_dist_plan_cache[i].h1 == h1 && g_dist_plan_cache[i].h2 == h2) {
+                if (i != 0) std::rotate(g_dist_plan_cache.begin(), g_dist_plan_cache.begin() + i, g_dist_plan_cache.begin() + i + 1);
+                phys_of = g_dist_plan_cache[0].phys;
+                log_of = g_dist_plan_cache[0].log;
+                return g_dist_plan_cache[0].steps;
+            }
+    }
+    static const int cand[6][2] = {{2, 8}, {1, 8}, {3, 8}, {2, 4}, {2, 12}, {1, 4}};  // (look-ahead depth, eviction window)
+    DistPlanEntry best;
+    double best_cost = 0.0;
+    size_t best_exchanges = 0;
+    for (int c = 0; c < tries; ++c) {
+        std::vector<int> phys = phys_of, log = log_of;
+        std::vector<DistStep> steps = plan_dist_steps(dense, diag, phys, log, n_local, cand[c][0], cand[c][1]);
+        size_t n_x = 0;
+        for (const DistStep &st : steps) n_x += st.kind == 0 ? 1 : 0;
+        const double cost = dist_schedule_cost(lowered, steps, phys_of, log_of, n_local, dtype, out_of_place);
+        if (c == 0 || cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && n_x < best_exchanges)) {
+            best_cost = cost;
+            best_exchanges = n_x;
+            best.steps = std::move(steps);
+            best.phys = std::move(phys);
+            best.log = std::move(log);
+        }
+    }
+    best.h1 = h1;
+    best.h2 = h2;
+    phys_of = best.phys;
+    log_of = best.log;
+    std::vector<DistStep> out = best.steps;
+    std::lock_guard<std::mutex> lock(g_dist_plan_mu);
+    g_dist_plan_cache.insert(g_dist_plan_cache.begin(), std::move(best));
+    if (g_dist_plan_cache.size() > 64) g_dist_plan_cache.pop_back();
+    return out;
+}
+
 // Gates on LOGICAL bits of the whole register, applied to the register itself (vecs == nullptr) or to a set of its
 // companions (lambda and the bras of the adjoint method): exchanges scheduled over the dependency DAG, everything between
 // two exchanges through the fused tile executor (or gate by gate when fuse is false).
@@ -733,7 +873,13 @@ void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool f
         QSV_CHECK(__builtin_popcountll(m) <= n_local, "gate acts on more wires than a shard holds");
     // the schedule is planned on a copy of the qubit map; the exchanges below replay it on the real one
     std::vector<int> plan_phys = d.phys_of, plan_log = d.log_of;
-    const std::vector<DistStep> steps = plan_dist_steps(dense, diag, plan_phys, plan_log, n_local);
+    // will the exchanges of this call go through the second buffer (a sweep can carry them)?  Same test as try_fused below,
+    // minus the allocation; rank-independent
+    const bool oop_mode = fuse && vecs == nullptr && fused_swap_enabled() && d.comp.empty() && !d.skip_main && d.p2p &&
+                          (d.shadow != nullptr || !d.shadow_tried);
+    const std::vector<DistStep> steps =
+        fuse ? plan_dist_steps_priced(lowered, dense, diag, plan_phys, plan_log, n_local, sv.dtype, oop_mode)
+             : plan_dist_steps(dense, diag, plan_phys, plan_log, n_local);
 
     std::vector<LoweredGate> batch;
     auto flush = [&](FusedExchange *fx) {

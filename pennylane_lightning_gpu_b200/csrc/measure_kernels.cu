@@ -233,7 +233,75 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// marginal probabilities, small output (<= 2^11 bins): shared-memory histogram per block
+// Marginal probabilities at HBM speed, any measured wires.  The state is read in ROWS of 32 consecutive amplitudes (one
+// per lane: 512 / 256 contiguous bytes), so the five lowest index bits are lane bits.  The measured bits above them
+// select a GROUP of rows (= the high part of the output bin), the other high bits are summed: a warp takes one chunk of
+// one group's rows, every lane adds up |psi|^2 of its column, lanes that differ only in SUMMED low bits are combined with
+// shuffles, and the remaining lanes -- one per value of the measured low bits -- write / add their bin.  No shared-memory
+// atomics (the first version spent 27 ms on 8 hot bins at 30 qubits), no strided reads.
+struct ProbsPlan {
+    Holes row_holes;            // measured high bits as positions in the row index (index bit - 5), ascending
+    unsigned char hi_out[40];   // output-bin bit of the j-th measured high bit
+    unsigned char hi_pos[40];   // its position in the row index
+    int n_hi;
+    unsigned lane_sum_mask;     // lane bits that are summed over
+    unsigned char lane_out[5];  // output-bin bit of lane bit b (255: summed)
+    int rows_log2;              // log2(rows per group)
+    int chunk_log2;             // log2(rows per chunk)
+    int use_atomics;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_probs_rows(const void *__restrict__ sv, double *__restrict__ out, uint64_t n_items, const __grid_constant__ ProbsPlan P) {
+    using A = typename VecOf<T, 1>::type;
+    const A *psi = reinterpret_cast<const A *>(sv);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int chunks_log2 = P.rows_log2 - P.chunk_log2;
+    uint64_t t_low = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+        if (P.lane_out[b] != 255 && ((lane >> b) & 1u)) t_low |= 1ull << P.lane_out[b];
+    for (uint64_t w = (((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; w < n_items; w += warps) {
+        const uint64_t g = w >> chunks_log2, c = w & ((1ull << chunks_log2) - 1ull);
+        uint64_t base_row = 0, t_high = 0;
+        for (int j = 0; j < P.n_hi; ++j)
+            if ((g >> j) & 1ull) {
+                base_row |= 1ull << P.hi_pos[j];
+                t_high |= 1ull << P.hi_out[j];
+            }
+        const uint64_t s0 = c << P.chunk_log2, s1 = s0 + (1ull << P.chunk_log2);
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        uint64_t s = s0;
+        for (; s + 4 <= s1; s += 4) {
+            const A a0 = psi[((expand_index(s, P.row_holes) | base_row) << 5) + lane];
+            const A a1 = psi[((expand_index(s + 1, P.row_holes) | base_row) << 5) + lane];
+            const A a2 = psi[((expand_index(s + 2, P.row_holes) | base_row) << 5) + lane];
+            const A a3 = psi[((expand_index(s + 3, P.row_holes) | base_row) << 5) + lane];
+            acc0 += (double)a0.x * (double)a0.x + (double)a0.y * (double)a0.y;
+            acc1 += (double)a1.x * (double)a1.x + (double)a1.y * (double)a1.y;
+            acc2 += (double)a2.x * (double)a2.x + (double)a2.y * (double)a2.y;
+            acc3 += (double)a3.x * (double)a3.x + (double)a3.y * (double)a3.y;
+        }
+        for (; s < s1; ++s) {
+            const A a0 = psi[((expand_index(s, P.row_holes) | base_row) << 5) + lane];
+            acc0 += (double)a0.x * (double)a0.x + (double)a0.y * (double)a0.y;
+        }
+        double acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+        for (int b = 0; b < 5; ++b)
+            if ((P.lane_sum_mask >> b) & 1u) acc += __shfl_xor_sync(0xffffffffu, acc, 1 << b);
+        if ((lane & P.lane_sum_mask) == 0u) {
+            if (P.use_atomics)
+                atomicAdd(out + (t_high | t_low), acc);
+            else
+                out[t_high | t_low] = acc;
+        }
+    }
+}
+
+// marginal probabilities, small output (<= 2^11 bins): shared-memory histogram per block (registers below 10 qubits)
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_probs_small(const void *__restrict__ sv, uint64_t length, int k, const unsigned char *__restrict__ bits,
@@ -350,6 +418,7 @@ __global__ void __launch_bounds__(256)
         const bool active = row < n_rows;
         const int64_t lo = active ? (int64_t)indptr[row] : 0, hi = active ? (int64_t)indptr[row + 1] : 0;
         double yr = 0, yi = 0;
+#pragma unroll 4
         for (int64_t j = lo + sub; j < hi; j += LPR) {
             const double2 v = values[j];
             T c[2];
@@ -616,7 +685,45 @@ void launch_probs(State &sv, const std::vector<int> &bits, double *out_host) {
     for (int i = 0; i < k; ++i) hb[i] = (unsigned char)bits[i];
     QSV_CUDA(cudaMemcpyAsync(dbits, hb, 64, cudaMemcpyHostToDevice, sv.stream));
     const bool f32 = sv.dtype == QSV_C64;
-    if (k <= 11) {
+    if (sv.n >= 10) {
+        // rows of 32 amplitudes; measured bits >= 5 select the group of rows, measured bits < 5 the lane's bin
+        ProbsPlan P;
+        memset(&P, 0, sizeof(P));
+        for (int b = 0; b < 5; ++b) P.lane_out[b] = 255;
+        std::vector<std::pair<int, int>> hi;  // (row-index position, output bit)
+        for (int q = 0; q < k; ++q) {
+            QSV_CHECK(bits[q] >= 0 && bits[q] < sv.n, "probability wire out of range");
+            if (bits[q] < 5)
+                P.lane_out[bits[q]] = (unsigned char)q;
+            else
+                hi.push_back({bits[q] - 5, q});
+        }
+        std::sort(hi.begin(), hi.end());
+        QSV_CHECK((int)hi.size() <= MAX_HOLES, "probability on more than 45 wires is not supported");
+        int pos[MAX_HOLES];
+        P.n_hi = (int)hi.size();
+        for (int j = 0; j < P.n_hi; ++j) {
+            pos[j] = hi[j].first;
+            P.hi_pos[j] = (unsigned char)hi[j].first;
+            P.hi_out[j] = (unsigned char)hi[j].second;
+        }
+        P.row_holes = make_holes(pos, P.n_hi, 0);
+        for (int b = 0; b < 5; ++b)
+            if (P.lane_out[b] == 255) P.lane_sum_mask |= 1u << b;
+        P.rows_log2 = sv.n - 5 - P.n_hi;
+        // enough chunks to fill the GPU, at least 64 rows (32 KiB) each when the groups are that long
+        const int want_items_log2 = 14;  // ~16k warp work items
+        P.chunk_log2 = std::max(std::min(P.rows_log2, 6), P.rows_log2 - std::max(0, want_items_log2 - P.n_hi));
+        P.chunk_log2 = std::min(P.chunk_log2, P.rows_log2);
+        P.use_atomics = P.chunk_log2 < P.rows_log2 ? 1 : 0;
+        const uint64_t n_items = 1ull << (P.n_hi + P.rows_log2 - P.chunk_log2);
+        if (P.use_atomics) QSV_CUDA(cudaMemsetAsync(bins, 0, nb * sizeof(double), sv.stream));
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_items + 7) / 8, NUM_SMS * 8));
+        if (f32)
+            k_probs_rows<float><<<grid, 256, 0, sv.stream>>>(sv.data, bins, n_items, P);
+        else
+            k_probs_rows<double><<<grid, 256, 0, sv.stream>>>(sv.data, bins, n_items, P);
+    } else if (k <= 11) {
         QSV_CUDA(cudaMemsetAsync(bins, 0, nb * sizeof(double), sv.stream));
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((sv.length() + 255) / 256, NUM_SMS * 4));
         if (f32)
@@ -721,6 +828,12 @@ void launch_csr(State &sv, const void *x, void *y, const void *dev_indptr, const
     const double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
     int lpr = 1;
     while (lpr < 32 && lpr < avg) lpr *= 2;
+    // QSV_CSR_LPR: lanes per row (A/B; fewer lanes = more rows in flight per warp and shorter shuffle trees)
+    static const int lpr_env = [] {
+        const char *v = std::getenv("QSV_CSR_LPR");
+        return v ? std::atoi(v) : 0;
+    }();
+    if (lpr_env == 1 || lpr_env == 2 || lpr_env == 4 || lpr_env == 8 || lpr_env == 16 || lpr_env == 32) lpr = lpr_env;
     const bool f32 = sv.dtype == QSV_C64;
     const bool i32 = index_bytes == 4;
     QSV_CHECK(index_bytes == 4 || index_bytes == 8, "CSR index width must be 4 or 8 bytes");

@@ -908,7 +908,12 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
     std::vector<const LoweredGate *> cur;
     for (size_t k = 0; k < plan.size(); ++k) {
         const SweepPlan &sw = plan[k];
-        if (!sw.fused) {
+        // the last sweep of the batch carries the exchange (its stores are routed element by element, xchg_target); a lone
+        // gate in that position runs through the tile kernel too when it can: one pass over the shard instead of the
+        // gate's own sweep plus a copy pass for the exchange
+        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1 &&
+                           (sw.fused || regs_fusable(merged[sw.gates[0]], sv.n));
+        if (!sw.fused && !carry) {
             const LoweredGate &g = merged[sw.gates[0]];
             if (dev_table)
                 launch_gate_multi(sv, g, dev_table, n_vecs);
@@ -918,8 +923,6 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
         }
         cur.clear();
         for (int i : sw.gates) cur.push_back(&merged[i]);
-        // the last sweep of the batch carries the exchange (its stores are routed element by element, xchg_target)
-        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1;
         run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs, carry ? fx : nullptr);
         if (carry) fx->done = true;
     }

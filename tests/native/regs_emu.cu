@@ -226,14 +226,14 @@ extern "C" int regs_emu_fused_exchange(const void *ops_handle, int n_local, int 
             std::vector<const LoweredGate *> cur;
             for (size_t k = 0; k < plan.size(); ++k) {
                 const SweepPlan &sw = plan[k];
-                if (!sw.fused) {
+                const bool carry = k + 1 == plan.size() && (sw.fused || regs_fusable(merged[sw.gates[0]], n_local));
+                if (!sw.fused && !carry) {
                     apply_lowered_host(psi, n_local, merged[sw.gates[0]]);
                     continue;
                 }
                 cur.clear();
                 for (int i : sw.gates) cur.push_back(&merged[i]);
                 build_reg_program(n_local, QSV_C128, 0, cur, sw.need, L, 4, P);
-                const bool carry = k + 1 == plan.size();
                 emulate_program<double, 4>(psi, n_local, P, carry ? xc : EmuXchg<double2>());
                 done = done || carry;
             }

@@ -316,7 +316,7 @@ def test_reordered_plans_are_legal_for_every_gate_family():
             m = m_next
 
 
-@pytest.mark.parametrize("n_total,n_local", [(8, 7), (9, 7), (10, 7), (9, 4), (7, 2)])
+@pytest.mark.parametrize("n_total,n_local", [(8, 7), (9, 7), (10, 7), (9, 4), (7, 2), (15, 13), (16, 13)])
 @pytest.mark.parametrize("dag", ["1", "0"])
 def test_sharded_executor_emulated_on_host_shards(n_total, n_local, dag, monkeypatch):
     """csrc/dist.cu: dist_apply_ops replayed on host shards for all ranks (tests/native/regs_emu.cu: dist_emu_apply_ops) with
@@ -335,8 +335,11 @@ def test_sharded_executor_emulated_on_host_shards(n_total, n_local, dag, monkeyp
     emu = C.CDLL(mod.build())
     emu.dist_emu_apply_ops.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     monkeypatch.setenv("QSV_DIST_DAG", dag)
+    # from 13 local qubits the schedule is the one priced with the sweep cost model (csrc/dist.cu: plan_dist_steps_priced;
+    # the default threshold of 26 local qubits is lowered here so that the host emulation can afford it)
+    monkeypatch.setenv("QSV_DIST_PLAN_MIN_LOCAL", "13")
     rng = np.random.default_rng(5 + n_total)
-    ops = workloads.random_gate_circuit(n_total, 50, 40 + n_total)
+    ops = workloads.random_gate_circuit(n_total, 50 if n_local < 13 else 120, 40 + n_total)
     extra = [{"name": "CZ", "wires": [0, n_total - 1], "params": []}, {"name": "RZ", "wires": [0], "params": [0.3]},
              {"name": "CNOT", "wires": [0, 3], "params": []}, {"name": "CRY", "wires": [4, 0], "params": [1.1]},
              {"name": "IsingXX", "wires": [0, 1], "params": [0.7]}, {"name": "SWAP", "wires": [0, n_total - 2], "params": []},
