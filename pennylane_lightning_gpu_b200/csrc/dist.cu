@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <mutex>
@@ -841,6 +842,9 @@ std::vector<DistStep> plan_dist_steps_priced(const std::vector<LoweredGate> &low
         size_t n_x = 0;
         for (const DistStep &st : steps) n_x += st.kind == 0 ? 1 : 0;
         const double cost = dist_schedule_cost(lowered, steps, phys_of, log_of, n_local, dtype, out_of_place);
+        if (std::getenv("QSV_DIST_PLAN_DEBUG"))
+            fprintf(stderr, "[qsv] exchange schedule depth=%d window=%d: %zu exchanges, model cost %.1f ms (30 local qubits)\n",
+                    cand[c][0], cand[c][1], n_x, cost);
         if (c == 0 || cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && n_x < best_exchanges)) {
             best_cost = cost;
             best_exchanges = n_x;
@@ -2306,6 +2310,7 @@ int qsv_dist_plan_from(const qsv_ops *ops, int n_total, int n_local, const int *
     }
     std::vector<uint64_t> dense, diag;
     std::vector<int> op_index;
+    std::vector<LoweredGate> lowered;
     for (size_t i = 0; i < ops->ops.size(); ++i) {
         const Op &op = ops->ops[i];
         if (op.name == "Identity") continue;
@@ -2316,9 +2321,11 @@ int qsv_dist_plan_from(const qsv_ops *ops, int n_total, int n_local, const int *
         dense.push_back(a);
         diag.push_back(b);
         op_index.push_back((int)i);
+        lowered.push_back(std::move(g));
     }
     int ns = 0;
-    for (const DistStep &st : plan_dist_steps(dense, diag, phys_of, log_of, n_local)) {
+    // the schedule qsv_dist_apply_ops executes for a fused complex128 circuit with room for the second buffer
+    for (const DistStep &st : plan_dist_steps_priced(lowered, dense, diag, phys_of, log_of, n_local, QSV_C128, true)) {
         if (steps && ns < max_steps) {
             steps[3 * ns] = st.kind;
             steps[3 * ns + 1] = st.kind == 0 ? st.a : op_index[st.a];
