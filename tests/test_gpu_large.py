@@ -94,3 +94,33 @@ def test_config2_30_qubits_complex64_vs_complex128(q):
     dist2 = n128 + n64 - 2.0 * dot_re
     assert abs(n128 - 1.0) <= 1e-10
     assert dist2 <= 1e-8, f"||psi64 - psi128||^2 = {dist2:.3e} (norms^2 {n128:.12f}, {n64:.12f})"
+
+
+def test_probabilities_at_24_qubits(q):
+    """csrc/measure_kernels.cu: k_probs_rows at a size where every branch of its work split is taken (one chunk per group
+    without atomics, several chunks per group with atomics, measured wires among the five lane bits, in any order)
+    against NumPy marginals of the same device state."""
+    from pennylane_lightning_gpu_b200 import workloads
+
+    n = 24
+    sv = q.StateVector(n, np.complex128)
+    sv.apply_ops(q.Ops(workloads.random_gate_circuit(n, 120, 7)), fuse=True)
+    psi = sv.d2h()
+    p_full = (np.abs(psi) ** 2).reshape([2] * n)
+    for wires in ([0], [n - 1], [3, 17], [n - 1, 0], [5, n - 2, 11], list(range(10)), list(range(n - 8, n)),
+                  [n - 3, 2, n - 1, 9, 20], list(range(0, n, 2)), list(range(n))):
+        got = sv.probs(wires)
+        # first listed wire = least significant bit of the output index (cuStateVec order, StateVectorCudaManaged.hpp:931-970)
+        keep = list(wires)
+        marg = p_full.sum(axis=tuple(a for a in range(n) if a not in keep)) if len(keep) < n else p_full
+        order = sorted(keep)
+        marg = np.transpose(marg, [order.index(w) for w in reversed(keep)]).reshape(-1)
+        assert got.shape == marg.shape
+        assert np.max(np.abs(got - marg)) <= 1e-12, wires
+    s32 = q.StateVector(n, np.complex64)
+    s32.h2d(psi.astype(np.complex64))
+    keep = [1, n - 1, 12]
+    got = s32.probs(keep)
+    marg = p_full.sum(axis=tuple(a for a in range(n) if a not in keep))
+    marg = np.transpose(marg, [sorted(keep).index(w) for w in reversed(keep)]).reshape(-1)
+    assert np.max(np.abs(got - marg)) <= 1e-6
