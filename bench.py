@@ -361,6 +361,12 @@ def run_ours(args):
             total_steps = args.steps + max(args.warmup, 3)
             detail["nvlink_swaps"]["out_of_place_exchanges_per_step"] = n_oop / total_steps
             detail["nvlink_swaps"]["carried_by_sweeps_per_step"] = n_carried / total_steps
+            try:
+                n_pull, n_pull_carried = sv.split_exchange_stats()
+                detail["nvlink_swaps"]["split_exchanges_per_step"] = n_pull / total_steps
+                detail["nvlink_swaps"]["second_halves_carried_by_sweeps_per_step"] = n_pull_carried / total_steps
+            except Exception:  # a reporting extra must not cost the bench line
+                pass
         if circuit == "config5":
             sw = detail["nvlink_swaps"]
             detail["config5"] = {

@@ -239,6 +239,9 @@ int qsv_dist_uses_peer_access(const qsv_state *local);
  * half of its tiles straight into the partner's buffer over NVLink) and how many of them a gate sweep carried; they are
  * not part of the swap statistics above, which time the in-place exchanges */
 int qsv_dist_fused_exchange_stats(const qsv_state *local, int *n_out_of_place, int *n_carried_by_sweeps);
+/* exchanges that were SPLIT between the sweep before (push a quarter of the shard, park a quarter) and the first sweep of the
+ * next batch (fetch what the partner parked; QSV_DIST_SPLIT_XCHG): second halves performed, and how many a sweep carried */
+int qsv_dist_split_exchange_stats(const qsv_state *local, int *n_second_halves, int *n_carried_by_sweeps);
 /* Qubit-map policy of a sharded register.  lazy = 0 (default; the reference's contract, StateVectorCudaMPI keeps every
  * gate's swaps paired, MPI.hpp:2533-2583): every collective entry point returns with the canonical layout, so
  * qsv_dist_d2h and the Python `state` property are purely LOCAL copies of the shard (StateVectorCudaBase.hpp:104-228)

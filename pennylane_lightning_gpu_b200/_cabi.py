@@ -98,6 +98,7 @@ SIGNATURES = {
     "qsv_dist_total_swap_stats": (_I, [_P, _IP, _U64P, C.POINTER(C.c_float), _I]),
     "qsv_dist_plan": (_I, [_P, _I, _I, _IP, _I, _IP, _IP]),
     "qsv_dist_fused_exchange_stats": (_I, [_P, _IP, _IP]),
+    "qsv_dist_split_exchange_stats": (_I, [_P, _IP, _IP]),
     "qsv_dist_plan_from": (_I, [_P, _I, _I, _IP, _IP, _I, _IP, _IP]),
     "qsv_dist_uses_peer_access": (_I, [_P]),
     "qsv_dist_set_basis_state": (_I, [_P, C.c_uint64]),

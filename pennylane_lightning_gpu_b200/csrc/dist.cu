@@ -87,6 +87,7 @@ struct DistCtx {
     PeerBuf shadow_pb;
     bool shadow_tried = false;
     int n_fused = 0, n_oop = 0;            // statistics: exchanges through the second buffer, and how many of them a sweep carried
+    int n_pull = 0, n_pull_carried = 0;    // split exchanges: second halves, and how many of them a sweep carried
     void **tab_dev = nullptr;              // device table of vector pointers for batched launches
     std::vector<void *> tab_cache;
 };
@@ -885,25 +886,8 @@ void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool f
         fuse ? plan_dist_steps_priced(lowered, dense, diag, plan_phys, plan_log, n_local, sv.dtype, oop_mode)
              : plan_dist_steps(dense, diag, plan_phys, plan_log, n_local);
 
-    std::vector<LoweredGate> batch;
-    auto flush = [&](FusedExchange *fx) {
-        if (batch.empty()) return;
-        if (vecs) {
-            void *const *table = pointer_table(sv, *vecs);
-            if (fuse) {
-                apply_gates_tiled(sv, batch, table, (int)vecs->size(), nullptr);
-            } else {
-                for (const auto &g : batch) launch_gate_multi(sv, g, table, (int)vecs->size());
-            }
-        } else if (fuse) {
-            apply_gates_tiled(sv, batch, nullptr, 1, fx);
-        } else {
-            for (const auto &g : batch) launch_gate(sv, g);
-        }
-        batch.clear();
-    };
-    // Exchanges fused into the last sweep of the batch before them (off unless QSV_DIST_FUSED_SWAP=1): the register then
-    // alternates between its own buffer and the second one; `home` is restored when the call ends.
+    // Exchanges carried by the sweeps around them (fused_swap_enabled): the register alternates between its own buffer
+    // and the second one; `home` is restored when the call ends.
     size_t n_exchanges = 0;
     for (const DistStep &st : steps) n_exchanges += st.kind == 0 ? 1 : 0;
     const bool try_fused = fuse && vecs == nullptr && fused_swap_enabled() && n_exchanges > 0 && d.comp.empty() &&
@@ -915,39 +899,91 @@ void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool f
         ~Home() { sv.data = p; }
     } restore_home{sv, home};
     bool in_shadow = false;
-    for (const DistStep &st : steps) {
+    auto buf = [&](bool shadow) -> const PeerBuf & { return shadow ? d.shadow_pb : d.main; };
+    // second half of a split exchange, owed to the next batch: the amplitudes the partner parked are still over there
+    struct PendingPull {
+        bool on = false;
+        int peer = 0, bit = 0, val = 0, stash = 0;
+    } pp;
+    static const int split_min_gates = [] {
+        const char *e = std::getenv("QSV_DIST_SPLIT_XCHG");  // 0: off; n > 0: split when >= n gates follow the exchange
+        return e ? std::atoi(e) : 24;
+    }();
+
+    std::vector<LoweredGate> batch;
+    auto flush = [&](FusedExchange *fx) {
+        if (vecs) {
+            if (batch.empty()) return;
+            void *const *table = pointer_table(sv, *vecs);
+            if (fuse) {
+                apply_gates_tiled(sv, batch, table, (int)vecs->size(), nullptr);
+            } else {
+                for (const auto &g : batch) launch_gate_multi(sv, g, table, (int)vecs->size());
+            }
+        } else if (fuse) {
+            FusedPull pull;
+            FusedPull *pl = nullptr;
+            if (pp.on) {
+                // the register lives in buf(in_shadow); what the partner parked sits in ITS buffer of the same role
+                pull.in_peer = buf(in_shadow).peer[pp.peer];
+                pull.out_mine = buf(!in_shadow).local;
+                pull.local_bit = pp.bit;
+                pull.my_value = pp.val;
+                pull.stash_bit = pp.stash;
+                const int peer1 = pp.peer;
+                // the partner has read what this rank parked for it: the buffer may be written again
+                pull.after = [&sv, peer1] { handshake(sv, peer1); };
+                pl = &pull;
+            }
+            if (!batch.empty() || pl) apply_gates_tiled(sv, batch, nullptr, 1, fx, pl);
+            if (pl) {
+                in_shadow = !in_shadow;  // the callee has set sv.data = pull.out_mine
+                pp.on = false;
+                d.n_pull += 1;
+                d.n_pull_carried += pull.carried ? 1 : 0;
+            }
+        } else {
+            for (const auto &g : batch) launch_gate(sv, g);
+        }
+        batch.clear();
+    };
+    for (size_t si = 0; si < steps.size(); ++si) {
+        const DistStep &st = steps[si];
         if (st.kind == 0) {
             // 16-byte units: index bit 0 of a complex64 shard cannot be exchanged out of place (rank-independent test)
             if (try_fused && !(sv.dtype == QSV_C64 && st.b == 0)) {
                 const int gb = st.a - n_local;
                 const int peer = d.rank ^ (1 << gb);
-                const PeerBuf &other_pb = in_shadow ? d.main : d.shadow_pb;
+                // Split the exchange between this batch's last sweep (push) and the next batch's first (pull) when enough
+                // gates follow for that batch to have more than one sweep: each carrier then moves a quarter of the shard
+                // over NVLink instead of one sweep moving half of it at the link's full rate.  Decided on the global step
+                // list, so every rank decides alike.
+                size_t following = 0;
+                while (si + 1 + following < steps.size() && steps[si + 1 + following].kind == 1) ++following;
+                const bool split = split_min_gates > 0 && (int)following >= split_min_gates && n_local >= 12 &&
+                                   regs_pull_supported();
+                const int stash = st.b == 4 ? 5 : 4;
+                // a pull owed to THIS batch runs first and moves the register: the push targets are what is "other" then
+                const bool shadow_at_push = pp.on ? !in_shadow : in_shadow;
                 FusedExchange fx;
-                fx.out_mine = other_pb.local;
-                fx.out_peer = other_pb.peer[peer];
+                for (int k = 0; k < 2; ++k) {
+                    fx.out_mine[k] = buf(!shadow_at_push).local;
+                    fx.out_peer[k] = buf(!shadow_at_push).peer[peer];
+                }
                 fx.local_bit = st.b;
                 fx.my_value = (d.rank >> gb) & 1;
-                // the partner has finished everything that read or wrote its other buffer (its previous fused sweep)
-                handshake(sv, peer);
+                fx.stash_bit = split ? stash : -1;
+                // the partner has finished everything that read or wrote its other buffer
+                fx.before = [&sv, peer] { handshake(sv, peer); };
                 flush(&fx);
                 if (fx.done) {
                     d.n_fused += 1;
                 } else {
-                    // no sweep to carry it on this rank (empty batch, a lone gate last, or the exchanged bit is a tile
-                    // bit of the last sweep): the same stores from a copy pass.  The partner cannot tell the difference,
-                    // so this choice need not be the same on both sides.
-                    const int shift = sv.dtype == QSV_C128 ? 0 : 1;
-                    const uint64_t count = sv.length() >> shift;
-                    const uint64_t bit_mask = 1ull << (st.b - shift);
-                    constexpr int U = 4;
-                    const unsigned grid =
-                        (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), 148 * 16));
-                    k_xchg_oop<U><<<grid, 256, 0, sv.stream>>>((const uint4 *)sv.data, (uint4 *)fx.out_mine,
-                                                               (uint4 *)fx.out_peer, count, bit_mask,
-                                                               fx.my_value ? bit_mask : 0ull);
-                    QSV_CUDA(cudaGetLastError());
-                    sv.stat_launches += 1;
-                    sv.stat_sweeps += 1;
+                    // no sweep to carry it on this rank (empty batch, or a last gate the tile kernel does not take): the same
+                    // stores from a copy pass.  The partner cannot tell the difference, so this choice need not be the same
+                    // on both sides.
+                    fx.before();
+                    launch_xchg_push_copy(sv, sv.data, fx.out_mine[0], fx.out_peer[0], st.b, fx.my_value, fx.stash_bit);
                 }
                 handshake(sv, peer);  // the partner has finished writing into this rank's other buffer
                 in_shadow = !in_shadow;
@@ -958,6 +994,13 @@ void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool f
                 d.phys_of[a] = st.b;
                 d.phys_of[b] = st.a;
                 d.n_oop += 1;  // not in n_swaps / total_bytes / total_ms: those describe the timed in-place exchanges
+                if (split) {
+                    pp.on = true;
+                    pp.peer = peer;
+                    pp.bit = st.b;
+                    pp.val = fx.my_value;
+                    pp.stash = stash;
+                }
                 continue;
             }
             flush(nullptr);
@@ -2268,6 +2311,14 @@ int qsv_dist_fused_exchange_stats(const qsv_state *sv, int *n_out_of_place, int 
     QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
     if (n_out_of_place) *n_out_of_place = sv->dist->n_oop;
     if (n_carried_by_sweeps) *n_carried_by_sweeps = sv->dist->n_fused;
+    QSV_API_END
+}
+
+int qsv_dist_split_exchange_stats(const qsv_state *sv, int *n_second_halves, int *n_carried_by_sweeps) {
+    QSV_API_BEGIN
+    QSV_CHECK(sv != nullptr && sv->dist != nullptr, "state vector is not part of a distributed register");
+    if (n_second_halves) *n_second_halves = sv->dist->n_pull;
+    if (n_carried_by_sweeps) *n_carried_by_sweeps = sv->dist->n_pull_carried;
     QSV_API_END
 }
 

@@ -229,19 +229,42 @@ void reduction_read(State &sv, const double *dev, double *host, size_t count);
 // circuits
 void apply_op(State &sv, const Op &op, bool extra_adjoint);
 void apply_ops_fused(State &sv, const std::vector<LoweredGate> &gates);
-// A global<->local index-bit exchange of a sharded register to be fused into the last sweep of a gate batch (dist.cu):
-// that sweep stores out of place, the tiles whose bit `local_bit` equals `my_value` to out_mine, the others to out_peer
-// (the partner's buffer, peer-mapped) with the bit flipped.  done is set when the batch ended in such a sweep.
+// A global<->local index-bit exchange of a sharded register, carried by the sweeps of the gate batches around it (dist.cu).
+// FusedExchange: the LAST sweep of a batch stores out of place -- amplitudes whose bit `local_bit` equals `my_value` to
+// out_mine, the others to out_peer (the partner's buffer, peer-mapped) with the bit flipped; with stash_bit >= 0 only the
+// leaving amplitudes whose stash bit is clear are pushed, the others wait in out_mine for the partner's pull.  Index [1] of
+// the targets applies when a pull earlier in the same batch has already moved the register to its other buffer.
+// `before` runs right before the carrying sweep (the handshake with the partner); done = a sweep carried it.
 struct FusedExchange {
-    void *out_mine = nullptr;
-    void *out_peer = nullptr;
+    void *out_mine[2] = {nullptr, nullptr};
+    void *out_peer[2] = {nullptr, nullptr};
     int local_bit = 0;
     int my_value = 0;
+    int stash_bit = -1;
+    std::function<void()> before;
     bool done = false;
+    bool moved_before = false;  // out: a pull earlier in the batch moved the register, so targets [1] are the ones to use
+};
+// FusedPull: the second half of a split exchange -- the FIRST sweep of the next batch reads out of place (from sv.data, or
+// from in_peer at the flipped offset for what the partner parked) and writes out_mine, where the register lives from then
+// on (the callee sets sv.data).  When the first sweep cannot carry it, the callee runs the copy-pass form before the batch.
+// `after` runs right after the pull (the handshake that tells the partner its parked amplitudes have been read).
+struct FusedPull {
+    const void *in_peer = nullptr;
+    void *out_mine = nullptr;
+    int local_bit = 0;
+    int my_value = 0;
+    int stash_bit = 0;
+    std::function<void()> after;
+    bool carried = false;  // statistics: a sweep did it (else the copy pass)
 };
 // same, on several vectors at once (dev_table = device array of n_vecs pointers, or null for sv.data)
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates, void *const *dev_table, int n_vecs,
-                       FusedExchange *fx = nullptr);
+                       FusedExchange *fx = nullptr, FusedPull *pull = nullptr);
+void launch_xchg_push_copy(State &sv, const void *in, void *out_mine, void *out_peer, int local_bit, int my_value, int stash_bit);
+void launch_xchg_pull_copy(State &sv, const void *in_mine, const void *in_peer, void *out, int local_bit, int my_value,
+                           int stash_bit);
+bool regs_pull_supported();
 // register-blocked tile kernel (tile_regs.cu) and its sweep planner (tile_kernels.cu)
 struct SweepPlan {
     std::vector<int> gates;  // indices into the (merged) gate list, in execution order
@@ -264,7 +287,8 @@ bool gates_commute_structurally(const LoweredGate &a, const LoweredGate &b);
 bool regs_fusable(const LoweredGate &g, int n_local);
 uint64_t regs_need_bits(const LoweredGate &g);
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L,
-                    void *const *table, int n_vecs, const FusedExchange *fx = nullptr);
+                    void *const *table, int n_vecs, const FusedExchange *fx = nullptr, int fx_idx = 0,
+                    const FusedPull *pull = nullptr);
 bool regs_tile_contains_bit(int n, uint64_t need, int L, int bit);
 void apply_observable(State &sv, const Obs &obs);          // sv <- O sv
 double observable_expval(State &sv, const Obs &obs);       // Re <sv|O|sv>

@@ -898,22 +898,40 @@ std::vector<SweepPlan> plan_sweeps_cached(int n_local, const std::vector<Lowered
 }
 
 static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
-                             FusedExchange *fx) {
+                             FusedExchange *fx, FusedPull *pull) {
     int L = env_int("QSV_REGS_LOW", 4);  // measured on B200 (profiles/r1_regs_ab.txt)
     L = std::max(1, std::min(L, 11));
     const std::vector<LoweredGate> merged = prepare_gates_regs(gates_in);
     const std::vector<SweepPlan> plan =
         plan_sweeps_cached(sv.n, merged, L, env_int("QSV_REGS_DAG", 1) != 0, std::min(48, env_int("QSV_REGS_MAX_GATES", 48)),
                            std::max(1, env_int("QSV_REGS_WINDOW", 512)), sv.dtype);
+    const bool single = dev_table == nullptr && n_vecs == 1;
+    auto tile_ok = [&](const SweepPlan &sw) { return sw.fused || regs_fusable(merged[sw.gates[0]], sv.n); };
+    // The second half of a split exchange comes first: carried by the first sweep when that sweep is not also the one that
+    // has to carry the next exchange (the two halves have fixed buffer roles, whatever the shape of this rank's batch: the
+    // pull always moves the register to its other buffer, the push always moves it again), else as a copy pass.
+    bool moved = false, pull_pending = false;
+    if (pull) {
+        QSV_CHECK(single, "internal: a split exchange works on one vector");
+        const bool first_carries = !plan.empty() && tile_ok(plan[0]) && regs_pull_supported() && !(fx && plan.size() == 1);
+        if (!first_carries) {
+            launch_xchg_pull_copy(sv, sv.data, pull->in_peer, pull->out_mine, pull->local_bit, pull->my_value, pull->stash_bit);
+            sv.data = pull->out_mine;
+            moved = true;
+            if (pull->after) pull->after();
+        } else {
+            pull_pending = true;
+        }
+    }
     std::vector<const LoweredGate *> cur;
     for (size_t k = 0; k < plan.size(); ++k) {
         const SweepPlan &sw = plan[k];
         // the last sweep of the batch carries the exchange (its stores are routed element by element, xchg_target); a lone
         // gate in that position runs through the tile kernel too when it can: one pass over the shard instead of the
         // gate's own sweep plus a copy pass for the exchange
-        const bool carry = fx != nullptr && k + 1 == plan.size() && dev_table == nullptr && n_vecs == 1 &&
-                           (sw.fused || regs_fusable(merged[sw.gates[0]], sv.n));
-        if (!sw.fused && !carry) {
+        const bool carry = fx != nullptr && k + 1 == plan.size() && single && tile_ok(sw);
+        const bool pulls = pull_pending && k == 0;
+        if (!sw.fused && !carry && !pulls) {
             const LoweredGate &g = merged[sw.gates[0]];
             if (dev_table)
                 launch_gate_multi(sv, g, dev_table, n_vecs);
@@ -923,18 +941,33 @@ static void apply_gates_regs(State &sv, const std::vector<LoweredGate> &gates_in
         }
         cur.clear();
         for (int i : sw.gates) cur.push_back(&merged[i]);
-        run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs, carry ? fx : nullptr);
+        if (carry && fx->before) fx->before();
+        run_sweep_regs(sv, cur, sw.need, L, dev_table, n_vecs, carry ? fx : nullptr, moved ? 1 : 0, pulls ? pull : nullptr);
+        if (pulls) {
+            sv.data = pull->out_mine;
+            moved = true;
+            pull->carried = true;
+            pull_pending = false;
+            if (pull->after) pull->after();
+        }
         if (carry) fx->done = true;
     }
+    if (fx) fx->moved_before = moved;
 }
 
 void apply_gates_tiled(State &sv, const std::vector<LoweredGate> &gates_in, void *const *dev_table, int n_vecs,
-                       FusedExchange *fx) {
+                       FusedExchange *fx, FusedPull *pull) {
     sv.use();
     if (fx) fx->done = false;
     if (sv.n >= 12 && env_int("QSV_TILE_KERNEL", 1) == 1) {
-        apply_gates_regs(sv, gates_in, dev_table, n_vecs, fx);
+        apply_gates_regs(sv, gates_in, dev_table, n_vecs, fx, pull);
         return;
+    }
+    if (pull) {  // the first-generation executor carries nothing: copy pass first
+        launch_xchg_pull_copy(sv, sv.data, pull->in_peer, pull->out_mine, pull->local_bit, pull->my_value, pull->stash_bit);
+        sv.data = pull->out_mine;
+        if (pull->after) pull->after();
+        if (fx) fx->moved_before = true;
     }
     const bool f32 = sv.dtype == QSV_C64;
     int tb = env_int("QSV_TILE_BITS", f32 ? 13 : 12);

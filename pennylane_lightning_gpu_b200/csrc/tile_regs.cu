@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cstdlib>
+#include <cstring>
 
 #include <vector>
 
@@ -46,18 +47,22 @@ __device__ unsigned long long g_sm_arrivals[256];
 // (xchg_target), so `bit` may also be a tile bit.  The transfer overlaps the arithmetic of the tiles in flight; no
 // separate exchange pass, no staging.
 struct XchgArgs {
+    // push (the sweep in front of an exchange): stores routed by xchg_target; bit_mask = 0 switches it off (everything goes to
+    // out_mine at its own offset: a plain out-of-place sweep, as the pull sweep is)
     void *out_mine;
     void *out_peer;
-    uint64_t bit_mask;  // 1 << (exchanged local bit)
-    uint64_t keep;      // bit_mask when this rank's value of the global bit is 1, else 0
-    // When the exchanged bit is outside the tile, whole tiles go one way.  Enumerated in index order, the tiles of the
-    // lower half of the shard would all stay and those of the upper half all leave (the exchanged bit is one of the top
-    // bits): no NVLink traffic during the first half of the sweep, twice the link rate wanted during the second (measured:
-    // the sweep took 19 ms instead of 13).  With `interleave` the LOWEST bit of the block index is the exchanged bit, so
-    // staying and leaving tiles alternate and the link carries a steady half of the sweep's stores.
+    uint64_t bit_mask;    // 1 << (exchanged local bit)
+    uint64_t keep;        // bit_mask when this rank's value of the global bit is 1, else 0
+    uint64_t stash_mask;  // != 0: the exchange is split, see xchg_target
+    // pull (the sweep behind a split exchange): loads routed by xchg_source; pull_bit_mask = 0 switches it off
+    const void *in_peer;
+    uint64_t pull_bit_mask, pull_keep, pull_stash_mask;
+    // When the exchanged bit is outside the tile, whole tiles go one way.  With `interleave` the LOWEST bit of the block
+    // index is the exchanged bit, so staying and leaving tiles alternate instead of all leaving tiles coming in the second
+    // half of the sweep.  (No measurable effect on the bench circuits, whose exchanged bits are tile bits.)
     int interleave;
     int bit_pos;
-    Holes holes2;       // tile bits + the exchanged bit
+    Holes holes2;         // tile bits + the exchanged bit
 };
 struct NoXchg {};
 
@@ -139,8 +144,21 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         uint64_t gr[RB_MAX];
 #pragma unroll
         for (int b = 0; b < RB; ++b) gr[b] = P.gl_load.reg[b];
+        if constexpr (XCHG) {
+            if (xa.pull_bit_mask != 0) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
+                for (int j = 0; j < NS; ++j) {
+                    const XchgTarget t = xchg_source(slot_offset<RB>(gt, gr, j), xa.pull_bit_mask, xa.pull_keep, xa.pull_stash_mask);
+                    x[j] = (t.stays ? gbase : reinterpret_cast<const A *>(xa.in_peer))[t.base];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) x[j] = gbase[slot_offset<RB>(gt, gr, j)];
+        }
     }
     const int last = P.n_passes - 1;
     for (int pv = 0;; ++pv) {
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
         if constexpr (XCHG) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep);
+                const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep, xa.stash_mask);
                 reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer)[t.base] = x[j];
             }
         } else {
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(1 << (RT_TB - RB), MINB)
             if constexpr (XCHG) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep);
+                    const XchgTarget t = xchg_target(slot_offset<RB>(gt, gr, j), xa.bit_mask, xa.keep, xa.stash_mask);
                     reinterpret_cast<A *>(t.stays ? xa.out_mine : xa.out_peer)[t.base] = x[j];
                 }
             } else {
@@ -1211,8 +1229,13 @@ void regs_sweep_work(int n, int dtype, const std::vector<const LoweredGate *> &g
     if (passes) *passes = P.n_passes;
 }
 
+bool regs_pull_supported() {
+    static const bool persist = env_int_regs("QSV_REGS_PERSIST", 0) != 0;
+    return !persist;  // the persistent variant streams its tiles with cp.async and has no routed loads
+}
+
 void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, uint64_t need, int L, void *const *table,
-                    int n_vecs, const FusedExchange *fx) {
+                    int n_vecs, const FusedExchange *fx, int fx_idx, const FusedPull *pull) {
     const int rb = regs_rb();
     RegProgram P;
     build_reg_program(sv.n, sv.dtype, sv.index_hi, gates, need, L, rb, P);
@@ -1222,29 +1245,41 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
     sv.stat_sweeps += 1;
     XchgArgs xa_store;
     const XchgArgs *xa = nullptr;
-    if (fx) {
-        xa_store.out_mine = fx->out_mine;
-        xa_store.out_peer = fx->out_peer;
-        xa_store.bit_mask = 1ull << fx->local_bit;
-        xa_store.keep = fx->my_value ? xa_store.bit_mask : 0ull;
-        xa_store.interleave = 0;
-        xa_store.bit_pos = fx->local_bit;
+    if (fx || pull) {
+        memset(&xa_store, 0, sizeof(xa_store));
         xa_store.holes2 = P.tile_holes;
-        static const bool interleave_ok = env_flag("QSV_DIST_XCHG_INTERLEAVE", 1);
-        if (interleave_ok && !regs_tile_contains_bit(sv.n, need, L, fx->local_bit) && sv.n > RT_TB && P.tile_holes.n < MAX_HOLES) {
-            // tile bits + the exchanged bit, ascending
-            int pos[MAX_HOLES + 1], m = 0;
-            bool placed = false;
-            for (int j = 0; j < P.tile_holes.n; ++j) {
-                if (!placed && fx->local_bit < (int)P.tile_holes.pos[j]) {
-                    pos[m++] = fx->local_bit;
-                    placed = true;
+        if (pull) {
+            QSV_CHECK(regs_pull_supported(), "internal: this sweep kernel cannot fetch from the partner");
+            xa_store.in_peer = pull->in_peer;
+            xa_store.pull_bit_mask = 1ull << pull->local_bit;
+            xa_store.pull_keep = pull->my_value ? xa_store.pull_bit_mask : 0ull;
+            xa_store.pull_stash_mask = 1ull << pull->stash_bit;
+            xa_store.out_mine = pull->out_mine;  // a plain out-of-place sweep unless it pushes as well
+        }
+        if (fx) {
+            xa_store.out_mine = fx->out_mine[fx_idx];
+            xa_store.out_peer = fx->out_peer[fx_idx];
+            xa_store.bit_mask = 1ull << fx->local_bit;
+            xa_store.keep = fx->my_value ? xa_store.bit_mask : 0ull;
+            xa_store.stash_mask = fx->stash_bit >= 0 ? 1ull << fx->stash_bit : 0ull;
+            xa_store.bit_pos = fx->local_bit;
+            static const bool interleave_ok = env_flag("QSV_DIST_XCHG_INTERLEAVE", 1);
+            if (interleave_ok && !regs_tile_contains_bit(sv.n, need, L, fx->local_bit) && sv.n > RT_TB &&
+                P.tile_holes.n < MAX_HOLES) {
+                // tile bits + the exchanged bit, ascending
+                int pos[MAX_HOLES + 1], m = 0;
+                bool placed = false;
+                for (int j = 0; j < P.tile_holes.n; ++j) {
+                    if (!placed && fx->local_bit < (int)P.tile_holes.pos[j]) {
+                        pos[m++] = fx->local_bit;
+                        placed = true;
+                    }
+                    pos[m++] = P.tile_holes.pos[j];
                 }
-                pos[m++] = P.tile_holes.pos[j];
+                if (!placed) pos[m++] = fx->local_bit;
+                xa_store.holes2 = make_holes(pos, m, 0);
+                xa_store.interleave = 1;
             }
-            if (!placed) pos[m++] = fx->local_bit;
-            xa_store.holes2 = make_holes(pos, m, 0);
-            xa_store.interleave = 1;
         }
         xa = &xa_store;
     }
@@ -1259,6 +1294,88 @@ void run_sweep_regs(State &sv, const std::vector<const LoweredGate *> &gates, ui
         else
             launch_regs_t<float, 3>(sv, P, table, n_vecs, xa);
     }
+}
+
+
+// ---- copy-pass forms of the two halves of an exchange (a batch whose first / last sweep cannot carry them) ------------
+namespace {
+// 16-byte units; masks are in units
+template <int U>
+__global__ void __launch_bounds__(256)
+    k_xchg_push_copy(const uint4 *__restrict__ in, uint4 *__restrict__ out_mine, uint4 *__restrict__ out_peer, uint64_t count,
+                     uint64_t bit_mask, uint64_t keep, uint64_t stash_mask) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * U;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 * U + threadIdx.x; i0 < count; i0 += stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) v[u] = in[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) {
+                const XchgTarget t = xchg_target(i, bit_mask, keep, stash_mask);
+                (t.stays ? out_mine : out_peer)[t.base] = v[u];
+            }
+        }
+    }
+}
+template <int U>
+__global__ void __launch_bounds__(256)
+    k_xchg_pull_copy(const uint4 *__restrict__ in_mine, const uint4 *__restrict__ in_peer, uint4 *__restrict__ out, uint64_t count,
+                     uint64_t bit_mask, uint64_t keep, uint64_t stash_mask) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * U;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 * U + threadIdx.x; i0 < count; i0 += stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) {
+                const XchgTarget t = xchg_source(i, bit_mask, keep, stash_mask);
+                v[u] = (t.stays ? in_mine : in_peer)[t.base];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * 256;
+            if (i < count) out[i] = v[u];
+        }
+    }
+}
+}  // namespace
+
+void launch_xchg_push_copy(State &sv, const void *in, void *out_mine, void *out_peer, int local_bit, int my_value,
+                           int stash_bit) {
+    sv.use();
+    const int shift = sv.dtype == QSV_C128 ? 0 : 1;  // complex64: two amplitudes per 16-byte unit
+    QSV_CHECK(local_bit >= shift && (stash_bit < 0 || stash_bit >= shift), "internal: exchanged bit below the copy unit");
+    const uint64_t count = sv.length() >> shift;
+    const uint64_t bit_mask = 1ull << (local_bit - shift);
+    constexpr int U = 4;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), NUM_SMS * 16));
+    k_xchg_push_copy<U><<<grid, 256, 0, sv.stream>>>((const uint4 *)in, (uint4 *)out_mine, (uint4 *)out_peer, count, bit_mask,
+                                                     my_value ? bit_mask : 0ull, stash_bit >= 0 ? 1ull << (stash_bit - shift) : 0ull);
+    QSV_CUDA(cudaGetLastError());
+    sv.stat_launches += 1;
+    sv.stat_sweeps += 1;
+}
+
+void launch_xchg_pull_copy(State &sv, const void *in_mine, const void *in_peer, void *out, int local_bit, int my_value,
+                           int stash_bit) {
+    sv.use();
+    const int shift = sv.dtype == QSV_C128 ? 0 : 1;
+    QSV_CHECK(local_bit >= shift && stash_bit >= shift, "internal: exchanged bit below the copy unit");
+    const uint64_t count = sv.length() >> shift;
+    const uint64_t bit_mask = 1ull << (local_bit - shift);
+    constexpr int U = 4;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 256 * U - 1) / (256 * U), NUM_SMS * 16));
+    k_xchg_pull_copy<U><<<grid, 256, 0, sv.stream>>>((const uint4 *)in_mine, (const uint4 *)in_peer, (uint4 *)out, count, bit_mask,
+                                                     my_value ? bit_mask : 0ull, 1ull << (stash_bit - shift));
+    QSV_CUDA(cudaGetLastError());
+    sv.stat_launches += 1;
+    sv.stat_sweeps += 1;
 }
 
 }  // namespace qsv

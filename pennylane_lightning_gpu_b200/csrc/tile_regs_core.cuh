@@ -81,9 +81,21 @@ struct XchgTarget {
     bool stays;
     uint64_t base;
 };
-__host__ __device__ __forceinline__ XchgTarget xchg_target(uint64_t offset, uint64_t bit_mask, uint64_t keep) {
-    const bool stays = (offset & bit_mask) == keep;
+// `stash_mask` != 0 splits the exchange between the sweep before it and the sweep after it (dist.cu): of the amplitudes that
+// leave, only those with the stash bit CLEAR are pushed to the partner now; the others are parked at their own offset of this
+// rank's other buffer, where the partner's next sweep fetches them (xchg_source) -- each of the two sweeps then carries a
+// quarter of the shard over NVLink instead of one sweep carrying half of it at the link's full rate.
+__host__ __device__ __forceinline__ XchgTarget xchg_target(uint64_t offset, uint64_t bit_mask, uint64_t keep,
+                                                           uint64_t stash_mask = 0) {
+    const bool stays = (offset & bit_mask) == keep || (offset & stash_mask) != 0;
     return {stays, stays ? offset : offset ^ bit_mask};
+}
+// Pull side: where the amplitude of the NEW layout at `offset` is read from -- this rank's buffer (it stayed, or the partner
+// pushed it), or the partner's buffer at the offset with the exchanged bit flipped (the partner parked it there).
+__host__ __device__ __forceinline__ XchgTarget xchg_source(uint64_t offset, uint64_t bit_mask, uint64_t keep,
+                                                           uint64_t stash_mask) {
+    const bool local = (offset & bit_mask) == keep || (offset & stash_mask) == 0;
+    return {local, local ? offset : offset ^ bit_mask};
 }
 
 template <typename T> __host__ __device__ __forceinline__ const T *const_pool(const RegProgram &P);

@@ -97,6 +97,12 @@ class DistributedStateVector:
         _check(lib().qsv_dist_fused_exchange_stats(self.local._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def split_exchange_stats(self):
+        """(second halves of split exchanges performed, how many of them a gate sweep carried) -- QSV_DIST_SPLIT_XCHG."""
+        a, b = C.c_int(0), C.c_int(0)
+        _check(lib().qsv_dist_split_exchange_stats(self.local._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def uses_peer_access(self) -> bool:
         return bool(lib().qsv_dist_uses_peer_access(self.local._h))

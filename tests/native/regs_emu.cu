@@ -58,7 +58,10 @@ template <typename A> void apply_lowered_host(std::vector<A> &psi, int n, const 
 template <typename A> struct EmuXchg {
     A *out_mine = nullptr;
     A *out_peer = nullptr;
-    uint64_t bit_mask = 0, keep = 0;
+    uint64_t bit_mask = 0, keep = 0, stash_mask = 0;
+    // pull side of a split exchange (k_tile_regs: xa.in_peer / pull_*): the first pass reads through xchg_source
+    const A *in_peer = nullptr;
+    uint64_t pull_bit_mask = 0, pull_keep = 0, pull_stash_mask = 0;
 };
 
 template <typename T, int RB>
@@ -81,7 +84,15 @@ void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegPro
                 A *x = &xs[(size_t)tid * NS];
                 if (first) {
                     const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_load.thr, P.gl_load.c, tid);
-                    for (int j = 0; j < NS; ++j) x[j] = psi[slot_offset<RB>(gt, P.gl_load.reg, j)];
+                    for (int j = 0; j < NS; ++j) {
+                        const uint64_t off = slot_offset<RB>(gt, P.gl_load.reg, j);
+                        if (xc.pull_bit_mask != 0) {
+                            const XchgTarget t = xchg_source(off, xc.pull_bit_mask, xc.pull_keep, xc.pull_stash_mask);
+                            x[j] = t.stays ? psi[t.base] : xc.in_peer[t.base];
+                        } else {
+                            x[j] = psi[off];
+                        }
+                    }
                 } else {
                     const uint32_t st = thread_offset<NTB>(ps.ld_thr, ps.ld_c, tid);
                     uint32_t sr[RB_MAX] = {0, 0, 0, 0};
@@ -117,7 +128,7 @@ void emulate_program(std::vector<typename Cx<T>::type> &psi, int n, const RegPro
                 if (last && xc.out_mine) {
                     const uint64_t gt = base ^ thread_offset64<NTB>(P.gl_store.thr, P.gl_store.c, tid);
                     for (int j = 0; j < NS; ++j) {
-                        const XchgTarget t = xchg_target(slot_offset<RB>(gt, P.gl_store.reg, j), xc.bit_mask, xc.keep);
+                        const XchgTarget t = xchg_target(slot_offset<RB>(gt, P.gl_store.reg, j), xc.bit_mask, xc.keep, xc.stash_mask);
                         (t.stays ? xc.out_mine : xc.out_peer)[t.base] = x[j];
                     }
                 } else if (last) {
@@ -255,6 +266,125 @@ extern "C" int regs_emu_fused_exchange(const void *ops_handle, int n_local, int 
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "regs_emu_fused_exchange: %s\n", e.what());
+        return 1;
+    }
+}
+
+// A SPLIT exchange (csrc/dist.cu, QSV_DIST_SPLIT_XCHG): two ranks of a register sharded on one global bit run batch 1, whose
+// last sweep pushes the leaving amplitudes with the stash bit clear to the partner and parks the others (xchg_target with a
+// stash mask), then batch 2, whose first sweep fetches the parked amplitudes from the partner (xchg_source) -- or the copy
+// passes when the batch cannot carry them (mode bit 0: push carried, bit 1: pull carried).  Buffer roles as in the
+// library: batch 1 runs in X and stores into Y, the pull reads Y (own and the partner's) and writes X.
+static void lower_all(const qsv_ops *ops, int n_local, std::vector<LoweredGate> &gates) {
+    for (const auto &op : ops->ops) {
+        if (op.name == "Identity") continue;
+        if (find_gate(op.name) != nullptr)
+            gates.push_back(lower_named(n_local, op.name, op.wires, op.params, op.inverse));
+        else
+            gates.push_back(lower_matrix(n_local, op.matrix.data(), {}, op.wires, op.inverse));
+    }
+}
+extern "C" int regs_emu_split_exchange(const void *ops1_handle, const void *ops2_handle, int n_local, int local_bit,
+                                       int stash_bit, const double *shard0, const double *shard1, double *out0, double *out1,
+                                       int *mode) {
+    try {
+        std::vector<LoweredGate> g1, g2;
+        lower_all(reinterpret_cast<const qsv_ops *>(ops1_handle), n_local, g1);
+        lower_all(reinterpret_cast<const qsv_ops *>(ops2_handle), n_local, g2);
+        const int L = 4;
+        const uint64_t N = 1ull << n_local;
+        const uint64_t bit_mask = 1ull << local_bit, stash_mask = 1ull << stash_bit;
+        std::vector<double2> X[2] = {std::vector<double2>(N), std::vector<double2>(N)};
+        std::vector<double2> Y[2] = {std::vector<double2>(N), std::vector<double2>(N)};
+        for (uint64_t i = 0; i < N; ++i) {
+            X[0][i] = make_double2(shard0[2 * i], shard0[2 * i + 1]);
+            X[1][i] = make_double2(shard1[2 * i], shard1[2 * i + 1]);
+        }
+        static RegProgram P;
+        int m = 0;
+        // batch 1 on both ranks: X -> Y (own and partner's)
+        {
+            const std::vector<LoweredGate> merged = prepare_gates_regs(g1);
+            const std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, true, 48, 512);
+            for (int r = 0; r < 2; ++r) {
+                EmuXchg<double2> xc;
+                xc.out_mine = Y[r].data();
+                xc.out_peer = Y[1 - r].data();
+                xc.bit_mask = bit_mask;
+                xc.keep = r ? bit_mask : 0;
+                xc.stash_mask = stash_mask;
+                bool done = false;
+                std::vector<const LoweredGate *> cur;
+                for (size_t k = 0; k < plan.size(); ++k) {
+                    const SweepPlan &sw = plan[k];
+                    const bool carry = k + 1 == plan.size() && (sw.fused || regs_fusable(merged[sw.gates[0]], n_local));
+                    if (!sw.fused && !carry) {
+                        apply_lowered_host(X[r], n_local, merged[sw.gates[0]]);
+                        continue;
+                    }
+                    cur.clear();
+                    for (int i : sw.gates) cur.push_back(&merged[i]);
+                    build_reg_program(n_local, QSV_C128, 0, cur, sw.need, L, 4, P);
+                    emulate_program<double, 4>(X[r], n_local, P, carry ? xc : EmuXchg<double2>());
+                    done = done || carry;
+                }
+                if (!done)  // k_xchg_push_copy
+                    for (uint64_t i = 0; i < N; ++i) {
+                        const XchgTarget t = xchg_target(i, bit_mask, xc.keep, stash_mask);
+                        (t.stays ? xc.out_mine : xc.out_peer)[t.base] = X[r][i];
+                    }
+                if (done) m |= 1;
+            }
+        }
+        // batch 2: the first sweep (or the copy pass) reads Y of both ranks and writes X; the other sweeps run in place on X
+        {
+            const std::vector<LoweredGate> merged = prepare_gates_regs(g2);
+            const std::vector<SweepPlan> plan = plan_sweeps_regs(n_local, merged, L, true, 48, 512);
+            for (int r = 0; r < 2; ++r) {
+                EmuXchg<double2> xc;
+                xc.out_mine = X[r].data();
+                xc.out_peer = nullptr;
+                xc.in_peer = Y[1 - r].data();
+                xc.pull_bit_mask = bit_mask;
+                xc.pull_keep = r ? bit_mask : 0;
+                xc.pull_stash_mask = stash_mask;
+                const bool first_carries =
+                    !plan.empty() && (plan[0].fused || regs_fusable(merged[plan[0].gates[0]], n_local));
+                if (!first_carries)  // k_xchg_pull_copy
+                    for (uint64_t i = 0; i < N; ++i) {
+                        const XchgTarget t = xchg_source(i, bit_mask, xc.pull_keep, stash_mask);
+                        X[r][i] = t.stays ? Y[r][t.base] : Y[1 - r][t.base];
+                    }
+                else
+                    m |= 2;
+                std::vector<const LoweredGate *> cur;
+                for (size_t k = 0; k < plan.size(); ++k) {
+                    const SweepPlan &sw = plan[k];
+                    const bool pulls = first_carries && k == 0;
+                    if (!sw.fused && !pulls) {
+                        apply_lowered_host(X[r], n_local, merged[sw.gates[0]]);
+                        continue;
+                    }
+                    cur.clear();
+                    for (int i : sw.gates) cur.push_back(&merged[i]);
+                    build_reg_program(n_local, QSV_C128, 0, cur, sw.need, L, 4, P);
+                    if (pulls)
+                        emulate_program<double, 4>(Y[r], n_local, P, xc);  // reads Y (and the partner's), stores into X
+                    else
+                        emulate_program<double, 4>(X[r], n_local, P);
+                }
+            }
+        }
+        for (uint64_t i = 0; i < N; ++i) {
+            out0[2 * i] = X[0][i].x;
+            out0[2 * i + 1] = X[0][i].y;
+            out1[2 * i] = X[1][i].x;
+            out1[2 * i + 1] = X[1][i].y;
+        }
+        if (mode) *mode = m;
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "regs_emu_split_exchange: %s\n", e.what());
         return 1;
     }
 }

@@ -275,3 +275,47 @@ def test_sweep_fused_with_exchange(emu):
     # the last sweep carries the exchange wherever the exchanged bit sits (outside the tile, thread bit, register bit); the
     # copy pass is left for batches that end in a lone unfused gate
     assert 1 in modes and modes <= {0, 1}
+
+
+def test_split_exchange_push_then_pull(emu):
+    """QSV_DIST_SPLIT_XCHG (csrc/dist.cu, csrc/tile_regs.cu): an exchange split between the last sweep of the batch before it
+    (xchg_target with a stash bit: push a quarter of the shard, park a quarter) and the first sweep of the batch after it
+    (xchg_source: fetch what the partner parked), emulated for the two ranks of a register sharded on one global bit with the
+    kernel's own per-thread code and routing rules -- carried by sweeps and in the copy-pass forms.  Must equal: gates of
+    batch 1 on both shards, global bit <-> local bit exchanged, gates of batch 2."""
+    import ctypes as C
+
+    import pennylane_lightning_gpu_b200 as q
+
+    dp = C.POINTER(C.c_double)
+    emu.regs_emu_split_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    modes = set()
+    cases = [(13, 12, 4, 60, 50), (14, 13, 4, 40, 30), (14, 9, 4, 50, 1), (13, 4, 5, 30, 40), (14, 12, 4, 1, 25), (13, 7, 4, 0, 20),
+             (13, 11, 4, 20, 0)]
+    for n_local, local_bit, stash, n1, n2 in cases:
+        ops1 = random_mixed_circuit(n_local, n1, 170 + n_local + local_bit) if n1 else []
+        ops2 = random_mixed_circuit(n_local, n2, 270 + n_local + local_bit) if n2 else []
+        shards = [rand_state(n_local, 300 + r) / np.sqrt(2) for r in range(2)]
+        mid = [orc.apply_ops(s.copy(), ops1) for s in shards]
+        idx = np.arange(1 << n_local)
+        bit = (idx >> local_bit) & 1
+        swapped = [np.empty_like(mid[0]), np.empty_like(mid[0])]
+        for r in range(2):
+            for y in range(2):
+                src = idx[bit == y]                       # on rank r with the bit = y ...
+                dst = src ^ ((y ^ r) << local_bit)        # ... goes to rank y with the bit = r
+                swapped[y][dst] = mid[r][src]
+        expect = [orc.apply_ops(s, ops2) for s in swapped]
+        out = [np.zeros(2 << n_local), np.zeros(2 << n_local)]
+        mode = C.c_int(-1)
+        ins = [np.ascontiguousarray(s).view(np.float64) for s in shards]
+        rec1, rec2 = q.Ops(ops1), q.Ops(ops2)  # kept alive across the call
+        rc = emu.regs_emu_split_exchange(rec1._h, rec2._h, n_local, local_bit, stash, ins[0].ctypes.data_as(dp),
+                                         ins[1].ctypes.data_as(dp), out[0].ctypes.data_as(dp), out[1].ctypes.data_as(dp),
+                                         C.byref(mode))
+        assert rc == 0
+        for r in range(2):
+            got = out[r].view(np.complex128)
+            assert np.max(np.abs(got - expect[r])) < 1e-12, (n_local, local_bit, stash, n1, n2, r, mode.value)
+        modes.add(mode.value)
+    assert 3 in modes and (0 in modes or 1 in modes or 2 in modes)  # both halves carried by sweeps, and copy-pass forms
