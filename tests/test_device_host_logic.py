@@ -88,3 +88,71 @@ def test_capabilities_and_jacobian_processing(lg):
     assert isinstance(one_obs, tuple) and len(one_obs) == 3 and float(one_obs[1]) == 0.2
     many = proc(np.arange(6.0).reshape(2, 3))
     assert isinstance(many, tuple) and isinstance(many[0], tuple) and float(many[1][2]) == 5.0
+
+
+class _FakeState:
+    """Records what the device sends to the binary module (no GPU)."""
+
+    def __init__(self):
+        self.seeds, self.applied, self.jac_calls = [], [], []
+
+    def GenerateSamples(self, n, shots, seed=None):
+        self.seeds.append(seed)
+        return np.zeros((shots, n), dtype=np.uint64)
+
+    def apply(self, *a):
+        self.applied.append(a)
+
+    def RX(self, wires, inv, params):
+        self.applied.append(("RX", wires, inv, params))
+
+
+def test_seeded_sampling_draws_a_fresh_sub_seed_per_call(lg):
+    """ADVICE (round 1): with `seed` set every generate_samples() call used to re-seed with the same value, so shot noise was
+    identical across observables and executions.  Now one stream of sub-seeds per device, reproducible for a given seed."""
+    def device(seed):
+        dev = _bare_device(lg)
+        dev._gpu_state, dev._seed, dev.num_wires, dev.shots = _FakeState(), seed, 3, 10
+        return dev
+
+    a, b, c = device(7), device(7), device(8)
+    for d in (a, b, c):
+        for _ in range(4):
+            d.generate_samples()
+    assert len(set(a._gpu_state.seeds)) == 4                      # fresh uniforms on every call
+    assert a._gpu_state.seeds == b._gpu_state.seeds               # reproducible
+    assert a._gpu_state.seeds != c._gpu_state.seeds
+    unseeded = device(None)
+    unseeded.generate_samples()
+    assert unseeded._gpu_state.seeds == [None]                    # the binary draws from random_device
+
+
+def test_apply_sends_the_whole_tape_in_one_call(lg):
+    """apply_cq hands the list of operations to the binary in ONE call (vector form of `apply`, fused executor); a matrix
+    operation travels with its matrix; `fuse_ops=False` restores one call per operation; `inverse` is per operation."""
+    dev = _bare_device(lg)
+    dev._gpu_state, dev._fuse_ops = _FakeState(), True
+    u = np.eye(2, dtype=complex)
+    ops = [lg.Op("RX", [0], [0.1]), lg.Op("Identity", [1]), lg.Op("QubitUnitary", [1], matrix=u),
+           lg.Op("RX", [2], [0.3], inverse=True)]
+    dev.apply_cq(ops)
+    assert len(dev._gpu_state.applied) == 1
+    names, wires, invs, params, mats = dev._gpu_state.applied[0]
+    assert names == ["RX", "QubitUnitary", "RX"] and wires == [[0], [1], [2]] and invs == [False, False, True]
+    assert params == [[0.1], [], [0.3]] and len(mats[0]) == 0 and np.array_equal(np.asarray(mats[1]).reshape(2, 2), u)
+    dev._gpu_state, dev._fuse_ops = _FakeState(), False
+    dev.apply_cq(ops)
+    assert [a[0] for a in dev._gpu_state.applied] == ["RX", "QubitUnitary", "RX"]
+
+
+def test_vjp_zero_dy_counts_all_parameters(lg):
+    """ADVICE (round 1): dy == 0 with trainable_params=None returned zeros(0); now one zero per parameter of the tape (Rot
+    counts three), and the length check comes first."""
+    dev = _bare_device(lg)
+    ops = [lg.Op("RX", [0], [0.1]), lg.Op("Rot", [1], [0.1, 0.2, 0.3]), lg.Op("CNOT", [0, 1])]
+    out = dev.vjp(ops, [lg.Obs("PauliZ", [0])], [0.0])
+    assert out.shape == (4,) and not out.any()
+    with pytest.raises(ValueError, match="same as the length of dy"):
+        dev.vjp(ops, [lg.Obs("PauliZ", [0])], [0.0, 0.0])
+    with pytest.raises(ValueError, match="inverse of Rot"):
+        lg.LightningGPU._check_adjdiff_supported_operations([lg.Op("Rot", [0], [0.1, 0.2, 0.3], inverse=True)])
