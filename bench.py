@@ -357,7 +357,7 @@ def run_ours(args):
             n_oop, n_carried = sv.fused_exchange_stats()
         except Exception:  # a reporting extra must not cost the bench line
             n_oop, n_carried = 0, 0
-        if n_oop:  # QSV_DIST_FUSED_SWAP=1: exchanges stored by the sweep before them (not part of the swap timing above)
+        if n_oop:  # exchanges carried by the sweeps around them (not part of the swap timing above)
             total_steps = args.steps + max(args.warmup, 3)
             detail["nvlink_swaps"]["out_of_place_exchanges_per_step"] = n_oop / total_steps
             detail["nvlink_swaps"]["carried_by_sweeps_per_step"] = n_carried / total_steps

@@ -235,7 +235,8 @@ int qsv_dist_total_swap_stats(qsv_state *local, int *n_swaps, uint64_t *bytes_se
 /* 1 when the exchanges run as direct NVLink load/store kernels on CUDA-IPC peer mappings (the default; NCCL
  * then only carries the handshakes), 0 when they fall back to staged NCCL send/recv (QSV_DIST_P2P=0) */
 int qsv_dist_uses_peer_access(const qsv_state *local);
-/* exchanges done through the second buffer (QSV_DIST_FUSED_SWAP=1: the sweep before an exchange stores out of place,
+/* exchanges done through the second buffer (default where it fits, QSV_DIST_FUSED_SWAP=0 switches it off: the sweep before an
+ * exchange stores out of place,
  * half of its tiles straight into the partner's buffer over NVLink) and how many of them a gate sweep carried; they are
  * not part of the swap statistics above, which time the in-place exchanges */
 int qsv_dist_fused_exchange_stats(const qsv_state *local, int *n_out_of_place, int *n_carried_by_sweeps);

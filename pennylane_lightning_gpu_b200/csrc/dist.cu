@@ -81,7 +81,7 @@ struct DistCtx {
     // (qsv_dist_set_lazy_map; the throughput setting of bench.py): the map persists between calls -- a swapped-in
     // qubit stays local until evicted -- and qsv_dist_d2h / qsv_dist_canonicalize become COLLECTIVE.
     bool lazy_map = false;
-    // exchanges fused into sweeps (QSV_DIST_FUSED_SWAP=1): a second shard-sized buffer, peer-mapped like the first;
+    // exchanges carried by sweeps (default; QSV_DIST_FUSED_SWAP=0 switches it off): a second shard-sized buffer, peer-mapped like the first;
     // a fused sweep reads the buffer the register lives in and writes this rank's and the partner's other buffer
     void *shadow = nullptr;
     PeerBuf shadow_pb;
@@ -470,34 +470,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Out-of-place form of the exchange for the double-buffer protocol (dist_apply_ops, QSV_DIST_FUSED_SWAP=1) when the last
-// sweep of a batch cannot carry it: every 16-byte unit of `in` goes to the same offset of this rank's other buffer when
-// its exchanged bit equals this rank's value of the global bit, else to the partner's other buffer with the bit flipped.
-template <int U>
-__global__ void __launch_bounds__(256)
-    k_xchg_oop(const uint4 *__restrict__ in, uint4 *__restrict__ out_mine, uint4 *__restrict__ out_peer, uint64_t count,
-               uint64_t bit_mask, uint64_t keep) {
-    const uint64_t stride = (uint64_t)gridDim.x * 256 * U;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 * U + threadIdx.x; i0 < count; i0 += stride) {
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * 256;
-            if (i < count) v[u] = in[i];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * 256;
-            if (i < count) {
-                if ((i & bit_mask) == keep)
-                    out_mine[i] = v[u];
-                else
-                    out_peer[i ^ bit_mask] = v[u];
-            }
-        }
-    }
-}
-
+// (The out-of-place forms of an exchange -- carried by a sweep, or as copy passes -- live in tile_regs.cu:
+// k_tile_regs<..., XCHG = true>, launch_xchg_push_copy, launch_xchg_pull_copy.)
 void handshake(State &sv, int peer) {
     DistCtx &d = *sv.dist;
     QSV_NCCL(ncclGroupStart());

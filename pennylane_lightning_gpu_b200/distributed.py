@@ -92,7 +92,7 @@ class DistributedStateVector:
         return n.value, b.value, ms.value
 
     def fused_exchange_stats(self):
-        """(exchanges done through the second buffer, how many of them a gate sweep carried) -- QSV_DIST_FUSED_SWAP=1."""
+        """(exchanges done through the second buffer, how many of them a gate sweep carried); on by default, QSV_DIST_FUSED_SWAP=0 switches it off."""
         a, b = C.c_int(0), C.c_int(0)
         _check(lib().qsv_dist_fused_exchange_stats(self.local._h, C.byref(a), C.byref(b)))
         return a.value, b.value

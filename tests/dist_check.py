@@ -413,7 +413,7 @@ def config3_adjoint_sharded(rank, local_rank, world, g):
 
 
 def fused_exchange_check(rank, local_rank, world, g):
-    """QSV_DIST_FUSED_SWAP=1 (off by default): exchanges through the second buffer, carried by the sweep before them where
+    """Exchanges through the second buffer (the default where it fits; QSV_DIST_FUSED_SWAP=0 switches it off), carried by the sweep before them where
     the exchanged bit is not one of its tile bits.  20 local qubits so that sweeps can carry them; 13 so that the
     copy-pass form runs too; repeated application (odd and even numbers of exchanges, register back home each time)."""
     failures = []

@@ -31,7 +31,7 @@ def test_sharded_register_matches_oracle(world):
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_fused_exchange_matches_oracle(world):
-    """QSV_DIST_FUSED_SWAP=1 (off by default, written after the round-1 GPU budget was spent): exchanges through a second
+    """Exchanges carried by sweeps (the default since round 2; QSV_DIST_FUSED_SWAP=0 switches it off): exchanges through a second
     buffer, stored by the sweep before them straight into the partner's memory."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
