@@ -879,10 +879,13 @@ void dist_run_lowered(State &sv, const std::vector<LoweredGate> &lowered, bool f
         bool on = false;
         int peer = 0, bit = 0, val = 0, stash = 0;
     } pp;
-    static const int split_min_gates = [] {
-        const char *e = std::getenv("QSV_DIST_SPLIT_XCHG");  // 0: off; n > 0: split when >= n gates follow the exchange
-        return e ? std::atoi(e) : 24;
+    // QSV_DIST_SPLIT_XCHG: 0 = off; n > 0 = split when >= n gates follow the exchange.  Default: 24 on up to 4 GPUs, where the
+    // split has been run on hardware (2 and 4 B200s: one and two partners per rank); off beyond that until it has been.
+    static const int split_env = [] {
+        const char *e = std::getenv("QSV_DIST_SPLIT_XCHG");
+        return e ? std::atoi(e) : -1;
     }();
+    const int split_min_gates = split_env >= 0 ? split_env : (d.world <= 4 ? 24 : 0);
 
     std::vector<LoweredGate> batch;
     auto flush = [&](FusedExchange *fx) {
